@@ -1,0 +1,173 @@
+"""TEST INFRASTRUCTURE — mints tests/golden/*.npz by executing the REFERENCE'S OWN Python on CPU.
+
+Run in the build container only (needs /root/reference):   python -m oracle.make_golden
+The reference code path executed, unmodified, per case:
+  KeyFrame.build_lidar_rays (mapping/keyframe.py:71) -> LidarRayDirections.build_lidar_rays
+  (common/ray_utils.py:269) -> Optimizer.compute_loss (mapping/optimizer.py:437) -> Model.forward
+  (models/model_tcnn.py:70) -> render_rays (models/rendering_tcnn.py:192) ->
+  OccGridRaySampler.get_samples (models/ray_sampling.py:53) -> DecoupledNeRF.forward
+  (models/nerf_tcnn.py:59; tcnn replaced by oracle/tcnn_standin.py) -> raw2outputs ->
+  JS margin + 3 losses -> loss.backward() -> Optimizer._step_occupancy_grid (optimizer.py:598).
+Randomness (randint / rand / randn) is replayed from seeded CPU generators so that the same
+numbers can be regenerated from the seeds stored in the fixture (see `case_randoms`).
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, REPO)
+
+from loner_b200 import synth  # noqa: E402
+from oracle import ref_harness as rh  # noqa: E402
+from oracle import tcnn_standin  # noqa: E402
+
+GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
+
+CASES = {
+    # name: geometry, K keyframes, rays per KF, S, hidden layers, width, grid, precision, pose grads
+    "c1_2x64_fp32":   dict(geom="canteen", K=1, n=2048, S=128, L=2, W=64, grid="zeros", prec="fp32", poses=False, rows=64),
+    "c1_2x64_fp16":   dict(geom="canteen", K=1, n=2048, S=128, L=2, W=64, grid="zeros", prec="fp16", poses=False, rows=64),
+    "kf3_2x64_fp16":  dict(geom="garden", K=3, n=96, S=128, L=2, W=64, grid="trained", prec="fp16", poses=True, rows=288),
+    "kf2_4x256_fp16": dict(geom="canteen", K=2, n=128, S=256, L=4, W=256, grid="trained", prec="fp16", poses=True, rows=64),
+    "kf2_4x256_fp32": dict(geom="canteen", K=2, n=128, S=256, L=4, W=256, grid="trained", prec="fp32", poses=True, rows=64),
+    "quad_4x256_fp16": dict(geom="quad", K=2, n=128, S=512, L=4, W=256, grid="trained", prec="fp16", poses=True, rows=32),
+}
+N_BEAMS, N_AZ = 16, 256   # 4,096-point scans keep the fixtures' regeneration cheap
+
+
+def case_randoms(seed, n_per_kf, K, M, n_rays, S):
+    """The replayed random numbers, regenerable from `seed` alone (CPU torch generators)."""
+    g = torch.Generator().manual_seed(seed)
+    idx = [torch.randint(0, M, (n_per_kf,), generator=g) for _ in range(K)]
+    g2 = torch.Generator().manual_seed(seed + 1)
+    u1 = torch.rand(n_rays, S // 2, generator=g2)
+    u2 = torch.rand(n_rays, S // 2, generator=g2)
+    noise = torch.randn(n_rays, S, generator=g2)
+    return idx, u1, u2, noise
+
+
+def build_reference_optimizer(ns, geom, S, L, W, tmpdir):
+    s = rh.load_settings()
+    g = synth.GEOMETRY[geom]
+    opt_s = s["mapper"]["optimizer"]
+    mc = opt_s["model_config"]
+    mc["data"]["ray_range"] = list(g["ray_range"])
+    mc["model"]["ray_range"] = list(g["ray_range"])
+    mc["model"]["render"]["N_samples_train"] = S
+    nc = mc["model"]["nerf_config"]
+    nc["pos_encoding_sigma"] = {"otype": "Frequency", "n_frequencies": 10}
+    nc["sigma_network"] = {"otype": "CutlassMLP" if W > 128 else "FullyFusedMLP", "activation": "ReLU",
+                           "output_activation": "None", "n_neurons": W, "n_hidden_layers": L}
+    opt_s["debug"] = s["debug"]["flags"]
+    opt_s["log_directory"] = tmpdir
+    wc = ns.pose_utils.compute_world_cube(None, None, None, None, g["ray_range"], padding=0.3,
+                                          traj_bounding_box={k: list(v) for k, v in g["bbox"].items()})
+    opt = ns.optimizer.Optimizer(s.mapper.optimizer, s.calibration, wc, "cpu", False, True, False)
+    return opt, wc, s
+
+
+def run_case(name, c, seed=1234):
+    ns = rh.import_reference()
+    tcnn_standin.PRECISION["mode"] = c["prec"]
+    torch.manual_seed(0)
+    with tempfile.TemporaryDirectory() as tmp:
+        opt, wc, settings = build_reference_optimizer(ns, c["geom"], c["S"], c["L"], c["W"], tmp)
+        g = synth.GEOMETRY[c["geom"]]
+        scans, poses = synth.make_window(c["geom"], c["K"], seed=7, n_beams=N_BEAMS, n_azimuth=N_AZ)
+        M = scans[0].distances.shape[0]
+        # occupancy grid
+        if c["grid"] == "trained":
+            grid0 = synth.trained_occupancy_grid(c["geom"])
+            with torch.no_grad():
+                opt._occupancy_grid_model.occupancy_grid.copy_(grid0)
+            opt._occupancy_grid = opt._occupancy_grid_model()
+            opt._ray_sampler.update_occ_grid(opt._occupancy_grid.detach())
+        # the reference's own containers
+        kfs = []
+        for k in range(c["K"]):
+            sc = ns.sensors.LidarScan(scans[k].ray_directions.clone(), scans[k].distances.clone(),
+                                      scans[k].timestamps.clone())
+            fr = ns.frame.Frame(None, sc, None)
+            p6 = synth.axis_angle_from_yaw_pose(poses[k])
+            fr._lidar_pose = ns.pose.Pose(pose_tensor=p6.clone(), fixed=not (c["poses"] and k > 0))
+            fr._gt_lidar_pose = fr._lidar_pose
+            kfs.append(ns.keyframe.KeyFrame(fr, "cpu"))
+        ray_range = torch.Tensor(list(g["ray_range"]))
+        # pass 1 (no randomness needed): ray build, to learn the post-filter ray count
+        idx, _, _, _ = case_randoms(seed, c["n"], c["K"], M, 1, c["S"])
+        rays_l, dep_l = [], []
+        for kf, ix in zip(kfs, idx):
+            r, d = kf.build_lidar_rays(ix, ray_range, wc, False)
+            rays_l.append(r)
+            dep_l.append(d)
+        rays = torch.vstack(rays_l).float()
+        depths = torch.cat(dep_l).float()
+        n_rays = rays.shape[0]
+        idx, u1, u2, noise = case_randoms(seed, c["n"], c["K"], M, n_rays, c["S"])
+        replay = rh.Replay()
+        replay.rand = [u1, u2]
+        replay.randn = [noise]
+        opt._optimization_settings.freeze_poses = not c["poses"]
+        with rh.injected_randomness(replay):
+            loss = opt.compute_loss(None, (rays, depths), 0)
+        assert not replay.rand and not replay.randn, "reference drew fewer randoms than queued"
+        params = opt._model.nerf_model._model_sigma.params
+        loss.backward()
+        res = opt._results_lidar
+        grid_before = opt._occupancy_grid.detach().clone()
+        opt._step_occupancy_grid()
+        grid_after = opt._occupancy_grid.detach().clone()
+        dgrid = grid_after - grid_before
+        nz = dgrid.flatten().nonzero()[:, 0]
+
+        rows = min(c["rows"], n_rays)
+        out = dict(
+            meta=np.array([seed, c["K"], c["n"], c["S"], c["L"], c["W"], N_BEAMS, N_AZ, n_rays], dtype=np.int64),
+            geom=np.array(c["geom"]), grid=np.array(c["grid"]), prec=np.array(c["prec"]),
+            scale=np.float32(float(wc.scale_factor)), shift=wc.shift.numpy().astype(np.float32),
+            params_seed=np.int64(1337),
+            rays=rays.detach().numpy(), depths=depths.numpy(),
+            z_vals=res["samples_fine"][:rows].detach().numpy(),
+            weights=res["weights_fine"][:rows].detach().numpy(),
+            depth_fine=res["depth_fine"].detach().numpy(),
+            opacity_fine=res["opacity_fine"].detach().numpy(),
+            variance=res["variance"].detach().numpy(),
+            loss=np.float32(loss.item()),
+            depth_eps=np.float32(opt._depth_eps),
+            grad_params_norm=np.float32(params.grad.norm().item()),
+            grad_params=params.grad.numpy() if params.numel() <= 20000 else params.grad.numpy()[::16],
+            ogm_delta_idx=nz.numpy().astype(np.int64)[:4096],
+            ogm_delta_val=dgrid.flatten()[nz].numpy()[:4096],
+            ogm_delta_sum=np.float64(dgrid.double().sum().item()),
+            ogm_delta_abs=np.float64(dgrid.double().abs().sum().item()),
+        )
+        if params.numel() <= 20000:
+            out["params"] = params.detach().numpy()
+        if c["poses"]:
+            out["grad_poses"] = np.stack([kf.get_lidar_pose().get_pose_tensor().grad.numpy()
+                                          if kf.get_lidar_pose().get_pose_tensor().grad is not None
+                                          else np.zeros(6, np.float32) for kf in kfs])
+        # loss terms, recomputed by the same reference formulas from the stored results
+        return out
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    only = sys.argv[1:]
+    for name, c in CASES.items():
+        if only and name not in only:
+            continue
+        out = run_case(name, c)
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: n_rays={out['meta'][-1]} loss={out['loss']:.6f} depth_eps={out['depth_eps']:.4f} "
+              f"-> {os.path.getsize(path)/1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,70 @@
+"""Rebuilds the inputs of a golden case (tests/golden/*.npz, minted by oracle/make_golden.py from
+the reference's own code) from the seeds stored in the fixture, and runs the oracle on them."""
+import glob
+import os
+import sys
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+from loner_b200 import synth  # noqa: E402
+from oracle import loner_oracle as orc  # noqa: E402
+from oracle import tcnn_standin  # noqa: E402
+
+GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def case_randoms(seed, n_per_kf, K, M, n_rays, S):
+    """Same generator protocol as oracle/make_golden.py::case_randoms."""
+    g = torch.Generator().manual_seed(seed)
+    idx = [torch.randint(0, M, (n_per_kf,), generator=g) for _ in range(K)]
+    g2 = torch.Generator().manual_seed(seed + 1)
+    u1 = torch.rand(n_rays, S // 2, generator=g2)
+    u2 = torch.rand(n_rays, S // 2, generator=g2)
+    noise = torch.randn(n_rays, S, generator=g2)
+    return idx, u1, u2, noise
+
+
+class Case:
+    def __init__(self, name):
+        self.name = name
+        self.g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        seed, K, n, S, L, W, nb, naz, n_rays = [int(v) for v in self.g["meta"]]
+        self.seed, self.K, self.n, self.S, self.L, self.W, self.n_rays = seed, K, n, S, L, W, n_rays
+        self.geom = str(self.g["geom"])
+        self.prec = str(self.g["prec"])
+        self.scale = float(self.g["scale"])
+        self.shift = torch.from_numpy(self.g["shift"])
+        self.ray_range = synth.GEOMETRY[self.geom]["ray_range"]
+        self.scans, poses = synth.make_window(self.geom, K, seed=7, n_beams=nb, n_azimuth=naz)
+        self.poses6 = [synth.axis_angle_from_yaw_pose(poses[k]) for k in range(K)]
+        self.M = self.scans[0].distances.shape[0]
+        self.idx, self.u1, self.u2, self.noise = case_randoms(seed, n, K, self.M, n_rays, S)
+        self.spec = orc.NetSpec(n_frequencies=10, n_neurons=W, n_hidden_layers=L, precision=self.prec)
+        self.params = tcnn_standin.xavier_uniform_flat(self.spec.shapes, int(self.g["params_seed"]))
+        if str(self.g["grid"]) == "trained":
+            self.grid = synth.trained_occupancy_grid(self.geom)
+        else:
+            self.grid = torch.zeros(1, 1, 100, 100, 100)
+        self.pose_grads = "grad_poses" in self.g.files
+
+    def run_oracle(self):
+        params = self.params.clone().requires_grad_(True)
+        poses6 = [p.clone().requires_grad_(self.pose_grads and k > 0) for k, p in enumerate(self.poses6)]
+        rays, depths, res, out = orc.mapping_iteration(
+            self.scans, poses6, self.idx, params, self.spec, self.grid, self.S, self.scale, self.shift,
+            self.ray_range, 1.0, self.u1, self.u2, self.noise, orc.LossCfg())
+        out["loss"].backward()
+        s = res["samples_fine"].detach() * self.scale
+        G = depths.reshape(-1, 1) * self.scale
+        grid_after = orc.occupancy_step(self.grid, res["points_fine"], s, G, 1e-4)
+        return dict(rays=rays, depths=depths, res=res, out=out, params=params, poses6=poses6,
+                    grid_after=grid_after)
