@@ -1,0 +1,140 @@
+/* loner_b200 — C ABI of the B200-native LONER mapping hot path.
+ *
+ * The reference (umautobots/LONER) has no FFI: its seam is Python module attributes
+ * (SURVEY.md 8b).  This header is the boundary a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md); every entry point names the reference function it replaces.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless its name ends in _host; the library
+ * never allocates, never synchronises the device, keeps no global state, and launches on the
+ * `stream` (a cudaStream_t passed as void*) the caller gives.  Return value: 0 = ok, otherwise
+ * a LONER_E_* code (loner_error_string() names it).  All tensors are contiguous fp32 unless
+ * stated.  Ray rows follow the reference layout (common/ray_utils.py:313-315):
+ *   [0:3] origin, [3:6] unit direction, [6:9] view direction, [9:11] zero, [11] near, [12] far.
+ */
+#ifndef LONER_B200_H
+#define LONER_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  LONER_OK = 0,
+  LONER_E_BAD_ARG = 1,     /* null pointer / non-positive size / unsupported shape */
+  LONER_E_UNSUPPORTED = 2, /* configuration outside what the kernels implement      */
+  LONER_E_LAUNCH = 3,      /* cudaGetLastError() after launch was not cudaSuccess    */
+  LONER_E_ARCH = 4         /* device is not sm_100                                   */
+};
+
+#define LONER_RAY_COLS 13
+#define LONER_FLAG_VALID 1u   /* far > near + 1/scale           (ray_utils.py:321) */
+#define LONER_FLAG_OPAQUE 2u  /* depth > 0 and not depth > far  (optimizer.py:460-463) */
+
+int loner_version(void);
+int loner_sm_arch(void); /* compute capability of the current device *10 + minor, e.g. 100 */
+const char* loner_error_string(int code);
+
+/* ---- a3/a4  LidarRayDirections.build_lidar_rays + get_far_val (common/ray_utils.py:269-322,
+ * :31-60).  points: keyframe store, one float4 (dx,dy,dz,dist[m]) per LiDAR return, all
+ * keyframes concatenated; ray_kf/ray_point: per output ray the keyframe id and the absolute
+ * index into `points`.  poses: [K,12] = 3x3 R row-major then t.  Rows are NOT compacted:
+ * flags[i] carries LONER_FLAG_VALID/OPAQUE and counters[0..1] += (#valid, #opaque). */
+int loner_ray_build(const void* points, const int32_t* ray_kf, const int64_t* ray_point, int64_t n,
+                    const float* poses, int32_t K, const float* shift3_host, float scale, float r0, float r1,
+                    float* rays, float* depths, uint8_t* flags, int32_t* counters, void* stream);
+
+/* backward of the above w.r.t. poses: d_rays [n,13] (columns 0..5 and 12 = far are read) ->
+ * d_poses [K,12] (accumulated with atomics; caller zeroes). */
+int loner_ray_build_bwd(const void* points, const int32_t* ray_kf, const int64_t* ray_point, int64_t n,
+                        const float* poses, int32_t K, const float* shift3_host, float scale, float r1,
+                        const float* d_rays, float* d_poses, void* stream);
+
+/* ---- a6  UniformRaySampler.get_samples (models/ray_sampling.py:22-43).  u: [n,S] uniforms in
+ * [0,1) or NULL (then Philox(seed) draws them).  z_vals [n,S], ascending. */
+int loner_sample_uniform(const float* rays, int64_t n, int32_t S, float perturb, const float* u,
+                         uint64_t seed, float* z_vals, void* stream);
+
+/* ---- a7/a8/a9  OccGridRaySampler.get_samples + OccupancyGridModel.interpolate + sample_pdf
+ * (models/ray_sampling.py:53-92, model_tcnn.py:124-131, rendering_tcnn.py:18-67).
+ * grid: [V,V,V] logits indexed [z][y][x]; u1,u2: [n,S/2] or NULL. */
+int loner_sample_ogm(const float* rays, int64_t n, int32_t S, float perturb, const float* grid, int32_t V,
+                     const float* u1, const float* u2, uint64_t seed, float* z_vals, void* stream);
+
+/* ---- a12  sigma head: Frequency encoding + bias-free ReLU MLP (models/nerf_tcnn.py:35-38,
+ * :59-78).  Network description. */
+typedef struct {
+  int32_t n_frequencies;   /* Frequency encoding, 3 input dims -> 6F features, padded to 16 with 1.0 */
+  int32_t n_neurons;       /* hidden width W: 128 or 256                                       */
+  int32_t n_hidden_layers; /* L >= 1 hidden layers                                             */
+  int32_t reserved;
+} loner_net_t;
+
+int64_t loner_mlp_param_count(const loner_net_t* net);       /* flat fp32 params, [out,in] row-major per layer */
+int64_t loner_mlp_packed_bytes(const loner_net_t* net);      /* fp16 tensor-core image of the params */
+int64_t loner_mlp_act_bytes(const loner_net_t* net, int64_t P);   /* activation stash for backward */
+int64_t loner_mlp_bwd_scratch_bytes(const loner_net_t* net, int64_t P); /* dZ stash + wgrad partial sums */
+
+/* fp32 master params -> fp16 swizzled tile image read by the tensor-core kernels */
+int loner_mlp_pack(const loner_net_t* net, const float* params, void* packed, void* stream);
+
+/* forward.  Either pos [P,3] in [-1,1] (DecoupledNeRF.forward API) or, when pos == NULL,
+ * rays [n,13] + z_vals [n,S] with P = n*S (points o + d*z are formed in registers, never stored).
+ * sigma [P] fp32.  acts: NULL (inference) or the activation stash consumed by loner_mlp_bwd. */
+int loner_mlp_fwd(const loner_net_t* net, const void* packed, const float* pos, const float* rays,
+                  const float* z_vals, int32_t S, int64_t P, float* sigma, void* acts, void* stream);
+
+/* backward.  d_sigma [P] -> d_params [param_count] (+=, caller zeroes) and, if d_pos != NULL,
+ * d_pos [P,3] (gradient w.r.t. the [-1,1] positions).  grad_scale: power-of-two loss scale
+ * applied to the fp16 intermediate gradients (undone before d_params / d_pos are written). */
+int loner_mlp_bwd(const loner_net_t* net, const void* packed, const float* pos, const float* rays,
+                  const float* z_vals, int32_t S, int64_t P, const float* d_sigma, const void* acts,
+                  float grad_scale, float* d_params, float* d_pos, void* scratch, void* stream);
+
+/* ---- a13  raw2outputs (models/rendering_tcnn.py:93-145), sigma-only, far appended, variance.
+ * noise: [n,S] standard normals or NULL (then Philox(seed) * raw_noise_std). */
+int loner_render_fwd(const float* sigma, const float* z_vals, const float* rays, int64_t n, int32_t S,
+                     const float* noise, float raw_noise_std, uint64_t seed, float* weights,
+                     float* depth, float* opacity, float* variance, void* stream);
+
+/* generic backward of raw2outputs: upstream grads (any may be NULL) -> d_sigma [n,S] and
+ * d_rays [n,13] (columns 3..5 through |d|; += ). */
+int loner_render_bwd(const float* sigma, const float* z_vals, const float* rays, int64_t n, int32_t S,
+                     const float* noise, float raw_noise_std, uint64_t seed, const float* g_weights,
+                     const float* g_depth, const float* g_opacity, const float* g_variance,
+                     float* d_sigma, float* d_rays, void* stream);
+
+/* ---- a13+a15+a16+a17  fused raw2outputs + JS dynamic margin + L1_JS loss, forward AND
+ * backward in one pass (mapping/optimizer.py:437-595, models/losses.py:29-51).
+ * counts: device int32[2] = global (#valid rays, #opaque rays) — the loss normalisers.
+ * loss_cfg: {scale_factor, min_depth_eps, min_js, max_js, alpha, los_lambda, depthloss_lambda}.
+ * loss_acc: device float[4] += {sum sq depth err, sum |w-w_gt|, sum |opacity-1|, sum eps_dyn}.
+ * Outputs weights/depth/opacity/variance/eps_dyn may be NULL.  d_sigma [n,S]; d_rays [n,13] +=
+ * (columns 3..5 through |d| and column 12 through far; the path through the network input is
+ * loner_mlp_bwd's d_pos). */
+int loner_render_loss(const float* sigma, const float* z_vals, const float* rays, const float* depths,
+                      const uint8_t* flags, int64_t n, int32_t S, const float* noise, float raw_noise_std,
+                      uint64_t seed, const int32_t* counts, const float* loss_cfg7_host, float* loss_acc,
+                      float* weights, float* depth, float* opacity, float* variance, float* eps_dyn,
+                      float* d_sigma, float* d_rays, void* stream);
+
+/* d_pos [n,S,3] -> d_rays [n,13] += (origin: sum_s d_pos; direction: sum_s z*d_pos). */
+int loner_points_bwd(const float* d_pos, const float* z_vals, int64_t n, int32_t S, float* d_rays,
+                     void* stream);
+
+/* ---- a18  torch.optim.Adam step on the flat fp32 params (mapping/optimizer.py:257-267,:376)
+ * fused with the fp16 repack.  step >= 1. */
+int loner_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
+                    int32_t step, float lr, float beta1, float beta2, float eps, float grad_unscale,
+                    void* stream);
+
+/* ---- a19  Optimizer._step_occupancy_grid + get_logits_grad (mapping/optimizer.py:598-609,
+ * models/losses.py:54-62): scatter the pseudo-gradient trilinearly into d_grid [V,V,V]
+ * (caller zeroes), then loner_sgd_step applies grid -= lr * d_grid. */
+int loner_ogm_grad(const float* rays, const float* z_vals, const float* depths, int64_t n, int32_t S,
+                   float scale, int32_t V, float* d_grid, void* stream);
+int loner_sgd_step(float* x, const float* g, int64_t count, float lr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,121 @@
+// Optimiser steps and the occupancy-grid update.
+// Replaces torch.optim.Adam as constructed at /root/reference/src/mapping/optimizer.py:257-267
+// (step at :376), torch.optim.SGD for the occupancy grid (:108-109, :606) and the grid half of
+// Optimizer._step_occupancy_grid + get_logits_grad (/root/reference/src/mapping/optimizer.py:598-609,
+// /root/reference/src/models/losses.py:54-62): the pseudo-gradient is scattered trilinearly
+// (the adjoint of ATen grid_sampler_3d, align_corners=False, zeros padding) straight from
+// rays + z_vals, so `points_fine` [N,S,3] never has to exist in HBM.
+#include "common.cuh"
+
+namespace loner {
+
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            int64_t n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float unscale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * unscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;       // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;     // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+    p[i] = p[i] - (lr / bc1) * (mi / denom);            // param.addcdiv_(exp_avg, denom, value=-step_size)
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sgd_kernel(float* __restrict__ x, const float* __restrict__ g, int64_t n, float lr) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = x[i] - lr * g[i];
+}
+
+__global__ void __launch_bounds__(256)
+ogm_grad_kernel(const float* __restrict__ rays, const float* __restrict__ z_vals, const float* __restrict__ depths,
+                int64_t n, int S, float scale, int V, float* __restrict__ d_grid) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * S) return;
+  const int64_t ray = i / S;
+  const float* R = rays + ray * LONER_RAY_COLS;
+  const float z = z_vals[i];
+  // get_logits_grad: x = s - gt in metres; +0.25 for x < -2, -2.5 for -2 < x < 2   (losses.py:54-62)
+  const float x = __fmul_rn(z, scale) - __fmul_rn(depths[ray], scale);
+  float g = 0.f;
+  if (-x - 2.f > 0.f) g = 0.25f;
+  else if (x + 2.f > 0.f && 2.f - x > 0.f) g = -2.5f;
+  if (g == 0.f) return;
+  const float px = __fadd_rn(R[0], __fmul_rn(R[3], z)), py = __fadd_rn(R[1], __fmul_rn(R[4], z)),
+              pz = __fadd_rn(R[2], __fmul_rn(R[5], z));
+  const float fV = (float)V;
+  const float ix = (__fmul_rn(__fadd_rn(px, 1.f), fV) - 1.f) * 0.5f;
+  const float iy = (__fmul_rn(__fadd_rn(py, 1.f), fV) - 1.f) * 0.5f;
+  const float iz = (__fmul_rn(__fadd_rn(pz, 1.f), fV) - 1.f) * 0.5f;
+  const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+  const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+  const float wx1 = ix - fx, wy1 = iy - fy, wz1 = iz - fz;
+  const float wx0 = (fx + 1.f) - ix, wy0 = (fy + 1.f) - iy, wz0 = (fz + 1.f) - iz;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int xi = x0 + (c & 1), yi = y0 + ((c >> 1) & 1), zi = z0 + (c >> 2);
+    const float w = ((c & 1) ? wx1 : wx0) * (((c >> 1) & 1) ? wy1 : wy0) * ((c >> 2) ? wz1 : wz0);
+    if ((unsigned)xi < (unsigned)V && (unsigned)yi < (unsigned)V && (unsigned)zi < (unsigned)V)
+      atomicAdd(d_grid + ((int64_t)zi * V + yi) * V + xi, g * w);
+  }
+}
+
+}  // namespace loner
+
+extern "C" int loner_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
+                               int32_t step, float lr, float beta1, float beta2, float eps, float grad_unscale,
+                               void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || count < 0 || step < 1) return LONER_E_BAD_ARG;
+  if (count == 0) return LONER_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  unsigned blocks = (unsigned)((count + 255) / 256);
+  if (blocks > 1184) blocks = 1184;
+  loner::adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, count, lr, beta1,
+                                                              beta2, eps, (float)bc1, (float)sqrt(bc2), grad_unscale);
+  LONER_CHECK_LAUNCH();
+  return LONER_OK;
+}
+
+extern "C" int loner_sgd_step(float* x, const float* g, int64_t count, float lr, void* stream) {
+  if (!x || !g || count < 0) return LONER_E_BAD_ARG;
+  if (count == 0) return LONER_OK;
+  unsigned blocks = (unsigned)((count + 255) / 256);
+  if (blocks > 2368) blocks = 2368;
+  loner::sgd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, g, count, lr);
+  LONER_CHECK_LAUNCH();
+  return LONER_OK;
+}
+
+extern "C" int loner_ogm_grad(const float* rays, const float* z_vals, const float* depths, int64_t n, int32_t S,
+                              float scale, int32_t V, float* d_grid, void* stream) {
+  if (!rays || !z_vals || !depths || !d_grid || n < 0 || S <= 0 || V <= 0) return LONER_E_BAD_ARG;
+  if (n == 0) return LONER_OK;
+  const int64_t total = n * S;
+  loner::ogm_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rays, z_vals, depths, n, S,
+                                                                                            scale, V, d_grid);
+  LONER_CHECK_LAUNCH();
+  return LONER_OK;
+}
+
+extern "C" int loner_version(void) { return 100; }
+
+extern "C" int loner_sm_arch(void) {
+  int dev = 0, major = 0, minor = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  return major * 10 + minor;
+}
+
+extern "C" const char* loner_error_string(int code) {
+  switch (code) {
+    case LONER_OK: return "ok";
+    case LONER_E_BAD_ARG: return "bad argument (null pointer, negative size)";
+    case LONER_E_UNSUPPORTED: return "configuration not supported by the sm_100a kernels";
+    case LONER_E_LAUNCH: return "CUDA launch failure";
+    case LONER_E_ARCH: return "device is not sm_100";
+    default: return "unknown error";
+  }
+}

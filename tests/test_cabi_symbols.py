@@ -1,0 +1,35 @@
+"""CPU-only: the C-ABI library builds/loads and exports every symbol include/loner_b200.h declares."""
+import ctypes
+import os
+import re
+
+from loner_b200 import build, lib
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(REPO, "include", "loner_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(loner_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    build.build()
+    so = ctypes.CDLL(lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(so, n), f"{n} declared in include/loner_b200.h but not exported"
+    assert set(lib.exported_symbols()) == set(names)
+
+
+def test_no_compute_entry_points_need_a_gpu_to_query_sizes():
+    l = lib.load()
+    assert l.loner_version() == 100
+    net = lib.NetT(10, 256, 4, 0)
+    assert l.loner_mlp_param_count(ctypes.byref(net)) == 217088
+    assert l.loner_mlp_packed_bytes(ctypes.byref(net)) == 64 * 256 * 2 + 3 * 256 * 256 * 2 + 256 * 4
+    bad = lib.NetT(10, 64, 1, 0)
+    assert l.loner_mlp_param_count(ctypes.byref(bad)) == -1
+    assert l.loner_error_string(2).decode().startswith("configuration not supported")
