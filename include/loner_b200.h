@@ -90,6 +90,14 @@ int loner_mlp_bwd(const loner_net_t* net, const void* packed, const float* pos, 
                   const float* z_vals, int32_t S, int64_t P, const float* d_sigma, const void* acts,
                   float grad_scale, float* d_params, float* d_pos, void* scratch, void* stream);
 
+/* the two halves of loner_mlp_bwd, separately launchable (dgrad must run first: it writes the
+ * loss-scaled fp16 layer gradients into `scratch` that wgrad contracts with the stashed activations) */
+int loner_mlp_dgrad(const loner_net_t* net, const void* packed, const float* pos, const float* rays,
+                    const float* z_vals, int32_t S, int64_t P, const float* d_sigma, const void* acts,
+                    float grad_scale, float* d_pos, void* scratch, void* stream);
+int loner_mlp_wgrad(const loner_net_t* net, const void* packed, int64_t P, const float* d_sigma,
+                    const void* acts, float grad_scale, float* d_params, void* scratch, void* stream);
+
 /* ---- a13  raw2outputs (models/rendering_tcnn.py:93-145), sigma-only, far appended, variance.
  * noise: [n,S] standard normals or NULL (then Philox(seed) * raw_noise_std). */
 int loner_render_fwd(const float* sigma, const float* z_vals, const float* rays, int64_t n, int32_t S,

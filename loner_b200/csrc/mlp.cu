@@ -782,29 +782,44 @@ extern "C" int loner_mlp_fwd(const loner_net_t* n, const void* packed, const flo
   return LONER_OK;
 }
 
-extern "C" int loner_mlp_bwd(const loner_net_t* n, const void* packed, const float* pos, const float* rays,
-                             const float* z_vals, int32_t S, int64_t P, const float* d_sigma, const void* acts,
-                             float grad_scale, float* d_params, float* d_pos, void* scratch, void* stream) {
-  Net net;
+static int bwd_common(const loner_net_t* n, Net& net, const void* packed, const void* acts, void* scratch, int64_t P) {
   if (!net_from(n, net)) return LONER_E_UNSUPPORTED;
-  if (!packed || !d_sigma || !acts || !d_params || !scratch || P < 0 || !(grad_scale > 0.f) ||
-      (d_pos && !pos && (!rays || !z_vals || S <= 0)))
-    return LONER_E_BAD_ARG;
+  if (!packed || !acts || !scratch || P < 0) return LONER_E_BAD_ARG;
+  return LONER_OK;
+}
+
+extern "C" int loner_mlp_dgrad(const loner_net_t* n, const void* packed, const float* pos, const float* rays,
+                               const float* z_vals, int32_t S, int64_t P, const float* d_sigma, const void* acts,
+                               float grad_scale, float* d_pos, void* scratch, void* stream) {
+  Net net;
+  int rc = bwd_common(n, net, packed, acts, scratch, P);
+  if (rc) return rc;
+  if (!d_sigma || !(grad_scale > 0.f) || (d_pos && !pos && (!rays || !z_vals || S <= 0))) return LONER_E_BAD_ARG;
+  if (P == 0) return LONER_OK;
+  const int64_t tiles = n_tiles(P);
+  const int sms = device_sm_count();
+  BwdArgs b;
+  b.net = net; b.packed = (const uint8_t*)packed; b.pos = pos; b.rays = rays; b.z = z_vals; b.S = S; b.P = P;
+  b.tiles = tiles; b.d_sigma = d_sigma; b.masks = (const uint8_t*)acts + tiles * act_tile_bytes(net);
+  b.dz = (uint8_t*)scratch; b.gscale = grad_scale; b.d_pos = d_pos;
+  cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+  mlp_dgrad_kernel<<<(unsigned)(tiles < sms ? tiles : sms), kBwdThreads, kBwdSmem, (cudaStream_t)stream>>>(b);
+  LONER_CHECK_LAUNCH();
+  return LONER_OK;
+}
+
+extern "C" int loner_mlp_wgrad(const loner_net_t* n, const void* packed, int64_t P, const float* d_sigma,
+                               const void* acts, float grad_scale, float* d_params, void* scratch, void* stream) {
+  Net net;
+  int rc = bwd_common(n, net, packed, acts, scratch, P);
+  if (rc) return rc;
+  if (!d_sigma || !d_params || !(grad_scale > 0.f)) return LONER_E_BAD_ARG;
   if (P == 0) return LONER_OK;
   const int64_t tiles = n_tiles(P);
   const int sms = device_sm_count();
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* dz = (uint8_t*)scratch;
   float* partials = (float*)(dz + tiles * dz_tile_bytes(net));
-
-  BwdArgs b;
-  b.net = net; b.packed = (const uint8_t*)packed; b.pos = pos; b.rays = rays; b.z = z_vals; b.S = S; b.P = P;
-  b.tiles = tiles; b.d_sigma = d_sigma; b.masks = (const uint8_t*)acts + tiles * act_tile_bytes(net);
-  b.dz = dz; b.gscale = grad_scale; b.d_pos = d_pos;
-  cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
-  mlp_dgrad_kernel<<<(unsigned)(tiles < sms ? tiles : sms), kBwdThreads, kBwdSmem, st>>>(b);
-  LONER_CHECK_LAUNCH();
-
   const WgradPlan plan = plan_wgrad(net);
   WgradArgs w;
   w.net = net; w.acts = (const uint8_t*)acts; w.dz = dz; w.tiles = tiles; w.partials = partials;
@@ -818,4 +833,12 @@ extern "C" int loner_mlp_bwd(const loner_net_t* n, const void* packed, const flo
   dwout_kernel<<<(unsigned)(sms * 2), 256, 0, st>>>(net, (const uint8_t*)acts, d_sigma, P, tiles, d_params);
   LONER_CHECK_LAUNCH();
   return LONER_OK;
+}
+
+extern "C" int loner_mlp_bwd(const loner_net_t* n, const void* packed, const float* pos, const float* rays,
+                             const float* z_vals, int32_t S, int64_t P, const float* d_sigma, const void* acts,
+                             float grad_scale, float* d_params, float* d_pos, void* scratch, void* stream) {
+  int rc = loner_mlp_dgrad(n, packed, pos, rays, z_vals, S, P, d_sigma, acts, grad_scale, d_pos, scratch, stream);
+  if (rc) return rc;
+  return loner_mlp_wgrad(n, packed, P, d_sigma, acts, grad_scale, d_params, scratch, stream);
 }

@@ -104,18 +104,24 @@ sample_ogm_kernel(const float* __restrict__ rays, int64_t n, int S, int H, int H
   // (2) cdf[0]=0, cdf[k]=sum_{i<k} pdf_i, k=1..H-2  (H-1 entries)   rendering_tcnn.py:34-38
   const int nb = H - 2;
   {
+    // torch.cumsum on the reference's CPU path accumulates fp32 rows in double (ATen acc_type) and
+    // rounds each prefix to fp32; do the same: low-probability bins have increments near the fp32
+    // rounding of the running sum, and the inverse CDF divides by them.
     const int chunk = (nb + 31) / 32;
     const int b = lane * chunk, e = min(b + chunk, nb);
-    float local = 0.f;
-    for (int k = b; k < e; ++k) local += cdf[k + 1] / wsum;
-    const float incl = warp_incl_scan_sum(local, lane);
-    float run = incl - local;
+    double local = 0.0;
+    for (int k = b; k < e; ++k) local += (double)__fdiv_rn(cdf[k + 1], wsum);
+    double incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += t;
+    }
+    double run = incl - local;
     __syncwarp();
-    float vals_prev = run;
     for (int k = b; k < e; ++k) {
-      const float pdf = cdf[k + 1] / wsum;
-      vals_prev += pdf;
-      cdf[k + 1] = vals_prev;        // cdf index k+1 = inclusive sum through weight k
+      run += (double)__fdiv_rn(cdf[k + 1], wsum);
+      cdf[k + 1] = (float)run;       // cdf index k+1 = inclusive sum through weight k
     }
     if (lane == 0) cdf[0] = 0.f;
   }

@@ -1,0 +1,327 @@
+"""Device-resident mapping step: the hot loop of Optimizer._do_iterate_optimizer
+(/root/reference/src/mapping/optimizer.py:276-384) as a fixed sequence of hand-written kernels.
+
+Per iteration (all on the current CUDA stream, no host synchronisation):
+  ray pick (torch.randint on device, optimizer.py:288)  ->  loner_ray_build (keyframe.py:71,
+  ray_utils.py:269)  ->  loner_sample_ogm / loner_sample_uniform (ray_sampling.py)  ->
+  loner_mlp_fwd (nerf_tcnn.py:59)  ->  loner_render_loss (rendering_tcnn.py:71 + optimizer.py:437,
+  forward AND backward)  ->  loner_mlp_bwd  ->  [pose gradients: loner_points_bwd,
+  loner_ray_build_bwd, Rodrigues by autograd]  ->  [NCCL all-reduce of the flat gradient]  ->
+  loner_adam_step + loner_mlp_pack  ->  every N_iters_acc steps loner_ogm_grad + loner_sgd_step
+  (optimizer.py:382-384, :598-609).
+
+Multi-GPU: one process per GPU, every rank holds all keyframes, draws its own
+rays, and the ranks exchange (a) the two loss normalisers before the loss kernel and (b) one flat
+gradient buffer after backward; parameters and optimiser state stay replicated.
+"""
+import contextlib
+import math
+from dataclasses import dataclass, field
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def axis_angle_to_matrix(aa: torch.Tensor) -> torch.Tensor:
+    """[...,3] -> [...,3,3] via the unit quaternion, as pytorch3d.transforms does for the reference
+    (common/pose_utils.py:294); stays in PyTorch so pose 6-vectors remain autograd leaves."""
+    angles = torch.norm(aa, p=2, dim=-1, keepdim=True)
+    half = 0.5 * angles
+    small = angles.abs() < 1e-6
+    safe = torch.where(small, torch.ones_like(angles), angles)
+    s_over_a = torch.where(small, 0.5 - (angles * angles) / 48, torch.sin(half) / safe)
+    q = torch.cat([torch.cos(half), aa * s_over_a], dim=-1)
+    r, i, j, k = torch.unbind(q, -1)
+    two_s = 2.0 / (q * q).sum(-1)
+    o = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+    return o.reshape(q.shape[:-1] + (3, 3))
+
+
+def poses6_to_poses12(poses6: torch.Tensor) -> torch.Tensor:
+    """[K,6] = [t, axis-angle] -> [K,12] = R row-major | t  (common/pose_utils.py:288-302)."""
+    R = axis_angle_to_matrix(poses6[:, 3:])
+    return torch.cat([R.reshape(-1, 9), poses6[:, :3]], dim=1)
+
+
+@dataclass
+class EngineConfig:
+    # geometry (WorldCube + ray_range of the sequence file)
+    scale: float
+    shift: tuple
+    ray_range: tuple
+    # network (nerf_config: pos_encoding_sigma / sigma_network keys)
+    n_frequencies: int = 10
+    n_neurons: int = 256
+    n_hidden_layers: int = 4
+    # render (default_model_config.yaml:11-20)
+    n_samples: int = 512
+    perturb: float = 1.0
+    raw_noise_std: float = 1.0
+    sampler: str = "OGM"
+    # occupancy grid (default_model_config.yaml:22-25)
+    voxel_size: int = 100
+    occ_lr: float = 1e-4
+    occ_every: int = 10
+    # loss (default_model_config.yaml:40-58)
+    min_depth_eps: float = 0.5
+    min_js: float = 1.0
+    max_js: float = 10.0
+    js_alpha: float = 1.0
+    los_lambda: float = 1000.0
+    depthloss_lambda: float = 0.005
+    # train (default_model_config.yaml:27-31)
+    lrate_sigma_mlp: float = 0.01
+    lrate_pose: float = 0.001
+    # engine
+    chunk_rays: int = 8192
+    seed: int = 0
+
+    def loss_cfg7(self):
+        return [self.scale, self.min_depth_eps, self.min_js, self.max_js, self.js_alpha, self.los_lambda,
+                self.depthloss_lambda]
+
+
+class MappingEngine:
+    def __init__(self, cfg: EngineConfig, device="cuda", params: torch.Tensor = None):
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        self.net = ops.Net(cfg.n_frequencies, cfg.n_neurons, cfg.n_hidden_layers)
+        if params is None:
+            params = xavier_uniform_flat(self.net.layer_shapes(), 1337)
+        assert params.numel() == self.net.param_count
+        self.params = params.detach().to(self.dev, torch.float32).contiguous().clone()
+        self.packed = torch.empty(self.net.packed_bytes, device=self.dev, dtype=torch.uint8)
+        ops.mlp_pack(self.net, self.params, self.packed)
+        self.exp_avg = torch.zeros_like(self.params)
+        self.exp_avg_sq = torch.zeros_like(self.params)
+        self.adam_t = 0
+        self.d_params = torch.zeros_like(self.params)
+        V = cfg.voxel_size
+        self.grid = torch.zeros(V, V, V, device=self.dev, dtype=torch.float32)
+        self.d_grid = torch.zeros_like(self.grid)
+        self.global_step = 0
+        # keyframe store
+        self.points = None
+        self.kf_offsets = []
+        self.kf_sizes = []
+        self.poses6 = []            # list of [6] leaf tensors on device
+        self.pose_opt = None
+        self.gen = torch.Generator(device=self.dev)
+        self.gen.manual_seed(cfg.seed)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self._bufs = {}
+        self.launches = 0           # kernels of OURS launched (bench reports it)
+        self.last = {}
+        self.timers = None          # name -> [(start_event, end_event)] when bench.py profiles sections
+
+    # ---------------------------------------------------------------- keyframes
+    def add_keyframe(self, ray_directions, distances, pose6):
+        pts = ops.pack_points(ray_directions, distances).to(self.dev)
+        off = 0 if self.points is None else self.points.shape[0]
+        self.points = pts if self.points is None else torch.cat([self.points, pts])
+        self.kf_offsets.append(off)
+        self.kf_sizes.append(pts.shape[0])
+        self.poses6.append(pose6.detach().to(self.dev, torch.float32).clone())
+        return len(self.poses6) - 1
+
+    def new_phase(self, optimize_poses: bool):
+        """A new Adam per optimisation phase, as the reference does (optimizer.py:257-267)."""
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.adam_t = 0
+        self.pose_opt = None
+        for k, p in enumerate(self.poses6):
+            p.requires_grad_(bool(optimize_poses and k > 0))     # keyframe 0 is anchored
+        if optimize_poses:
+            leaves = [p for p in self.poses6 if p.requires_grad]
+            if leaves:
+                self.pose_opt = torch.optim.Adam([{"params": leaves, "lr": self.cfg.lrate_pose}])
+
+    # ---------------------------------------------------------------- helpers
+    @contextlib.contextmanager
+    def _sec(self, name):
+        """CUDA-event bracket around one kernel family on the launching stream (bench.py roofline)."""
+        if self.timers is None:
+            yield
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        self.timers.setdefault(name, []).append((a, b))
+
+    def _buf(self, name, nbytes):
+        b = self._bufs.get(name)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(nbytes, device=self.dev, dtype=torch.uint8)
+            self._bufs[name] = b
+        return b
+
+    def _pick_rays(self, window, n_per_kf):
+        K = len(window)
+        sizes = torch.tensor([self.kf_sizes[k] for k in window], device=self.dev, dtype=torch.float32)
+        offs = torch.tensor([self.kf_offsets[k] for k in window], device=self.dev, dtype=torch.int64)
+        u = torch.rand(K, n_per_kf, device=self.dev, generator=self.gen)
+        idx = (u * sizes[:, None]).long().clamp_(max=int(max(self.kf_sizes)) - 1)
+        ray_point = (idx + offs[:, None]).reshape(-1).contiguous()
+        ray_kf = torch.arange(K, device=self.dev, dtype=torch.int32).repeat_interleave(n_per_kf).contiguous()
+        return ray_kf, ray_point
+
+    def _allreduce(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    # ---------------------------------------------------------------- the step
+    def step(self, window, n_per_kf, optimize_poses=False, injected=None, want_outputs=False):
+        """One mapping iteration over `window` (keyframe ids), n_per_kf rays per keyframe on THIS rank.
+        injected: optional dict(ray_point, u1, u2, noise) for parity tests.  Returns the loss (0-dim
+        device tensor, no host sync)."""
+        cfg = self.cfg
+        K = len(window)
+        if injected is not None and "ray_point" in injected:
+            ray_point = injected["ray_point"].to(self.dev)
+            ray_kf = torch.arange(K, device=self.dev, dtype=torch.int32).repeat_interleave(n_per_kf).contiguous()
+        else:
+            ray_kf, ray_point = self._pick_rays(window, n_per_kf)
+        poses6 = torch.stack([self.poses6[k] for k in window])
+        poses12 = poses6_to_poses12(poses6)
+        counters = torch.zeros(2, device=self.dev, dtype=torch.int32)
+        rays, depths, flags = ops.ray_build(self.points, ray_kf, ray_point, poses12.detach().contiguous(),
+                                            cfg.shift, cfg.scale, cfg.ray_range, counters)
+        self.launches += 1
+        self._allreduce(counters)
+        out = self._step_on_rays(rays, depths, flags, counters, optimize_poses, injected, want_outputs)
+        if optimize_poses and out["d_rays"] is not None:
+            d_poses12 = ops.ray_build_bwd(self.points, ray_kf, ray_point, poses12.detach().contiguous(), cfg.shift,
+                                          cfg.scale, cfg.ray_range, out["d_rays"])
+            self.launches += 1
+            self._allreduce(d_poses12)
+            for p in self.poses6:
+                p.grad = None
+            poses12.backward(d_poses12)
+            if self.pose_opt is not None:
+                self.pose_opt.step()
+        return out["loss"]
+
+    def step_from_host(self, rays_host, depths_host):
+        """The reference-facing call (Optimizer.compute_loss + backward + Adam, optimizer.py:340-380)
+        fed with HOST rays [N,13] and depths [N] (pinned), as the reference's data_prep_on_cpu path
+        does: H2D copy -> step -> loss read back."""
+        cfg = self.cfg
+        rays = rays_host.to(self.dev, non_blocking=True)
+        depths = depths_host.to(self.dev, non_blocking=True)
+        far, near = rays[:, 12], rays[:, 11]
+        valid = far > near + 1.0 / cfg.scale
+        opaque = valid & (depths > 0) & ~(depths > far)
+        flags = (valid.to(torch.uint8) + 2 * opaque.to(torch.uint8)).contiguous()
+        counters = torch.stack([valid.sum(), opaque.sum()]).to(torch.int32)
+        self._allreduce(counters)
+        out = self._step_on_rays(rays, depths, flags, counters, False, None, False)
+        return float(out["loss"].item())
+
+    def _step_on_rays(self, rays, depths, flags, counters, optimize_poses, injected, want_outputs):
+        cfg = self.cfg
+        N, S = rays.shape[0], cfg.n_samples
+        gscale = ops.default_grad_scale(N * self.world, S, cfg.los_lambda)
+        loss_acc = torch.zeros(4, device=self.dev, dtype=torch.float32)
+        self.d_params.zero_()
+        d_rays = torch.zeros(N, ops.RAY_COLS, device=self.dev, dtype=torch.float32) if optimize_poses else None
+        outs = []
+        seed = (cfg.seed * 1000003 + self.global_step * 7919 + 13) & 0x7FFFFFFFFFFF
+        z_all = [] if (self.global_step % cfg.occ_every == 0 and cfg.sampler == "OGM") else None
+        for c0 in range(0, N, cfg.chunk_rays):
+            c1 = min(N, c0 + cfg.chunk_rays)
+            r, dpt, fl = rays[c0:c1], depths[c0:c1], flags[c0:c1]
+            n = c1 - c0
+            P = n * S
+            inj = injected or {}
+            u1 = inj["u1"][c0:c1].contiguous().to(self.dev) if "u1" in inj else None
+            u2 = inj["u2"][c0:c1].contiguous().to(self.dev) if "u2" in inj else None
+            noise = inj["noise"][c0:c1].contiguous().to(self.dev) if "noise" in inj else None
+            with self._sec("sample"):
+                if cfg.sampler == "OGM":
+                    z = ops.sample_ogm(r, self.grid, S, cfg.perturb, u1, u2, seed=seed + c0)
+                else:
+                    z = ops.sample_uniform(r, S, cfg.perturb, u1, seed=seed + c0)
+            acts = self._buf("acts", self.net.act_bytes(P))
+            with self._sec("mlp_fwd"):
+                sigma, _ = ops.mlp_fwd(self.net, self.packed, P, rays=r, z=z, stash=True, acts=acts)
+            with self._sec("render_loss"):
+                res = ops.render_loss(sigma, z, r, dpt, fl, counters, cfg.loss_cfg7(), noise=noise,
+                                      raw_noise_std=cfg.raw_noise_std, seed=seed + c0 + 1, loss_acc=loss_acc,
+                                      want_outputs=want_outputs, d_rays=d_rays[c0:c1] if optimize_poses else None)
+            scratch = self._buf("scratch", self.net.bwd_scratch_bytes(P))
+            with self._sec("mlp_dgrad"):
+                d_pos = ops.mlp_dgrad(self.net, self.packed, P, res["d_sigma"], acts, gscale, scratch, rays=r, z=z,
+                                      want_dpos=optimize_poses)
+            with self._sec("mlp_wgrad"):
+                ops.mlp_wgrad(self.net, self.packed, P, res["d_sigma"], acts, gscale, self.d_params, scratch)
+            self.launches += 3 + 4
+            if optimize_poses:
+                ops.points_bwd(d_pos, z, d_rays[c0:c1])
+                self.launches += 1
+            if z_all is not None:
+                z_all.append(z)
+            if want_outputs:
+                res["z_vals"] = z
+                res["sigma"] = sigma
+                outs.append(res)
+        # gradient exchange: one flat buffer (MLP grads | 4 loss sums)
+        if self.world > 1:
+            flat = torch.cat([self.d_params, loss_acc])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            self.d_params.copy_(flat[:-4])
+            loss_acc = flat[-4:]
+        self.adam_t += 1
+        with self._sec("adam_pack"):
+            ops.adam_step(self.params, self.d_params, self.exp_avg, self.exp_avg_sq, self.adam_t, cfg.lrate_sigma_mlp)
+            ops.mlp_pack(self.net, self.params, self.packed)
+        self.launches += 2
+        # occupancy grid every occ_every global steps (optimizer.py:382-384)
+        if z_all is not None:
+            self.d_grid.zero_()
+            for ci, c0 in enumerate(range(0, N, cfg.chunk_rays)):
+                c1 = min(N, c0 + cfg.chunk_rays)
+                ops.ogm_grad(rays[c0:c1], z_all[ci], depths[c0:c1], cfg.scale, cfg.voxel_size, self.d_grid)
+                self.launches += 1
+            self._allreduce(self.d_grid)
+            ops.sgd_step(self.grid, self.d_grid, cfg.occ_lr)
+            self.launches += 1
+        self.global_step += 1
+        cnt = counters.to(torch.float32)
+        loss = (cfg.depthloss_lambda * loss_acc[0] / cnt[1] + cfg.los_lambda * loss_acc[1] / (cnt[0] * S)
+                + loss_acc[2] / cnt[1])
+        self.last = dict(loss_acc=loss_acc, counters=counters, depth_eps=loss_acc[3] / cnt[0], outs=outs,
+                         rays=rays, depths=depths, flags=flags)
+        return dict(loss=loss, d_rays=d_rays)
+
+    # ---------------------------------------------------------------- inference (test mode)
+    @torch.no_grad()
+    def render(self, rays, n_samples=None, seed=0):
+        """Model.forward(testing=True) (models/model_tcnn.py:70-105): perturb = 0; like the reference the
+        importance draws and raw_noise_std stay active."""
+        cfg = self.cfg
+        S = n_samples or cfg.n_samples
+        if cfg.sampler == "OGM":
+            z = ops.sample_ogm(rays, self.grid, S, 0.0, None, None, seed=seed)
+        else:
+            z = ops.sample_uniform(rays, S, 0.0, None, seed=seed)
+        sigma, _ = ops.mlp_fwd(self.net, self.packed, rays.shape[0] * S, rays=rays, z=z, stash=False)
+        w, d, o, v = ops.render_fwd(sigma, z, rays, noise=None, raw_noise_std=cfg.raw_noise_std, seed=seed + 1,
+                                    want_weights=False)
+        self.launches += 3
+        return dict(depth_fine=d, opacity_fine=o, variance=v, samples_fine=z)
+
+
+def xavier_uniform_flat(layer_shapes, seed):
+    """Flat fp32 params ([out,in] row-major per layer), xavier-uniform like tcnn's default init."""
+    g = torch.Generator().manual_seed(seed)
+    chunks = []
+    for (n_out, n_in) in layer_shapes:
+        bound = math.sqrt(6.0 / (n_in + n_out))
+        chunks.append(((torch.rand(n_out, n_in, generator=g) * 2 - 1) * bound).reshape(-1))
+    return torch.cat(chunks)

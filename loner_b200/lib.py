@@ -33,6 +33,8 @@ _SIGS = {
     "loner_mlp_pack": (_c.c_int, [_vp, _vp, _vp, _vp]),
     "loner_mlp_fwd": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "loner_mlp_bwd": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
+    "loner_mlp_dgrad": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _f32, _vp, _vp, _vp]),
+    "loner_mlp_wgrad": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _f32, _vp, _vp, _vp]),
     "loner_render_fwd": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _f32, _u64, _vp, _vp, _vp, _vp, _vp]),
     "loner_render_bwd": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _f32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "loner_render_loss": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _f32, _u64, _vp, _vp, _vp,

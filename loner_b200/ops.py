@@ -125,6 +125,21 @@ def mlp_bwd(net: Net, packed, P, d_sigma, acts, grad_scale, d_params, pos=None, 
     return d_pos
 
 
+def mlp_dgrad(net: Net, packed, P, d_sigma, acts, grad_scale, scratch, pos=None, rays=None, z=None, want_dpos=False):
+    d_pos = torch.empty(P, 3, device=packed.device, dtype=torch.float32) if want_dpos else None
+    S = z.shape[1] if z is not None else 1
+    L.check(L.load().loner_mlp_dgrad(net.ref(), L.ptr(packed), L.ptr(pos), L.ptr(rays), L.ptr(z), S, P,
+                                     L.ptr(_f32(d_sigma)), L.ptr(acts), float(grad_scale), L.ptr(d_pos),
+                                     L.ptr(scratch), L.stream_ptr()), "loner_mlp_dgrad")
+    return d_pos
+
+
+def mlp_wgrad(net: Net, packed, P, d_sigma, acts, grad_scale, d_params, scratch):
+    L.check(L.load().loner_mlp_wgrad(net.ref(), L.ptr(packed), P, L.ptr(_f32(d_sigma)), L.ptr(acts),
+                                     float(grad_scale), L.ptr(d_params), L.ptr(scratch), L.stream_ptr()),
+            "loner_mlp_wgrad")
+
+
 def render_fwd(sigma, z, rays, noise=None, raw_noise_std=0.0, seed=0, want_weights=True):
     n, S = z.shape
     dev = z.device

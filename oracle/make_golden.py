@@ -35,6 +35,7 @@ CASES = {
     "kf3_2x64_fp16":  dict(geom="garden", K=3, n=96, S=128, L=2, W=64, grid="trained", prec="fp16", poses=True, rows=288),
     "kf2_4x256_fp16": dict(geom="canteen", K=2, n=128, S=256, L=4, W=256, grid="trained", prec="fp16", poses=True, rows=64),
     "kf2_4x256_fp32": dict(geom="canteen", K=2, n=128, S=256, L=4, W=256, grid="trained", prec="fp32", poses=True, rows=64),
+    "kf2_2x128_fp16": dict(geom="garden", K=2, n=128, S=128, L=2, W=128, grid="trained", prec="fp16", poses=True, rows=64),
     "quad_4x256_fp16": dict(geom="quad", K=2, n=128, S=512, L=4, W=256, grid="trained", prec="fp16", poses=True, rows=32),
 }
 N_BEAMS, N_AZ = 16, 256   # 4,096-point scans keep the fixtures' regeneration cheap

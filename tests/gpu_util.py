@@ -38,12 +38,12 @@ def oracle_layers(pos, params, spec):
 
 
 def relerr(a, b):
-    a = a.detach().double().cpu()
-    b = b.detach().double().cpu()
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
 def norm_relerr(a, b):
-    a = a.detach().double().cpu().flatten()
-    b = b.detach().double().cpu().flatten()
+    a = torch.as_tensor(a).detach().double().cpu().flatten()
+    b = torch.as_tensor(b).detach().double().cpu().flatten()
     return float((a - b).norm() / (b.norm() + 1e-30))
