@@ -700,14 +700,16 @@ inline int device_sm_count() {
 }
 
 inline WgradPlan plan_wgrad(const Net& net) {
+  // The kernel is HBM-bound (it streams the A_l and dZ_{l+1} images once): give every layer a share
+  // of the SMs proportional to the BYTES it reads per tile, not to its flops.
   const int sms = device_sm_count();
   WgradPlan p;
   double total = 0;
-  for (int l = 0; l < net.L; ++l) total += (double)layer_K(net, l) * net.W;
+  for (int l = 0; l < net.L; ++l) total += (double)((l == 0 ? 1 : net.nb) + net.nb);
   int used = 0;
   int64_t off = 0;
   for (int l = 0; l < net.L; ++l) {
-    int g = (int)((double)sms * layer_K(net, l) * net.W / total);
+    int g = (int)((double)sms * ((l == 0 ? 1 : net.nb) + net.nb) / total);
     if (g < 1) g = 1;
     p.item_begin[l] = used;
     p.part_off[l] = off;
