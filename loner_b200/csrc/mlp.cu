@@ -51,7 +51,19 @@ __host__ __device__ inline int64_t mask_tile_bytes(const Net& n) { return (int64
 __host__ __device__ inline int64_t dz_tile_bytes(const Net& n) { return (int64_t)kBlk * n.L * n.nb; }
 
 // ------------------------------------------------------------------------------------------
-// pack: fp32 master [out,in] row-major -> fp16 image rows = in (k), cols = out (n)
+// pack: fp32 master [out,in] row-major -> two fp16 images, rows = in (k), cols = out (n):
+//   "bwd" image  [column block][K rows][128 B]          (dgrad streams it one column block = one
+//                                                         64-wide slice of its contraction at a time)
+//   "fwd" image  [K chunk of 64 rows][column block][64 rows][128 B]   (forward streams it one
+//                                                         64-row slice of ITS contraction at a time)
+// so that every pipeline stage of either kernel is ONE contiguous bulk copy.
+__host__ __device__ inline int64_t packed_fwd_base(const Net& n) { return packed_wout_off(n) + (int64_t)n.W * 4; }
+// forward image: layer 0 always occupies one full 64-row chunk (rows >= Epad are never read)
+__host__ __device__ inline int64_t fwd_off(const Net& n, int l) {
+  return l == 0 ? 0 : (int64_t)64 * n.W * 2 + (int64_t)(l - 1) * n.W * n.W * 2;
+}
+__host__ __device__ inline int64_t packed_total(const Net& n) { return packed_fwd_base(n) + fwd_off(n, n.L); }
+
 __global__ void pack_kernel(Net net, const float* __restrict__ params, uint8_t* __restrict__ packed) {
   const int l = blockIdx.y;
   if (l == net.L) {   // output layer: row 0 of [16, W], kept as fp32 values of the fp16-rounded weights
@@ -63,7 +75,8 @@ __global__ void pack_kernel(Net net, const float* __restrict__ params, uint8_t* 
   }
   const int K = layer_K(net, l), N = net.W;
   const float* Wm = params + param_off(net, l);
-  uint8_t* img = packed + packed_off(net, l);
+  uint8_t* img_b = packed + packed_off(net, l);
+  uint8_t* img_f = packed + packed_fwd_base(net) + fwd_off(net, l);
   const int chunks = K * (N / 8);
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += gridDim.x * blockDim.x) {
     const int k = c % K, n0 = (c / K) * 8;
@@ -72,8 +85,100 @@ __global__ void pack_kernel(Net net, const float* __restrict__ params, uint8_t* 
     for (int i = 0; i < 4; ++i)
       h[i] = __floats2half2_rn(Wm[(int64_t)(n0 + 2 * i) * K + k], Wm[(int64_t)(n0 + 2 * i + 1) * K + k]);
     const int cb = n0 / 64, j = (n0 % 64) / 8;
-    uint8_t* dst = img + (int64_t)cb * K * 128 + (int64_t)k * 128 + ((j ^ (k & 7)) * 16);
-    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(h);
+    const int sw = (j ^ (k & 7)) * 16;
+    *reinterpret_cast<uint4*>(img_b + (int64_t)cb * K * 128 + (int64_t)k * 128 + sw) = *reinterpret_cast<uint4*>(h);
+    *reinterpret_cast<uint4*>(img_f + (int64_t)(k >> 6) * (net.nb * 8192) + cb * 8192 + (k & 63) * 128 + sw) =
+        *reinterpret_cast<uint4*>(h);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared pieces of the two pipelined kernels (forward, dgrad).
+//
+// One CTA per SM, 576 threads:  warp 0 = weight producer (bulk copies into a 3-slot ring),
+// warp 1 = MMA issuer, warps 2-9 = epilogue group of tile X, warps 10-17 = epilogue group of tile Y
+// (two warps per TMEM lane quarter, each owning half of the columns).
+// Two tiles of 128 samples are in flight with one 256-column TMEM accumulator each; the MMA order
+// inside a layer is X[c0,c1] Y[c0,c1] X[c2,c3] Y[c2,c3] so that every 32 KB weight chunk is read
+// from L2 once per tile PAIR and X's epilogue overlaps Y's last MMAs (and vice versa).
+constexpr int kPipeThreads = 576;
+constexpr int kGroupThreads = 256;
+constexpr int kRingSlots = 3;
+constexpr int kSlotBytes = 32768;
+constexpr int kPipeSmem = 2 * 65536 + kRingSlots * kSlotBytes + 2304;
+
+struct PipeSmem {
+  uint8_t* tileA[2];
+  uint8_t* ring;
+  float* wout;        // [256]
+  float* part;        // [2][128] per-row partial sums handed from the upper column half to the lower
+  uint32_t w_full[kRingSlots], w_empty[kRingSlots], a_ready[2], acc_full[2];
+  uint32_t* tmem_slot;
+};
+
+__device__ __forceinline__ PipeSmem carve(uint8_t* base) {
+  PipeSmem p;
+  p.tileA[0] = base;
+  p.tileA[1] = base + 65536;
+  p.ring = base + 131072;
+  p.wout = reinterpret_cast<float*>(base + 131072 + kRingSlots * kSlotBytes);
+  p.part = p.wout + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p.part + 256);
+  for (int i = 0; i < kRingSlots; ++i) { p.w_full[i] = smem_u32(&bars[i]); p.w_empty[i] = smem_u32(&bars[kRingSlots + i]); }
+  p.a_ready[0] = smem_u32(&bars[2 * kRingSlots]); p.a_ready[1] = smem_u32(&bars[2 * kRingSlots + 1]);
+  p.acc_full[0] = smem_u32(&bars[2 * kRingSlots + 2]); p.acc_full[1] = smem_u32(&bars[2 * kRingSlots + 3]);
+  p.tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 * kRingSlots + 4]);
+  return p;
+}
+
+__device__ __forceinline__ void pipe_init(const PipeSmem& sm, int tid, int warp, const float* wout_src, int W) {
+  if (warp == 1) tmem_alloc<512>(smem_u32(sm.tmem_slot));
+  if (tid == 0) {
+    for (int i = 0; i < kRingSlots; ++i) { mbar_init(sm.w_full[i], 1); mbar_init(sm.w_empty[i], 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(sm.a_ready[t], kGroupThreads); mbar_init(sm.acc_full[t], 1); }
+    fence_mbar_init();
+  }
+  for (int j = tid; j < W; j += kPipeThreads) sm.wout[j] = wout_src[j];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+
+__device__ __forceinline__ void group_bar(int group) {
+  asm volatile("bar.sync %0, 256;" ::"r"(group + 1) : "memory");
+}
+
+// two fp32 -> packed half2 (lo = a, hi = b) with ReLU folded into the conversion
+__device__ __forceinline__ uint32_t cvt_relu_h2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_sat_h2(float a, float b) {   // saturates to the finite fp16 range
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// bits |= (v > 0) << kBit in two instructions (FSETP + predicated LOP3)
+template <int kBit>
+__device__ __forceinline__ void set_bit_if_pos(uint32_t& bits, float v) {
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, 0f00000000;\n\t@p or.b32 %0, %0, %2;\n\t}"
+      : "+r"(bits)
+      : "f"(v), "n"(1u << kBit));
+}
+
+// One 32-column slab of an epilogue: registers v[0..32) hold this row's fp32 accumulators for columns
+// [col0, col0+32); converts, (optionally) masks, and stores the four 16-byte chunks of the fp16 image.
+template <class F>
+__device__ __forceinline__ void store_slab(uint8_t* rowbase, uint32_t xs, int col0, F&& pack) {
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t hh[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) hh[e] = pack(ch * 8 + 2 * e);
+    const int c0 = col0 + ch * 8;
+    const uint32_t off = (uint32_t)(c0 >> 6) * kBlk + ((((uint32_t)(c0 & 63) >> 3) << 4) ^ xs);
+    *reinterpret_cast<uint4*>(rowbase + off) = *reinterpret_cast<uint4*>(hh);
   }
 }
 
@@ -109,15 +214,24 @@ __device__ __forceinline__ void sample_pos01(const float* pos, const float* rays
   for (int a = 0; a < 3; ++a) x[a] = __fmul_rn(__fadd_rn(p[a], 1.0f), 0.5f);           // nerf_tcnn.py:63
 }
 
-// sin/cos(pi * 2^f * x): the scaling is exact, the reduction to [-1,1] is exact, sincospif does the rest
-__device__ __forceinline__ void freq_pair(float x, int f, float& s, float& c) {
-  const float t = ldexpf(x, f);
-  const float r = t - 2.0f * rintf(0.5f * t);
-  sincospif(r, &s, &c);
+// sin/cos(pi * 2^f * x).  2^f * x is exact in fp32, and so is its reduction r to [-1, 1]; sin(pi r) and
+// cos(pi r) then come from the SFU (__sinf/__cosf on |pi r| <= pi: abs error < 1e-6, far below the
+// fp16 rounding of the encoded feature).  `scale` = 2^f as a float.
+__device__ __forceinline__ void freq_pair(float x, float scale, float& s, float& c) {
+  const float t = x * scale;
+  const float r = fmaf(-2.0f, rintf(0.5f * t), t);
+  const float a = 3.14159265358979323846f * r;
+  s = __sinf(a);
+  c = __cosf(a);
 }
 
-// Writes the 32 encoded features [32*half, 32*half+32) of row r into column block 0 of `sA`.
-__device__ __forceinline__ void encode_row(uint8_t* sA, int r, int half, const float (&x)[3], const Net& net) {
+// Writes encoded features [32*half, 32*half+32) of row r (column block 0 of `sA`): features
+// [0, 6F) are sin/cos pairs ordered [dim][freq][sin,cos], [6F, Epad) = 1.0 (tcnn pads the encoded
+// width to 16 with ones), rest 0.  (dim0, f0) = position of feature pair 16*half, precomputed.
+__device__ __forceinline__ void encode_row(uint8_t* sA, int r, int half, const float (&x)[3], const Net& net,
+                                           int dim0, int f0) {
+  int dim = dim0, f = f0;
+  float scale = (float)(1 << f0);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int cj = half * 4 + c;
@@ -126,164 +240,193 @@ __device__ __forceinline__ void encode_row(uint8_t* sA, int r, int half, const f
     for (int q = 0; q < 4; ++q) {
       const int pair = cj * 4 + q;            // features 2*pair, 2*pair+1
       float s, co;
-      if (pair < 3 * net.F) {
-        const int dim = pair / net.F, f = pair - dim * net.F;
+      if (dim < 3) {
         const float xv = dim == 0 ? x[0] : (dim == 1 ? x[1] : x[2]);
-        freq_pair(xv, f, s, co);
+        freq_pair(xv, scale, s, co);
       } else if (2 * pair < net.Epad) {
-        s = 1.0f; co = 1.0f;                  // tcnn pads the encoded width to 16 with 1.0
+        s = 1.0f; co = 1.0f;
       } else {
         s = 0.0f; co = 0.0f;
       }
       h[q] = __floats2half2_rn(s, co);
+      ++f; scale *= 2.0f;
+      if (f == net.F) { f = 0; scale = 1.0f; ++dim; }
     }
     *reinterpret_cast<uint4*>(sA + r * 128 + ((cj ^ (r & 7)) * 16)) = *reinterpret_cast<uint4*>(h);
   }
 }
 
-constexpr int kFwdThreads = 256;
-// dynamic smem: 1 KB alignment slack | A (64 KB) | W (128 KB) | misc (4 KB)
-constexpr int kFwdSmem = 1024 + 65536 + 131072 + 4096;
-
-template <bool kStash>
-__global__ void __launch_bounds__(kFwdThreads, 1) mlp_fwd_kernel(const FwdArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  uint8_t* sA = base;
-  uint8_t* sW = base + 65536;
-  float* s_part = reinterpret_cast<float*>(base + 65536 + 131072);   // [2][128] sigma partials
-  float* s_wout = s_part + 256;                                      // [W]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_wout + 256);        // [0]=weights landed, [1]=mma done
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2);
+template <int W, bool kStash>
+__global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  const PipeSmem sm = carve(smem_raw);
   const Net net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t bar_w = smem_u32(&bars[0]), bar_m = smem_u32(&bars[1]);
+  pipe_init(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W);
+  const uint32_t tmem = *sm.tmem_slot;
+  const int64_t pairs = (a.tiles + 1) / 2;
+  constexpr int kNb = W / 64;
+  constexpr uint32_t kChunkBytes = kNb * 8192;      // 64 K-rows x W out-features, fp16
 
-  if (warp == 0) tmem_alloc<256>(smem_u32(s_tmem));
-  if (tid == 32) { mbar_init(bar_w, 1); mbar_init(bar_m, 1); fence_mbar_init(); }
-  for (int j = tid; j < net.W; j += kFwdThreads)
-    s_wout[j] = reinterpret_cast<const float*>(a.packed + packed_wout_off(net))[j];
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *s_tmem;
-  uint32_t ph_w = 0, ph_m = 0;
-
-  const int q = warp & 3, h = warp >> 2;
-  const int row = q * 32 + lane;                 // TMEM lane == sample row of the tile
-  const int cols_per_thread = net.W / 2;
-
-  for (int64_t tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
-    // weights of layer 0 -> sW (previous tile's MMAs are complete: bar_m was waited on)
-    if (tid == 0) {
-      const uint32_t bytes = (uint32_t)(net.Epad * net.W * 2);
-      mbar_expect_tx(bar_w, bytes);
-      // column blocks of layer 0 are Epad*128 bytes each, contiguous in the packed image
-      bulk_g2s(smem_u32(sW), a.packed + packed_off(net, 0), bytes, bar_w);
-      if (kStash) bulk_wait_read0();   // previous tile's stash stores have finished reading sA
-    }
-    __syncthreads();
-    {  // encode A_0 (thread: row = tid & 127, half = tid >> 7)
-      const int r = tid & 127, hf = tid >> 7;
-      int64_t gs = tile * kTile + r;
-      if (gs >= a.P) gs = a.P - 1;
-      float x[3];
-      sample_pos01(a.pos, a.rays, a.z, a.S, gs, x);
-      encode_row(sA, r, hf, x, net);
-    }
-    fence_async_smem();
-    __syncthreads();
-    if (kStash && tid == 0) {
-      bulk_s2g(a.acts + tile * act_tile_bytes(net), smem_u32(sA), kBlk);
-      bulk_commit();
-    }
-
-    for (int l = 0; l < net.L; ++l) {
-      const int K = layer_K(net, l);
-      if (tid == 0) {
-        mbar_wait(bar_w, ph_w);
-        tc_fence_after();
-        const uint32_t idesc = make_idesc_f16(128, net.W, 0, 1);
-        for (int ks = 0; ks < K / 16; ++ks) {
-          const uint64_t ad = make_desc_sw128(smem_u32(sA) + (ks >> 2) * kBlk + (ks & 3) * 32, 16, 1024);
-          const uint64_t bd = make_desc_sw128(smem_u32(sW) + ks * 2048, (uint32_t)K * 128, 1024);
-          umma_f16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- producer: one contiguous bulk copy per 64-row weight chunk
+      const uint8_t* fimg = a.packed + packed_fwd_base(net);
+      uint32_t g = 0;
+      for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+        for (int l = 0; l < net.L; ++l) {
+          const int nch = (l == 0) ? 1 : kNb;
+          for (int c = 0; c < nch; ++c, ++g) {
+            const uint32_t slot = g % kRingSlots, use = g / kRingSlots;
+            if (use > 0) mbar_wait(sm.w_empty[slot], (use - 1) & 1);
+            mbar_expect_tx(sm.w_full[slot], kChunkBytes);
+            bulk_g2s(smem_u32(sm.ring + slot * kSlotBytes), fimg + fwd_off(net, l) + (int64_t)c * kChunkBytes,
+                     kChunkBytes, sm.w_full[slot]);
+          }
         }
-        umma_commit(bar_m);
       }
-      ph_w ^= 1;
-      mbar_wait(bar_m, ph_m);
-      ph_m ^= 1;
-      tc_fence_after();
-      if (tid == 0) {
-        if (l + 1 < net.L) {   // sW is free: fetch the next layer while the epilogue runs
-          const uint32_t bytes = (uint32_t)(net.W * net.W * 2);
-          mbar_expect_tx(bar_w, bytes);
-          bulk_g2s(smem_u32(sW), a.packed + packed_off(net, l + 1), bytes, bar_w);
-        }
-        if (kStash) bulk_wait_read0();     // stash store of this layer's input image is done with sA
-      }
-      __syncthreads();
-
-      // epilogue: TMEM -> relu -> fp16 -> sA (the next layer's A operand / the stash image)
-      const bool last = (l == net.L - 1);
-      float sig = 0.f;
-      uint32_t mbits[4] = {0u, 0u, 0u, 0u};
-      for (int it = 0; it < cols_per_thread / 32; ++it) {
-        const int col0 = h * cols_per_thread + it * 32;
-        uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
-        tmem_ld_wait();
-        uint32_t bits = 0u;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          __half2 hh[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float f0 = __uint_as_float(v[ch * 8 + 2 * e]), f1 = __uint_as_float(v[ch * 8 + 2 * e + 1]);
-            bits |= (f0 > 0.f ? 1u : 0u) << (ch * 8 + 2 * e);
-            bits |= (f1 > 0.f ? 1u : 0u) << (ch * 8 + 2 * e + 1);
-            hh[e] = __floats2half2_rn(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
-            if (last) {
-              const int c = col0 + ch * 8 + 2 * e;
-              sig = fmaf(__low2float(hh[e]), s_wout[c], sig);
-              sig = fmaf(__high2float(hh[e]), s_wout[c + 1], sig);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer
+      constexpr uint32_t idesc = make_idesc_f16(128, W, 0, 1);
+      uint32_t g_base = 0, par_a[2] = {0u, 0u};
+      for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+        for (int l = 0; l < net.L; ++l) {
+          const int nch = (l == 0) ? 1 : kNb;
+          const int ksteps0 = (l == 0) ? net.Epad / 16 : 4;   // layer 0 contracts over Epad (<= 64) features
+          for (int c0 = 0; c0 < nch; c0 += 2) {
+            const int c1 = min(c0 + 2, nch);
+            for (int t = 0; t < 2; ++t) {
+              if (c0 == 0) { mbar_wait(sm.a_ready[t], par_a[t]); par_a[t] ^= 1u; tc_fence_after(); }
+              for (int c = c0; c < c1; ++c) {
+                const uint32_t g = g_base + c, slot = g % kRingSlots;
+                if (t == 0) { mbar_wait(sm.w_full[slot], (g / kRingSlots) & 1); tc_fence_after(); }
+                const uint32_t sa = smem_u32(sm.tileA[t]) + c * kBlk, sb = smem_u32(sm.ring + slot * kSlotBytes);
+                for (int ks = 0; ks < ksteps0; ++ks) {
+                  const uint64_t ad = make_desc_sw128(sa + ks * 32, 16, 1024);
+                  const uint64_t bd = make_desc_sw128(sb + ks * 2048, 8192, 1024);
+                  umma_f16(tmem + t * 256, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                }
+                if (t == 1) umma_commit(sm.w_empty[slot]);     // both tiles have consumed this chunk
+              }
+              if (c1 == nch) umma_commit(sm.acc_full[t]);
             }
           }
-          if (!last || kStash) {
-            const int c0 = col0 + ch * 8;
-            const int cb = c0 >> 6, j = (c0 & 63) >> 3;
-            *reinterpret_cast<uint4*>(sA + cb * kBlk + row * 128 + ((j ^ (row & 7)) * 16)) =
-                *reinterpret_cast<uint4*>(hh);
-          }
+          g_base += nch;
         }
-        mbits[it] = bits;
-      }
-      if (kStash) {
-        uint32_t* mrow = reinterpret_cast<uint32_t*>(a.masks + tile * mask_tile_bytes(net)) +
-                         ((int64_t)l * kTile + row) * (net.W / 32) + h * (cols_per_thread / 32);
-        for (int it = 0; it < cols_per_thread / 32; ++it) mrow[it] = mbits[it];
-      }
-      if (last) s_part[h * 128 + row] = sig;
-      tc_fence_before();
-      fence_async_smem();
-      __syncthreads();
-      if (kStash && tid == 0) {
-        bulk_s2g(a.acts + tile * act_tile_bytes(net) + kBlk + (int64_t)l * net.nb * kBlk, smem_u32(sA),
-                 (uint32_t)(net.nb * kBlk));
-        bulk_commit();
-      }
-      if (last && tid < 128) {
-        const int64_t gs = tile * kTile + tid;
-        if (gs < a.P) a.sigma[gs] = s_part[tid] + s_part[128 + tid];
       }
     }
+  } else {
+    // ---------------- epilogue groups: thread = (sample row, column half)
+    const int e = warp - 2;
+    const int t = e >> 3;
+    const int h = (e & 7) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool elected = ((e & 7) == 0) && lane == 0;
+    uint8_t* sA = sm.tileA[t];
+    uint8_t* rowbase = sA + row * 128;
+    const uint32_t xs = (uint32_t)(row & 7) << 4;
+    constexpr int kCols = W / 2;                      // columns per thread
+    const uint32_t acc = tmem + t * 256 + ((uint32_t)(q * 32) << 16) + h * kCols;
+    float* part = sm.part + t * 128;
+    uint32_t par_acc = 0;
+    const int enc_dim0 = (16 * h) / net.F, enc_f0 = (16 * h) % net.F;
+    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+      const int64_t tile = 2 * pair + t;
+      const bool active = tile < a.tiles;
+      int64_t gs = tile * kTile + row;
+      const bool in = active && gs < a.P;
+      if (gs >= a.P) gs = a.P - 1;
+      if (kStash) { if (elected) bulk_wait_read0(); group_bar(t); }
+      {
+        float x[3];
+        sample_pos01(a.pos, a.rays, a.z, a.S, gs, x);
+        encode_row(sA, row, h, x, net, enc_dim0, enc_f0);
+      }
+      fence_async_smem();
+      mbar_arrive(sm.a_ready[t]);
+      if (kStash) {
+        group_bar(t);
+        if (elected && active) { bulk_s2g(a.acts + tile * act_tile_bytes(net), smem_u32(sA), kBlk); bulk_commit(); }
+      }
+      for (int l = 0; l < net.L; ++l) {
+        const bool last = (l == net.L - 1);
+        mbar_wait(sm.acc_full[t], par_acc);
+        par_acc ^= 1u;
+        tc_fence_after();
+        if (kStash) { if (elected) bulk_wait_read0(); group_bar(t); }
+        float sig = 0.f;
+        uint32_t mbits[kCols / 32];
+#pragma unroll
+        for (int it = 0; it < kCols / 32; ++it) {
+          uint32_t v[32];
+          tmem_ld32(acc + it * 32, v);
+          tmem_ld_wait();
+          const int col0 = h * kCols + it * 32;
+          if (kStash) {
+            uint32_t bits = 0u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              // (unrolled with a compile-time bit index)
+              switch (i) {
+#define LONER_BIT(I) case I: set_bit_if_pos<I>(bits, __uint_as_float(v[I])); break;
+                LONER_BIT(0) LONER_BIT(1) LONER_BIT(2) LONER_BIT(3) LONER_BIT(4) LONER_BIT(5) LONER_BIT(6) LONER_BIT(7)
+                LONER_BIT(8) LONER_BIT(9) LONER_BIT(10) LONER_BIT(11) LONER_BIT(12) LONER_BIT(13) LONER_BIT(14)
+                LONER_BIT(15) LONER_BIT(16) LONER_BIT(17) LONER_BIT(18) LONER_BIT(19) LONER_BIT(20) LONER_BIT(21)
+                LONER_BIT(22) LONER_BIT(23) LONER_BIT(24) LONER_BIT(25) LONER_BIT(26) LONER_BIT(27) LONER_BIT(28)
+                LONER_BIT(29) LONER_BIT(30) LONER_BIT(31)
+#undef LONER_BIT
+              }
+            }
+            mbits[it] = bits;
+          }
+          if (!last || kStash) {
+            store_slab(rowbase, xs, col0, [&](int i0) {
+              return cvt_relu_h2(__uint_as_float(v[i0]), __uint_as_float(v[i0 + 1]));
+            });
+          }
+          if (last) {
+#pragma unroll
+            for (int i0 = 0; i0 < 32; i0 += 2) {
+              const uint32_t hh = cvt_relu_h2(__uint_as_float(v[i0]), __uint_as_float(v[i0 + 1]));
+              const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&hh));
+              const float2 w2 = *reinterpret_cast<const float2*>(sm.wout + col0 + i0);
+              sig = fmaf(r2.x, w2.x, sig);
+              sig = fmaf(r2.y, w2.y, sig);
+            }
+          }
+        }
+        tc_fence_before();
+        if (kStash && active) {
+          uint32_t* mrow = reinterpret_cast<uint32_t*>(a.masks + tile * mask_tile_bytes(net)) +
+                           ((int64_t)l * kTile + row) * (W / 32) + h * (kCols / 32);
+#pragma unroll
+          for (int it = 0; it < kCols / 32; ++it) mrow[it] = mbits[it];
+        }
+        if (!last) {
+          fence_async_smem();
+          mbar_arrive(sm.a_ready[t]);
+        } else {
+          if (h == 1) part[row] = sig;
+          if (kStash) fence_async_smem();
+        }
+        if (kStash || last) group_bar(t);
+        if (last && h == 0 && in) a.sigma[gs] = sig + part[row];
+        if (kStash && elected && active) {
+          bulk_s2g(a.acts + tile * act_tile_bytes(net) + kBlk + (int64_t)l * kNb * kBlk, smem_u32(sA),
+                   (uint32_t)(kNb * kBlk));
+          bulk_commit();
+        }
+      }
+    }
+    if (kStash && elected) bulk_wait0();
   }
-  if (kStash && tid == 0) bulk_wait0();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem);
+  if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -304,197 +447,182 @@ struct BwdArgs {
   float* d_pos;          // [P,3] or null
 };
 
-constexpr int kBwdThreads = 256;
-constexpr int kBwdSmem = 1024 + 65536 + 131072 + 8192;
-
-__global__ void __launch_bounds__(kBwdThreads, 1) mlp_dgrad_kernel(const BwdArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  uint8_t* sG = base;
-  uint8_t* sW = base + 65536;
-  float* s_wout = reinterpret_cast<float*>(base + 65536 + 131072);   // [W]
-  float* s_dx = s_wout + 256;                                        // [2][128][3] input-grad partials
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dx + 768);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2);
+template <int W>
+__global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  const PipeSmem sm = carve(smem_raw);
   const Net net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t bar_w = smem_u32(&bars[0]), bar_m = smem_u32(&bars[1]);
-
-  if (warp == 0) tmem_alloc<256>(smem_u32(s_tmem));
-  if (tid == 32) { mbar_init(bar_w, 1); mbar_init(bar_m, 1); fence_mbar_init(); }
-  for (int j = tid; j < net.W; j += kBwdThreads)
-    s_wout[j] = reinterpret_cast<const float*>(a.packed + packed_wout_off(net))[j];
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *s_tmem;
-  uint32_t ph_w = 0, ph_m = 0;
-  const int q = warp & 3, h = warp >> 2;
-  const int row = q * 32 + lane;
-  const int cpt = net.W / 2;          // columns per thread for W-wide outputs
+  pipe_init(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W);
+  const uint32_t tmem = *sm.tmem_slot;
+  const int64_t pairs = (a.tiles + 1) / 2;
   const bool want_dx = a.d_pos != nullptr;
+  const int l_lo = want_dx ? 0 : 1;        // GEMMs run for l = L-1 .. l_lo : dA_l = dZ_{l+1} * W_l
+  constexpr int kNb = W / 64;              // contraction (out-features of layer l) in 64-wide chunks
 
-  for (int64_t tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
-    const int64_t gs = tile * kTile + row;
-    const bool in = gs < a.P;
-    if (tid == 0) {
-      if (net.L > 1 || want_dx) {     // first GEMM's weights: layer L-1 (or layer 0 when L == 1)
-        const int lw = net.L - 1;
-        const uint32_t bytes = (uint32_t)(layer_K(net, lw) * net.W * 2);
-        mbar_expect_tx(bar_w, bytes);
-        bulk_g2s(smem_u32(sW), a.packed + packed_off(net, lw), bytes, bar_w);
-      }
-      bulk_wait_read0();              // previous tile's dZ stores are done with sG
-    }
-    __syncthreads();
-    {  // dZ_L = d_sigma * w_out * relu'(Z_L)
-      const float ds = in ? a.d_sigma[gs] * a.gscale : 0.f;
-      const uint32_t* mrow = reinterpret_cast<const uint32_t*>(a.masks + tile * mask_tile_bytes(net)) +
-                             ((int64_t)(net.L - 1) * kTile + row) * (net.W / 32) + h * (cpt / 32);
-      for (int it = 0; it < cpt / 32; ++it) {
-        const uint32_t bits = mrow[it];
-        const int col0 = h * cpt + it * 32;
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          __half2 hh[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = col0 + ch * 8 + 2 * e;
-            float g0 = ((bits >> (ch * 8 + 2 * e)) & 1u) ? ds * s_wout[c] : 0.f;
-            float g1 = ((bits >> (ch * 8 + 2 * e + 1)) & 1u) ? ds * s_wout[c + 1] : 0.f;
-            g0 = fminf(fmaxf(g0, -65504.f), 65504.f);
-            g1 = fminf(fmaxf(g1, -65504.f), 65504.f);
-            hh[e] = __floats2half2_rn(g0, g1);
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+        for (int l = net.L - 1; l >= l_lo; --l) {
+          const uint32_t bytes = (uint32_t)layer_K(net, l) * 128u;     // one column block: K_l rows x 128 B
+          for (int c = 0; c < kNb; ++c, ++g) {
+            const uint32_t slot = g % kRingSlots, use = g / kRingSlots;
+            if (use > 0) mbar_wait(sm.w_empty[slot], (use - 1) & 1);
+            mbar_expect_tx(sm.w_full[slot], bytes);
+            bulk_g2s(smem_u32(sm.ring + slot * kSlotBytes), a.packed + packed_off(net, l) + (int64_t)c * bytes, bytes,
+                     sm.w_full[slot]);
           }
-          const int c0 = col0 + ch * 8;
-          const int cb = c0 >> 6, j = (c0 & 63) >> 3;
-          *reinterpret_cast<uint4*>(sG + cb * kBlk + row * 128 + ((j ^ (row & 7)) * 16)) =
-              *reinterpret_cast<uint4*>(hh);
         }
       }
     }
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(net.L - 1) * net.nb * kBlk, smem_u32(sG),
-               (uint32_t)(net.nb * kBlk));
-      bulk_commit();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t g_base = 0, par_a[2] = {0u, 0u};
+      for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+        for (int l = net.L - 1; l >= l_lo; --l) {
+          const uint32_t idesc = make_idesc_f16(128, layer_K(net, l), 0, 0);
+          for (int c0 = 0; c0 < kNb; c0 += 2) {
+            const int c1 = min(c0 + 2, kNb);
+            for (int t = 0; t < 2; ++t) {
+              if (c0 == 0) { mbar_wait(sm.a_ready[t], par_a[t]); par_a[t] ^= 1u; tc_fence_after(); }
+              for (int c = c0; c < c1; ++c) {
+                const uint32_t g = g_base + c, slot = g % kRingSlots;
+                if (t == 0) { mbar_wait(sm.w_full[slot], (g / kRingSlots) & 1); tc_fence_after(); }
+                const uint32_t sa = smem_u32(sm.tileA[t]) + c * kBlk, sb = smem_u32(sm.ring + slot * kSlotBytes);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t ad = make_desc_sw128(sa + ks * 32, 16, 1024);
+                  const uint64_t bd = make_desc_sw128(sb + ks * 32, 16, 1024);
+                  umma_f16(tmem + t * 256, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                }
+                if (t == 1) umma_commit(sm.w_empty[slot]);
+              }
+              if (c1 == kNb) umma_commit(sm.acc_full[t]);
+            }
+          }
+          g_base += kNb;
+        }
+      }
     }
-
-    // dA_l = dZ_{l+1} * W_l  for l = L-1 .. 1 (and l = 0 when input gradients are wanted)
-    for (int l = net.L - 1; l >= (want_dx ? 0 : 1); --l) {
-      const int Nout = layer_K(net, l);     // width of dA_l (in-features of layer l)
-      if (tid == 0) {
-        mbar_wait(bar_w, ph_w);
-        tc_fence_after();
-        const uint32_t idesc = make_idesc_f16(128, Nout, 0, 0);
-        for (int ks = 0; ks < net.W / 16; ++ks) {     // contraction over the out-features of layer l
-          const uint64_t ad = make_desc_sw128(smem_u32(sG) + (ks >> 2) * kBlk + (ks & 3) * 32, 16, 1024);
-          const uint64_t bd =
-              make_desc_sw128(smem_u32(sW) + (ks >> 2) * (Nout * 128) + (ks & 3) * 32, 16, 1024);
-          umma_f16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
-        }
-        umma_commit(bar_m);
-      }
-      ph_w ^= 1;
-      mbar_wait(bar_m, ph_m);
-      ph_m ^= 1;
-      tc_fence_after();
-      if (tid == 0) {
-        const int ln = l - 1;
-        if (ln >= (want_dx ? 0 : 1)) {
-          const uint32_t bytes = (uint32_t)(layer_K(net, ln) * net.W * 2);
-          mbar_expect_tx(bar_w, bytes);
-          bulk_g2s(smem_u32(sW), a.packed + packed_off(net, ln), bytes, bar_w);
-        }
-        bulk_wait_read0();
-      }
-      __syncthreads();
-
-      if (l >= 1) {
-        // epilogue: dZ_l = dA_l * relu'(Z_l)  -> fp16 image in sG
-        const uint32_t* mrow = reinterpret_cast<const uint32_t*>(a.masks + tile * mask_tile_bytes(net)) +
-                               ((int64_t)(l - 1) * kTile + row) * (net.W / 32) + h * (cpt / 32);
-        for (int it = 0; it < cpt / 32; ++it) {
-          const int col0 = h * cpt + it * 32;
-          uint32_t v[32];
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
-          tmem_ld_wait();
+  } else {
+    const int e = warp - 2;
+    const int t = e >> 3;
+    const int h = (e & 7) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool elected = ((e & 7) == 0) && lane == 0;
+    uint8_t* sG = sm.tileA[t];
+    uint8_t* rowbase = sG + row * 128;
+    const uint32_t xs = (uint32_t)(row & 7) << 4;
+    constexpr int kCols = W / 2;
+    const uint32_t acc_row = tmem + t * 256 + ((uint32_t)(q * 32) << 16);
+    const uint32_t acc = acc_row + h * kCols;
+    uint32_t par_acc = 0;
+    constexpr int kWords = W / 32;
+    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+      const int64_t tile = 2 * pair + t;
+      const bool active = tile < a.tiles;
+      const int64_t gs = tile * kTile + row;
+      const bool in = active && gs < a.P;
+      const uint32_t* mtile = reinterpret_cast<const uint32_t*>(a.masks + (active ? tile : 0) * mask_tile_bytes(net));
+      if (elected) bulk_wait_read0();
+      group_bar(t);
+      {  // dZ_L = d_sigma * w_out * relu'(Z_L)
+        const float ds = in ? a.d_sigma[gs] * a.gscale : 0.f;
+        const uint32_t* mrow = mtile + ((int64_t)(net.L - 1) * kTile + row) * kWords + h * (kCols / 32);
+#pragma unroll
+        for (int it = 0; it < kCols / 32; ++it) {
           const uint32_t bits = mrow[it];
+          const int col0 = h * kCols + it * 32;
+          store_slab(rowbase, xs, col0, [&](int i0) {
+            const float2 w2 = *reinterpret_cast<const float2*>(sm.wout + col0 + i0);
+            const float g0 = ((bits >> i0) & 1u) ? ds * w2.x : 0.f;
+            const float g1 = ((bits >> (i0 + 1)) & 1u) ? ds * w2.y : 0.f;
+            return cvt_sat_h2(g0, g1);
+          });
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(sm.a_ready[t]);
+      group_bar(t);
+      if (elected && active) {
+        bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(net.L - 1) * kNb * kBlk, smem_u32(sG),
+                 (uint32_t)(kNb * kBlk));
+        bulk_commit();
+      }
+      for (int l = net.L - 1; l >= l_lo; --l) {
+        mbar_wait(sm.acc_full[t], par_acc);
+        par_acc ^= 1u;
+        tc_fence_after();
+        if (elected) bulk_wait_read0();
+        group_bar(t);
+        if (l >= 1) {
+          // dZ_l = dA_l * relu'(Z_l)  -> fp16 image in sG (next GEMM's A operand and wgrad's B operand)
+          const uint32_t* mrow = mtile + ((int64_t)(l - 1) * kTile + row) * kWords + h * (kCols / 32);
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            __half2 hh[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float g0 = ((bits >> (ch * 8 + 2 * e)) & 1u) ? __uint_as_float(v[ch * 8 + 2 * e]) : 0.f;
-              float g1 = ((bits >> (ch * 8 + 2 * e + 1)) & 1u) ? __uint_as_float(v[ch * 8 + 2 * e + 1]) : 0.f;
-              g0 = fminf(fmaxf(g0, -65504.f), 65504.f);
-              g1 = fminf(fmaxf(g1, -65504.f), 65504.f);
-              hh[e] = __floats2half2_rn(g0, g1);
-            }
-            const int c0 = col0 + ch * 8;
-            const int cb = c0 >> 6, j = (c0 & 63) >> 3;
-            *reinterpret_cast<uint4*>(sG + cb * kBlk + row * 128 + ((j ^ (row & 7)) * 16)) =
-                *reinterpret_cast<uint4*>(hh);
+          for (int it = 0; it < kCols / 32; ++it) {
+            uint32_t v[32];
+            tmem_ld32(acc + it * 32, v);
+            const uint32_t bits = mrow[it];
+            tmem_ld_wait();
+            store_slab(rowbase, xs, h * kCols + it * 32, [&](int i0) {
+              const float g0 = ((bits >> i0) & 1u) ? __uint_as_float(v[i0]) : 0.f;
+              const float g1 = ((bits >> (i0 + 1)) & 1u) ? __uint_as_float(v[i0 + 1]) : 0.f;
+              return cvt_sat_h2(g0, g1);
+            });
           }
-        }
-        tc_fence_before();
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-          bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(l - 1) * net.nb * kBlk, smem_u32(sG),
-                   (uint32_t)(net.nb * kBlk));
-          bulk_commit();
-        }
-      } else {
-        // l == 0: dEnc [128 x Epad] -> d_pos through the sin/cos encoding
-        float x[3];
-        {
-          int64_t g2 = in ? gs : a.P - 1;
-          sample_pos01(a.pos, a.rays, a.z, a.S, g2, x);
-        }
-        float dx[3] = {0.f, 0.f, 0.f};
-        if (h * 32 < net.Epad) {
-          uint32_t v[32];
-          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32), v);
-          tmem_ld_wait();
+          tc_fence_before();
+          fence_async_smem();
+          if (l - 1 >= l_lo) mbar_arrive(sm.a_ready[t]);
+          group_bar(t);
+          if (elected && active) {
+            bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(l - 1) * kNb * kBlk, smem_u32(sG),
+                     (uint32_t)(kNb * kBlk));
+            bulk_commit();
+          }
+        } else if (h == 0) {
+          // l == 0: dEnc [128 x Epad] -> d_pos through the sin/cos encoding (lower-half warps only)
+          float x[3];
+          sample_pos01(a.pos, a.rays, a.z, a.S, in ? gs : a.P - 1, x);
+          float dx[3] = {0.f, 0.f, 0.f};
+          int dim = 0, f = 0;
+          float scale = 1.0f;
+          for (int it = 0; it * 32 < net.Epad; ++it) {
+            uint32_t v[32];
+            tmem_ld32(acc_row + it * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int pq = 0; pq < 16; ++pq) {
-            const int pair = h * 16 + pq;
-            if (pair < 3 * net.F) {
-              const int dim = pair / net.F, f = pair - dim * net.F;
-              const float xv = dim == 0 ? x[0] : (dim == 1 ? x[1] : x[2]);
-              float s, c;
-              freq_pair(xv, f, s, c);
-              const float k = ldexpf(3.14159265358979323846f, f);
-              const float g = (__uint_as_float(v[2 * pq]) * c - __uint_as_float(v[2 * pq + 1]) * s) * k;
-              if (dim == 0) dx[0] += g; else if (dim == 1) dx[1] += g; else dx[2] += g;
+            for (int pq = 0; pq < 16; ++pq) {
+              if (dim < 3) {
+                const float xv = dim == 0 ? x[0] : (dim == 1 ? x[1] : x[2]);
+                float s, c;
+                freq_pair(xv, scale, s, c);
+                // d/dx sin(pi 2^f x) = pi 2^f cos, d/dx cos = -pi 2^f sin
+                const float g = (__uint_as_float(v[2 * pq]) * c - __uint_as_float(v[2 * pq + 1]) * s) *
+                                (3.14159265358979323846f * scale);
+                if (dim == 0) dx[0] += g; else if (dim == 1) dx[1] += g; else dx[2] += g;
+              }
+              ++f; scale *= 2.0f;
+              if (f == net.F) { f = 0; scale = 1.0f; ++dim; }
             }
           }
-        }
-        s_dx[(h * 128 + row) * 3 + 0] = dx[0];
-        s_dx[(h * 128 + row) * 3 + 1] = dx[1];
-        s_dx[(h * 128 + row) * 3 + 2] = dx[2];
-        tc_fence_before();
-        __syncthreads();
-        if (tid < 128) {
-          const int64_t g3 = tile * kTile + tid;
-          if (g3 < a.P) {
+          tc_fence_before();
+          if (in) {
             const float inv = 0.5f / a.gscale;      // x = (pos + 1) / 2
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-              a.d_pos[g3 * 3 + d] = (s_dx[tid * 3 + d] + s_dx[(128 + tid) * 3 + d]) * inv;
+            a.d_pos[gs * 3 + 0] = dx[0] * inv;
+            a.d_pos[gs * 3 + 1] = dx[1] * inv;
+            a.d_pos[gs * 3 + 2] = dx[2] * inv;
           }
         }
-        __syncthreads();
       }
     }
+    if (elected) bulk_wait0();
   }
-  if (tid == 0) bulk_wait0();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem);
+  if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -647,38 +775,59 @@ __global__ void wgrad_reduce_kernel(Net net, const float* __restrict__ partials,
   }
 }
 
-// dW_out[j] = sum_s d_sigma[s] * A_L[s,j]   (row 0 of the padded [16, W] output matrix)
+// dW_out[j] = sum_s d_sigma[s] * A_L[s,j]   (row 0 of the padded [16, W] output matrix).
+// HBM-streaming: a warp reads 4 image rows (4 x 128 B) per instruction; lane = (row%4, 16-byte
+// logical chunk j), so each lane owns 8 fixed columns per column block.
 __global__ void __launch_bounds__(256) dwout_kernel(Net net, const uint8_t* __restrict__ acts,
                                                     const float* __restrict__ d_sigma, int64_t P, int64_t tiles,
                                                     float* __restrict__ d_params) {
   __shared__ float red[256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * 8 + warp, nw = (int64_t)gridDim.x * 8;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};    // lane owns logical columns cb*64 + 2*lane, +1
+  const int j = lane & 7, rsub = lane >> 3;
+  float acc[4][8];
+#pragma unroll
+  for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[cb][i] = 0.f;
   const int64_t aL = (int64_t)kBlk + (int64_t)(net.L - 1) * net.nb * kBlk;
   for (int64_t tile = gw; tile < tiles; tile += nw) {
     const uint8_t* img = acts + tile * act_tile_bytes(net) + aL;
-    for (int r = 0; r < kTile; ++r) {
+#pragma unroll 4
+    for (int r0 = 0; r0 < kTile; r0 += 4) {
+      const int r = r0 + rsub;
       const int64_t gs = tile * kTile + r;
-      if (gs >= P) break;
-      const float ds = __ldg(d_sigma + gs);
-      const int slot = ((lane >> 2) ^ (r & 7)) * 16 + (lane & 3) * 4;
-      for (int cb = 0; cb < net.nb; ++cb) {
-        const __half2 v = *reinterpret_cast<const __half2*>(img + cb * kBlk + r * 128 + slot);
-        acc[2 * cb] = fmaf(ds, __low2float(v), acc[2 * cb]);
-        acc[2 * cb + 1] = fmaf(ds, __high2float(v), acc[2 * cb + 1]);
+      const float ds = gs < P ? __ldg(d_sigma + gs) : 0.f;
+      const int slot = (j ^ (r & 7)) * 16;
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        if (cb < net.nb) {
+          const uint4 v = *reinterpret_cast<const uint4*>(img + cb * kBlk + r * 128 + slot);
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            acc[cb][2 * i] = fmaf(ds, f.x, acc[cb][2 * i]);
+            acc[cb][2 * i + 1] = fmaf(ds, f.y, acc[cb][2 * i + 1]);
+          }
+        }
       }
     }
   }
-  for (int j = threadIdx.x; j < 256; j += blockDim.x) red[j] = 0.f;
+  for (int c = threadIdx.x; c < 256; c += blockDim.x) red[c] = 0.f;
   __syncthreads();
-  for (int cb = 0; cb < net.nb; ++cb) {
-    atomicAdd(&red[cb * 64 + 2 * lane], acc[2 * cb]);
-    atomicAdd(&red[cb * 64 + 2 * lane + 1], acc[2 * cb + 1]);
-  }
+#pragma unroll
+  for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = acc[cb][i];
+      v += __shfl_xor_sync(kFull, v, 8);
+      v += __shfl_xor_sync(kFull, v, 16);
+      if (rsub == 0 && cb < net.nb) atomicAdd(&red[cb * 64 + j * 8 + i], v);
+    }
   __syncthreads();
-  for (int j = threadIdx.x; j < net.W; j += blockDim.x)
-    if (red[j] != 0.f) atomicAdd(d_params + param_off(net, net.L) + j, red[j]);
+  for (int c = threadIdx.x; c < net.W; c += blockDim.x)
+    if (red[c] != 0.f) atomicAdd(d_params + param_off(net, net.L) + c, red[c]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -736,7 +885,7 @@ extern "C" int64_t loner_mlp_param_count(const loner_net_t* n) {
 extern "C" int64_t loner_mlp_packed_bytes(const loner_net_t* n) {
   Net net;
   if (!net_from(n, net)) return -1;
-  return packed_wout_off(net) + (int64_t)net.W * 4;
+  return packed_total(net);
 }
 static inline int64_t n_tiles(int64_t P) { return (P + kTile - 1) / kTile; }
 extern "C" int64_t loner_mlp_act_bytes(const loner_net_t* n, int64_t P) {
@@ -772,14 +921,14 @@ extern "C" int loner_mlp_fwd(const loner_net_t* n, const void* packed, const flo
   a.tiles = n_tiles(P); a.sigma = sigma; a.acts = (uint8_t*)acts;
   a.masks = acts ? (uint8_t*)acts + a.tiles * act_tile_bytes(net) : nullptr;
   const int sms = device_sm_count();
-  const unsigned grid = (unsigned)(a.tiles < sms ? a.tiles : sms);
-  if (acts) {
-    cudaFuncSetAttribute(mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
-    mlp_fwd_kernel<true><<<grid, kFwdThreads, kFwdSmem, (cudaStream_t)stream>>>(a);
-  } else {
-    cudaFuncSetAttribute(mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
-    mlp_fwd_kernel<false><<<grid, kFwdThreads, kFwdSmem, (cudaStream_t)stream>>>(a);
-  }
+  const int64_t pairs = (a.tiles + 1) / 2;
+  const unsigned grid = (unsigned)(pairs < sms ? pairs : sms);
+  auto launch = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem);
+    kern<<<grid, kPipeThreads, kPipeSmem, (cudaStream_t)stream>>>(a);
+  };
+  if (net.W == 256) { if (acts) launch(mlp_fwd_kernel<256, true>); else launch(mlp_fwd_kernel<256, false>); }
+  else              { if (acts) launch(mlp_fwd_kernel<128, true>); else launch(mlp_fwd_kernel<128, false>); }
   LONER_CHECK_LAUNCH();
   return LONER_OK;
 }
@@ -804,8 +953,12 @@ extern "C" int loner_mlp_dgrad(const loner_net_t* n, const void* packed, const f
   b.net = net; b.packed = (const uint8_t*)packed; b.pos = pos; b.rays = rays; b.z = z_vals; b.S = S; b.P = P;
   b.tiles = tiles; b.d_sigma = d_sigma; b.masks = (const uint8_t*)acts + tiles * act_tile_bytes(net);
   b.dz = (uint8_t*)scratch; b.gscale = grad_scale; b.d_pos = d_pos;
-  cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
-  mlp_dgrad_kernel<<<(unsigned)(tiles < sms ? tiles : sms), kBwdThreads, kBwdSmem, (cudaStream_t)stream>>>(b);
+  const int64_t pairs = (tiles + 1) / 2;
+  auto launch = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem);
+    kern<<<(unsigned)(pairs < sms ? pairs : sms), kPipeThreads, kPipeSmem, (cudaStream_t)stream>>>(b);
+  };
+  if (net.W == 256) launch(mlp_dgrad_kernel<256>); else launch(mlp_dgrad_kernel<128>);
   LONER_CHECK_LAUNCH();
   return LONER_OK;
 }
@@ -832,7 +985,7 @@ extern "C" int loner_mlp_wgrad(const loner_net_t* n, const void* packed, int64_t
   dim3 rgrid(64, net.L);
   wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(net, partials, w, 1.0f / grad_scale, d_params);
   LONER_CHECK_LAUNCH();
-  dwout_kernel<<<(unsigned)(sms * 2), 256, 0, st>>>(net, (const uint8_t*)acts, d_sigma, P, tiles, d_params);
+  dwout_kernel<<<(unsigned)(sms * 4), 256, 0, st>>>(net, (const uint8_t*)acts, d_sigma, P, tiles, d_params);
   LONER_CHECK_LAUNCH();
   return LONER_OK;
 }

@@ -117,6 +117,10 @@ class MappingEngine:
         self.launches = 0           # kernels of OURS launched (bench reports it)
         self.last = {}
         self.timers = None          # name -> [(start_event, end_event)] when bench.py profiles sections
+        self._wcache = {}
+        self._pose_cache = None
+        self._counters = torch.zeros(2, device=self.dev, dtype=torch.int32)
+        self._loss_acc = torch.zeros(4, device=self.dev, dtype=torch.float32)
 
     # ---------------------------------------------------------------- keyframes
     def add_keyframe(self, ray_directions, distances, pose6):
@@ -126,6 +130,7 @@ class MappingEngine:
         self.kf_offsets.append(off)
         self.kf_sizes.append(pts.shape[0])
         self.poses6.append(pose6.detach().to(self.dev, torch.float32).clone())
+        self._pose_cache = None
         return len(self.poses6) - 1
 
     def new_phase(self, optimize_poses: bool):
@@ -134,6 +139,7 @@ class MappingEngine:
         self.exp_avg_sq.zero_()
         self.adam_t = 0
         self.pose_opt = None
+        self._pose_cache = None
         for k, p in enumerate(self.poses6):
             p.requires_grad_(bool(optimize_poses and k > 0))     # keyframe 0 is anchored
         if optimize_poses:
@@ -161,15 +167,34 @@ class MappingEngine:
             self._bufs[name] = b
         return b
 
+    def _window_consts(self, window, n_per_kf):
+        """Per-window constants live on the device; built once (no per-step host->device traffic)."""
+        key = (tuple(window), n_per_kf)
+        c = self._wcache.get(key)
+        if c is None:
+            K = len(window)
+            c = dict(
+                sizes=torch.tensor([self.kf_sizes[k] for k in window], device=self.dev, dtype=torch.float32)[:, None],
+                maxi=torch.tensor([self.kf_sizes[k] - 1 for k in window], device=self.dev, dtype=torch.int64)[:, None],
+                offs=torch.tensor([self.kf_offsets[k] for k in window], device=self.dev, dtype=torch.int64)[:, None],
+                ray_kf=torch.arange(K, device=self.dev, dtype=torch.int32).repeat_interleave(n_per_kf).contiguous())
+            self._wcache = {key: c}
+        return c
+
     def _pick_rays(self, window, n_per_kf):
-        K = len(window)
-        sizes = torch.tensor([self.kf_sizes[k] for k in window], device=self.dev, dtype=torch.float32)
-        offs = torch.tensor([self.kf_offsets[k] for k in window], device=self.dev, dtype=torch.int64)
-        u = torch.rand(K, n_per_kf, device=self.dev, generator=self.gen)
-        idx = (u * sizes[:, None]).long().clamp_(max=int(max(self.kf_sizes)) - 1)
-        ray_point = (idx + offs[:, None]).reshape(-1).contiguous()
-        ray_kf = torch.arange(K, device=self.dev, dtype=torch.int32).repeat_interleave(n_per_kf).contiguous()
-        return ray_kf, ray_point
+        c = self._window_consts(window, n_per_kf)
+        u = torch.rand(len(window), n_per_kf, device=self.dev, generator=self.gen)
+        idx = torch.minimum((u * c["sizes"]).long(), c["maxi"])
+        return c["ray_kf"], (idx + c["offs"]).reshape(-1)
+
+    def _poses12(self, window, optimize_poses):
+        """[K,12] pose matrices; recomputed through autograd only while poses are being optimised."""
+        key = tuple(window)
+        if not optimize_poses and self._pose_cache is not None and self._pose_cache[0] == key:
+            return self._pose_cache[1]
+        p12 = poses6_to_poses12(torch.stack([self.poses6[k] for k in window]))
+        self._pose_cache = None if optimize_poses else (key, p12.detach().contiguous())
+        return p12
 
     def _allreduce(self, t):
         if self.world > 1:
@@ -184,12 +209,11 @@ class MappingEngine:
         K = len(window)
         if injected is not None and "ray_point" in injected:
             ray_point = injected["ray_point"].to(self.dev)
-            ray_kf = torch.arange(K, device=self.dev, dtype=torch.int32).repeat_interleave(n_per_kf).contiguous()
+            ray_kf = self._window_consts(window, n_per_kf)["ray_kf"]
         else:
             ray_kf, ray_point = self._pick_rays(window, n_per_kf)
-        poses6 = torch.stack([self.poses6[k] for k in window])
-        poses12 = poses6_to_poses12(poses6)
-        counters = torch.zeros(2, device=self.dev, dtype=torch.int32)
+        poses12 = self._poses12(window, optimize_poses)
+        counters = self._counters.zero_()
         rays, depths, flags = ops.ray_build(self.points, ray_kf, ray_point, poses12.detach().contiguous(),
                                             cfg.shift, cfg.scale, cfg.ray_range, counters)
         self.launches += 1
@@ -227,7 +251,7 @@ class MappingEngine:
         cfg = self.cfg
         N, S = rays.shape[0], cfg.n_samples
         gscale = ops.default_grad_scale(N * self.world, S, cfg.los_lambda)
-        loss_acc = torch.zeros(4, device=self.dev, dtype=torch.float32)
+        loss_acc = self._loss_acc.zero_()
         self.d_params.zero_()
         d_rays = torch.zeros(N, ops.RAY_COLS, device=self.dev, dtype=torch.float32) if optimize_poses else None
         outs = []
