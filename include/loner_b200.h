@@ -142,6 +142,9 @@ int loner_ogm_grad(const float* rays, const float* z_vals, const float* depths, 
                    float scale, int32_t V, float* d_grid, void* stream);
 int loner_sgd_step(float* x, const float* g, int64_t count, float lr, void* stream);
 
+/* hardware probe (not on the product path): TMEM -> register bandwidth of tcgen05.ld */
+int loner_probe_tmem(int warps, int iters, int mode, long long* cycles, unsigned* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -167,18 +167,124 @@ __device__ __forceinline__ void set_bit_if_pos(uint32_t& bits, float v) {
       : "f"(v), "n"(1u << kBit));
 }
 
-// One 32-column slab of an epilogue: registers v[0..32) hold this row's fp32 accumulators for columns
-// [col0, col0+32); converts, (optionally) masks, and stores the four 16-byte chunks of the fp16 image.
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
+// One 32-column slab of an epilogue: `pack(i)` yields the packed half2 of this row's columns
+// (col0+i, col0+i+1).  The four 16-byte chunks go to the shared-memory tile image (`srow` = the
+// row's base inside the tile, or null) and/or straight to the image in HBM (`grow`, or null) as
+// two 32-byte sectors: chunks 2m and 2m+1 share a sector, swapped when the row's swizzle is odd.
+// xs = (row & 7) << 4.
 template <class F>
-__device__ __forceinline__ void store_slab(uint8_t* rowbase, uint32_t xs, int col0, F&& pack) {
+__device__ __forceinline__ void store_slab(uint8_t* srow, uint8_t* grow, uint32_t xs, int col0, F&& pack) {
+  const bool odd = (xs & 16u) != 0u;
 #pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
-    uint32_t hh[4];
+  for (int m = 0; m < 2; ++m) {
+    uint32_t a[4], b[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) hh[e] = pack(ch * 8 + 2 * e);
-    const int c0 = col0 + ch * 8;
-    const uint32_t off = (uint32_t)(c0 >> 6) * kBlk + ((((uint32_t)(c0 & 63) >> 3) << 4) ^ xs);
-    *reinterpret_cast<uint4*>(rowbase + off) = *reinterpret_cast<uint4*>(hh);
+    for (int e = 0; e < 4; ++e) { a[e] = pack(m * 16 + 2 * e); b[e] = pack(m * 16 + 8 + 2 * e); }
+    const int c0 = col0 + m * 16;                                        // first column of chunk 2m'
+    const uint32_t cb_off = (uint32_t)(c0 >> 6) * kBlk;
+    const uint32_t j0 = ((uint32_t)(c0 & 63) >> 3) << 4;                  // logical chunk byte offset (even chunk)
+    if (srow != nullptr) {
+      *reinterpret_cast<uint4*>(srow + cb_off + (j0 ^ xs)) = *reinterpret_cast<uint4*>(a);
+      *reinterpret_cast<uint4*>(srow + cb_off + ((j0 + 16u) ^ xs)) = *reinterpret_cast<uint4*>(b);
+    }
+    if (grow != nullptr) {
+      uint32_t w[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { w[e] = odd ? b[e] : a[e]; w[4 + e] = odd ? a[e] : b[e]; }
+      st_global_256(grow + cb_off + (j0 ^ (xs & 0x60u)), w);
+    }
+  }
+}
+
+// Half a slab: 16 columns = chunks (2m, 2m+1) = one 32-byte sector of the image.  hh[8] = packed half2.
+__device__ __forceinline__ void store16(uint8_t* srow, uint8_t* grow, uint32_t xs, int c0, const uint32_t (&hh)[8]) {
+  const uint32_t cb_off = (uint32_t)(c0 >> 6) * kBlk;
+  const uint32_t j0 = ((uint32_t)(c0 & 63) >> 3) << 4;
+  if (srow != nullptr) {
+    *reinterpret_cast<uint4*>(srow + cb_off + (j0 ^ xs)) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    *reinterpret_cast<uint4*>(srow + cb_off + ((j0 + 16u) ^ xs)) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+  }
+  if (grow != nullptr) {
+    const bool odd = (xs & 16u) != 0u;
+    uint32_t w[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { w[e] = odd ? hh[4 + e] : hh[e]; w[4 + e] = odd ? hh[e] : hh[4 + e]; }
+    st_global_256(grow + cb_off + (j0 ^ (xs & 0x60u)), w);
+  }
+}
+
+// Copies this thread's kCols columns of its row from the shared-memory tile image to the image in HBM
+// (32-byte sectors).  Runs AFTER the tile has been handed to the MMA warp, so that store back-pressure
+// from HBM never sits between an epilogue and the next layer's tensor-core work.
+template <int kCols>
+__device__ __forceinline__ void copy_out(const uint8_t* srow, uint8_t* grow, uint32_t xs, int col_begin) {
+  const bool odd = (xs & 16u) != 0u;
+#pragma unroll
+  for (int i = 0; i < kCols / 16; ++i) {
+    const int c0 = col_begin + i * 16;
+    const uint32_t cb_off = (uint32_t)(c0 >> 6) * kBlk;
+    const uint32_t j0 = ((uint32_t)(c0 & 63) >> 3) << 4;
+    const uint4 a = *reinterpret_cast<const uint4*>(srow + cb_off + (j0 ^ xs));
+    const uint4 b = *reinterpret_cast<const uint4*>(srow + cb_off + ((j0 + 16u) ^ xs));
+    const uint4 lo = odd ? b : a, hi = odd ? a : b;
+    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    st_global_256(grow + cb_off + (j0 ^ (xs & 0x60u)), w);
+  }
+}
+
+// Drains kCols accumulator columns of this thread's TMEM lane in 16-column loads, keeping the next
+// load in flight while `proc(i, v)` works on the current one (tcgen05.ld latency is ~300-450 clk,
+// tests/gpu_probe.py).
+template <int kCols, class Proc>
+__device__ __forceinline__ void drain_cols(uint32_t acc, Proc&& proc) {
+  uint32_t va[16], vb[16];
+  tmem_ld16(acc, va);
+  tmem_ld_wait16(va);
+#pragma unroll
+  for (int i = 0; i < kCols / 16; ++i) {
+    if (i & 1) {
+      if (i + 1 < kCols / 16) { tmem_ld16(acc + (i + 1) * 16, va); pin16(vb); }
+      proc(i, vb);
+      if (i + 1 < kCols / 16) tmem_ld_wait16(va);
+    } else {
+      if (i + 1 < kCols / 16) { tmem_ld16(acc + (i + 1) * 16, vb); pin16(va); }
+      proc(i, va);
+      if (i + 1 < kCols / 16) tmem_ld_wait16(vb);
+    }
+  }
+}
+
+// Per-tile inputs of a row, fetched one tile pair ahead of their use.
+struct RowIn {
+  float v[7];   // pos mode: x,y,z ; ray mode: z, o[3], d[3]
+};
+__device__ __forceinline__ RowIn load_row(const float* pos, const float* rays, const float* z, int S, int s_shift,
+                                          int64_t gs) {
+  RowIn r;
+  if (pos) {
+    r.v[0] = pos[gs * 3 + 0]; r.v[1] = pos[gs * 3 + 1]; r.v[2] = pos[gs * 3 + 2];
+    r.v[3] = r.v[4] = r.v[5] = r.v[6] = 0.f;
+  } else {
+    const int64_t ray = s_shift >= 0 ? (gs >> s_shift) : (int64_t)((uint64_t)gs / (uint32_t)S);
+    const float* R = rays + ray * LONER_RAY_COLS;
+    r.v[0] = z[gs];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) r.v[1 + a] = R[a];
+  }
+  return r;
+}
+// sample position in [0,1]^3:  (o + d z + 1) / 2     rendering_tcnn.py:241, nerf_tcnn.py:63
+__device__ __forceinline__ void row_pos01(bool pos_mode, const RowIn& r, float (&x)[3]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float p = pos_mode ? r.v[a] : __fadd_rn(r.v[1 + a], __fmul_rn(r.v[4 + a], r.v[0]));
+    x[a] = __fmul_rn(__fadd_rn(p, 1.0f), 0.5f);
   }
 }
 
@@ -190,29 +296,13 @@ struct FwdArgs {
   const float* rays;     // [n,13]
   const float* z;        // [n,S]
   int S;
+  int s_shift;           // log2(S) when S is a power of two, else -1
   int64_t P;
   int64_t tiles;
   float* sigma;          // [P]
   uint8_t* acts;         // activation stash or null
   uint8_t* masks;        // relu bit masks or null
 };
-
-// sample position in [0,1]^3 for global sample index gs (clamped by the caller)
-__device__ __forceinline__ void sample_pos01(const float* pos, const float* rays, const float* z, int S, int64_t gs,
-                                             float (&x)[3]) {
-  float p[3];
-  if (pos) {
-    p[0] = pos[gs * 3 + 0]; p[1] = pos[gs * 3 + 1]; p[2] = pos[gs * 3 + 2];
-  } else {
-    const int64_t ray = gs / S;
-    const float zz = z[gs];
-    const float* R = rays + ray * LONER_RAY_COLS;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) p[a] = __fadd_rn(R[a], __fmul_rn(R[3 + a], zz));      // rendering_tcnn.py:241
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) x[a] = __fmul_rn(__fadd_rn(p[a], 1.0f), 0.5f);           // nerf_tcnn.py:63
-}
 
 // sin/cos(pi * 2^f * x).  2^f * x is exact in fp32, and so is its reduction r to [-1, 1]; sin(pi r) and
 // cos(pi r) then come from the SFU (__sinf/__cosf on |pi r| <= pi: abs error < 1e-6, far below the
@@ -228,10 +318,11 @@ __device__ __forceinline__ void freq_pair(float x, float scale, float& s, float&
 // Writes encoded features [32*half, 32*half+32) of row r (column block 0 of `sA`): features
 // [0, 6F) are sin/cos pairs ordered [dim][freq][sin,cos], [6F, Epad) = 1.0 (tcnn pads the encoded
 // width to 16 with ones), rest 0.  (dim0, f0) = position of feature pair 16*half, precomputed.
-__device__ __forceinline__ void encode_row(uint8_t* sA, int r, int half, const float (&x)[3], const Net& net,
-                                           int dim0, int f0) {
+__device__ __forceinline__ void encode_row(uint8_t* sA, uint8_t* grow, int r, int half, const float (&x)[3],
+                                           const Net& net, int dim0, int f0) {
   int dim = dim0, f = f0;
   float scale = (float)(1 << f0);
+  uint32_t keep[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int cj = half * 4 + c;
@@ -253,6 +344,19 @@ __device__ __forceinline__ void encode_row(uint8_t* sA, int r, int half, const f
       if (f == net.F) { f = 0; scale = 1.0f; ++dim; }
     }
     *reinterpret_cast<uint4*>(sA + r * 128 + ((cj ^ (r & 7)) * 16)) = *reinterpret_cast<uint4*>(h);
+    if (grow != nullptr) {                 // chunks cj (even) and cj+1 share one 32-byte sector of the image
+      const uint32_t* hw = reinterpret_cast<const uint32_t*>(h);
+      if ((c & 1) == 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) keep[e] = hw[e];
+      } else {
+        const bool odd = (r & 1) != 0;
+        uint32_t w[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { w[e] = odd ? hw[e] : keep[e]; w[4 + e] = odd ? keep[e] : hw[e]; }
+        st_global_256(grow + (((cj - 1) ^ (r & 6)) * 16), w);
+      }
+    }
   }
 }
 
@@ -325,104 +429,93 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
     const int h = (e & 7) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const bool elected = ((e & 7) == 0) && lane == 0;
     uint8_t* sA = sm.tileA[t];
-    uint8_t* rowbase = sA + row * 128;
+    uint8_t* srow = sA + row * 128;
     const uint32_t xs = (uint32_t)(row & 7) << 4;
     constexpr int kCols = W / 2;                      // columns per thread
     const uint32_t acc = tmem + t * 256 + ((uint32_t)(q * 32) << 16) + h * kCols;
     float* part = sm.part + t * 128;
     uint32_t par_acc = 0;
     const int enc_dim0 = (16 * h) / net.F, enc_f0 = (16 * h) % net.F;
+    const bool pos_mode = a.pos != nullptr;
+    auto row_index = [&](int64_t pair) {
+      int64_t gs = (2 * pair + t) * kTile + row;
+      return gs < a.P ? gs : a.P - 1;
+    };
+    RowIn nxt = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, row_index(blockIdx.x));
     for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
       const int64_t tile = 2 * pair + t;
       const bool active = tile < a.tiles;
-      int64_t gs = tile * kTile + row;
+      const int64_t gs = tile * kTile + row;
       const bool in = active && gs < a.P;
-      if (gs >= a.P) gs = a.P - 1;
-      if (kStash) { if (elected) bulk_wait_read0(); group_bar(t); }
+      uint8_t* gtile = (kStash && active) ? a.acts + tile * act_tile_bytes(net) + row * 128 : nullptr;
+      if (kStash) group_bar(t);     // the other column-half's copy-out of the previous tile is done with sA
       {
         float x[3];
-        sample_pos01(a.pos, a.rays, a.z, a.S, gs, x);
-        encode_row(sA, row, h, x, net, enc_dim0, enc_f0);
+        row_pos01(pos_mode, nxt, x);
+        encode_row(sA, gtile, row, h, x, net, enc_dim0, enc_f0);
       }
       fence_async_smem();
       mbar_arrive(sm.a_ready[t]);
-      if (kStash) {
-        group_bar(t);
-        if (elected && active) { bulk_s2g(a.acts + tile * act_tile_bytes(net), smem_u32(sA), kBlk); bulk_commit(); }
-      }
+      if (pair + gridDim.x < pairs) nxt = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, row_index(pair + gridDim.x));
       for (int l = 0; l < net.L; ++l) {
         const bool last = (l == net.L - 1);
+        uint8_t* grow = gtile ? gtile + kBlk + (int64_t)l * kNb * kBlk : nullptr;
         mbar_wait(sm.acc_full[t], par_acc);
         par_acc ^= 1u;
         tc_fence_after();
-        if (kStash) { if (elected) bulk_wait_read0(); group_bar(t); }
-        float sig = 0.f;
+        float sig0 = 0.f, sig1 = 0.f;
         uint32_t mbits[kCols / 32];
 #pragma unroll
-        for (int it = 0; it < kCols / 32; ++it) {
-          uint32_t v[32];
-          tmem_ld32(acc + it * 32, v);
-          tmem_ld_wait();
-          const int col0 = h * kCols + it * 32;
+        for (int it = 0; it < kCols / 32; ++it) mbits[it] = 0u;
+        drain_cols<kCols>(acc, [&](int i, const uint32_t (&v)[16]) {
+          const int col0 = h * kCols + i * 16;
           if (kStash) {
-            uint32_t bits = 0u;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              // (unrolled with a compile-time bit index)
-              switch (i) {
-#define LONER_BIT(I) case I: set_bit_if_pos<I>(bits, __uint_as_float(v[I])); break;
-                LONER_BIT(0) LONER_BIT(1) LONER_BIT(2) LONER_BIT(3) LONER_BIT(4) LONER_BIT(5) LONER_BIT(6) LONER_BIT(7)
-                LONER_BIT(8) LONER_BIT(9) LONER_BIT(10) LONER_BIT(11) LONER_BIT(12) LONER_BIT(13) LONER_BIT(14)
-                LONER_BIT(15) LONER_BIT(16) LONER_BIT(17) LONER_BIT(18) LONER_BIT(19) LONER_BIT(20) LONER_BIT(21)
-                LONER_BIT(22) LONER_BIT(23) LONER_BIT(24) LONER_BIT(25) LONER_BIT(26) LONER_BIT(27) LONER_BIT(28)
-                LONER_BIT(29) LONER_BIT(30) LONER_BIT(31)
+            uint32_t b0 = 0u, b1 = 0u;      // two independent chains
+#define LONER_BIT(B, I) set_bit_if_pos<I>(B, __uint_as_float(v[I]));
+            LONER_BIT(b0, 0) LONER_BIT(b1, 8) LONER_BIT(b0, 1) LONER_BIT(b1, 9) LONER_BIT(b0, 2) LONER_BIT(b1, 10)
+            LONER_BIT(b0, 3) LONER_BIT(b1, 11) LONER_BIT(b0, 4) LONER_BIT(b1, 12) LONER_BIT(b0, 5) LONER_BIT(b1, 13)
+            LONER_BIT(b0, 6) LONER_BIT(b1, 14) LONER_BIT(b0, 7) LONER_BIT(b1, 15)
 #undef LONER_BIT
-              }
-            }
-            mbits[it] = bits;
+            mbits[i >> 1] |= (b0 | b1) << ((i & 1) * 16);
           }
-          if (!last || kStash) {
-            store_slab(rowbase, xs, col0, [&](int i0) {
-              return cvt_relu_h2(__uint_as_float(v[i0]), __uint_as_float(v[i0 + 1]));
-            });
-          }
+          uint32_t hh[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) hh[e] = cvt_relu_h2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+          if (!last || kStash) store16(srow, nullptr, xs, col0, hh);
           if (last) {
 #pragma unroll
-            for (int i0 = 0; i0 < 32; i0 += 2) {
-              const uint32_t hh = cvt_relu_h2(__uint_as_float(v[i0]), __uint_as_float(v[i0 + 1]));
-              const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&hh));
-              const float2 w2 = *reinterpret_cast<const float2*>(sm.wout + col0 + i0);
-              sig = fmaf(r2.x, w2.x, sig);
-              sig = fmaf(r2.y, w2.y, sig);
+            for (int e = 0; e < 8; ++e) {
+              const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&hh[e]));
+              const float2 w2 = *reinterpret_cast<const float2*>(sm.wout + col0 + 2 * e);
+              sig0 = fmaf(r2.x, w2.x, sig0);
+              sig1 = fmaf(r2.y, w2.y, sig1);
             }
           }
-        }
+        });
+        const float sig = sig0 + sig1;
         tc_fence_before();
         if (kStash && active) {
           uint32_t* mrow = reinterpret_cast<uint32_t*>(a.masks + tile * mask_tile_bytes(net)) +
                            ((int64_t)l * kTile + row) * (W / 32) + h * (kCols / 32);
+          if (kCols / 32 == 4) {
+            *reinterpret_cast<uint4*>(mrow) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
+          } else {
 #pragma unroll
-          for (int it = 0; it < kCols / 32; ++it) mrow[it] = mbits[it];
+            for (int it = 0; it < kCols / 32; ++it) mrow[it] = mbits[it];
+          }
         }
         if (!last) {
           fence_async_smem();
           mbar_arrive(sm.a_ready[t]);
         } else {
           if (h == 1) part[row] = sig;
-          if (kStash) fence_async_smem();
+          group_bar(t);
+          if (h == 0 && in) a.sigma[gs] = sig + part[row];
         }
-        if (kStash || last) group_bar(t);
-        if (last && h == 0 && in) a.sigma[gs] = sig + part[row];
-        if (kStash && elected && active) {
-          bulk_s2g(a.acts + tile * act_tile_bytes(net) + kBlk + (int64_t)l * kNb * kBlk, smem_u32(sA),
-                   (uint32_t)(kNb * kBlk));
-          bulk_commit();
-        }
+        if (kStash && grow != nullptr) copy_out<kCols>(srow, grow, xs, h * kCols);
       }
     }
-    if (kStash && elected) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -438,6 +531,7 @@ struct BwdArgs {
   const float* rays;
   const float* z;
   int S;
+  int s_shift;
   int64_t P;
   int64_t tiles;
   const float* d_sigma;
@@ -512,23 +606,24 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
     const int h = (e & 7) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const bool elected = ((e & 7) == 0) && lane == 0;
     uint8_t* sG = sm.tileA[t];
-    uint8_t* rowbase = sG + row * 128;
+    uint8_t* srow = sG + row * 128;
     const uint32_t xs = (uint32_t)(row & 7) << 4;
     constexpr int kCols = W / 2;
     const uint32_t acc_row = tmem + t * 256 + ((uint32_t)(q * 32) << 16);
     const uint32_t acc = acc_row + h * kCols;
     uint32_t par_acc = 0;
     constexpr int kWords = W / 32;
+    const bool pos_mode = a.pos != nullptr;
     for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
       const int64_t tile = 2 * pair + t;
       const bool active = tile < a.tiles;
       const int64_t gs = tile * kTile + row;
       const bool in = active && gs < a.P;
       const uint32_t* mtile = reinterpret_cast<const uint32_t*>(a.masks + (active ? tile : 0) * mask_tile_bytes(net));
-      if (elected) bulk_wait_read0();
-      group_bar(t);
+      uint8_t* gtile = active ? a.dz + tile * dz_tile_bytes(net) + row * 128 : nullptr;
+      RowIn rin;
+      if (want_dx && h == 0) rin = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, in ? gs : a.P - 1);
       {  // dZ_L = d_sigma * w_out * relu'(Z_L)
         const float ds = in ? a.d_sigma[gs] * a.gscale : 0.f;
         const uint32_t* mrow = mtile + ((int64_t)(net.L - 1) * kTile + row) * kWords + h * (kCols / 32);
@@ -536,7 +631,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
         for (int it = 0; it < kCols / 32; ++it) {
           const uint32_t bits = mrow[it];
           const int col0 = h * kCols + it * 32;
-          store_slab(rowbase, xs, col0, [&](int i0) {
+          store_slab(srow, nullptr, xs, col0, [&](int i0) {
             const float2 w2 = *reinterpret_cast<const float2*>(sm.wout + col0 + i0);
             const float g0 = ((bits >> i0) & 1u) ? ds * w2.x : 0.f;
             const float g1 = ((bits >> (i0 + 1)) & 1u) ? ds * w2.y : 0.f;
@@ -546,46 +641,40 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
       }
       fence_async_smem();
       mbar_arrive(sm.a_ready[t]);
-      group_bar(t);
-      if (elected && active) {
-        bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(net.L - 1) * kNb * kBlk, smem_u32(sG),
-                 (uint32_t)(kNb * kBlk));
-        bulk_commit();
-      }
+      if (gtile) copy_out<kCols>(srow, gtile + (int64_t)(net.L - 1) * kNb * kBlk, xs, h * kCols);
       for (int l = net.L - 1; l >= l_lo; --l) {
         mbar_wait(sm.acc_full[t], par_acc);
         par_acc ^= 1u;
         tc_fence_after();
-        if (elected) bulk_wait_read0();
-        group_bar(t);
         if (l >= 1) {
-          // dZ_l = dA_l * relu'(Z_l)  -> fp16 image in sG (next GEMM's A operand and wgrad's B operand)
+          // dZ_l = dA_l * relu'(Z_l)  -> fp16 image (next GEMM's A operand in smem, wgrad's B operand in HBM)
           const uint32_t* mrow = mtile + ((int64_t)(l - 1) * kTile + row) * kWords + h * (kCols / 32);
+          uint8_t* grow = gtile ? gtile + (int64_t)(l - 1) * kNb * kBlk : nullptr;
+          const bool feeds_gemm = (l - 1 >= l_lo);
+          uint32_t mw[kCols / 32];
 #pragma unroll
-          for (int it = 0; it < kCols / 32; ++it) {
-            uint32_t v[32];
-            tmem_ld32(acc + it * 32, v);
-            const uint32_t bits = mrow[it];
-            tmem_ld_wait();
-            store_slab(rowbase, xs, h * kCols + it * 32, [&](int i0) {
-              const float g0 = ((bits >> i0) & 1u) ? __uint_as_float(v[i0]) : 0.f;
-              const float g1 = ((bits >> (i0 + 1)) & 1u) ? __uint_as_float(v[i0 + 1]) : 0.f;
-              return cvt_sat_h2(g0, g1);
-            });
-          }
+          for (int it = 0; it < kCols / 32; ++it) mw[it] = mrow[it];
+          drain_cols<kCols>(acc, [&](int i, const uint32_t (&v)[16]) {
+            const uint32_t bits = mw[i >> 1] >> ((i & 1) * 16);
+            uint32_t hh[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float g0 = ((bits >> (2 * e)) & 1u) ? __uint_as_float(v[2 * e]) : 0.f;
+              const float g1 = ((bits >> (2 * e + 1)) & 1u) ? __uint_as_float(v[2 * e + 1]) : 0.f;
+              hh[e] = cvt_sat_h2(g0, g1);
+            }
+            store16(srow, nullptr, xs, h * kCols + i * 16, hh);
+          });
           tc_fence_before();
-          fence_async_smem();
-          if (l - 1 >= l_lo) mbar_arrive(sm.a_ready[t]);
-          group_bar(t);
-          if (elected && active) {
-            bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(l - 1) * kNb * kBlk, smem_u32(sG),
-                     (uint32_t)(kNb * kBlk));
-            bulk_commit();
+          if (feeds_gemm) {
+            fence_async_smem();
+            mbar_arrive(sm.a_ready[t]);
           }
+          if (grow) copy_out<kCols>(srow, grow, xs, h * kCols);
         } else if (h == 0) {
           // l == 0: dEnc [128 x Epad] -> d_pos through the sin/cos encoding (lower-half warps only)
           float x[3];
-          sample_pos01(a.pos, a.rays, a.z, a.S, in ? gs : a.P - 1, x);
+          row_pos01(pos_mode, rin, x);
           float dx[3] = {0.f, 0.f, 0.f};
           int dim = 0, f = 0;
           float scale = 1.0f;
@@ -597,10 +686,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
             for (int pq = 0; pq < 16; ++pq) {
               if (dim < 3) {
                 const float xv = dim == 0 ? x[0] : (dim == 1 ? x[1] : x[2]);
-                float s, c;
-                freq_pair(xv, scale, s, c);
+                float sn, cs;
+                freq_pair(xv, scale, sn, cs);
                 // d/dx sin(pi 2^f x) = pi 2^f cos, d/dx cos = -pi 2^f sin
-                const float g = (__uint_as_float(v[2 * pq]) * c - __uint_as_float(v[2 * pq + 1]) * s) *
+                const float g = (__uint_as_float(v[2 * pq]) * cs - __uint_as_float(v[2 * pq + 1]) * sn) *
                                 (3.14159265358979323846f * scale);
                 if (dim == 0) dx[0] += g; else if (dim == 1) dx[1] += g; else dx[2] += g;
               }
@@ -615,10 +704,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
             a.d_pos[gs * 3 + 1] = dx[1] * inv;
             a.d_pos[gs * 3 + 2] = dx[2] * inv;
           }
+        } else {
+          tc_fence_before();
         }
       }
     }
-    if (elected) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -918,6 +1008,7 @@ extern "C" int loner_mlp_fwd(const loner_net_t* n, const void* packed, const flo
   if (P == 0) return LONER_OK;
   FwdArgs a;
   a.net = net; a.packed = (const uint8_t*)packed; a.pos = pos; a.rays = rays; a.z = z_vals; a.S = S; a.P = P;
+  a.s_shift = (S > 0 && (S & (S - 1)) == 0) ? __builtin_ctz((unsigned)S) : -1;
   a.tiles = n_tiles(P); a.sigma = sigma; a.acts = (uint8_t*)acts;
   a.masks = acts ? (uint8_t*)acts + a.tiles * act_tile_bytes(net) : nullptr;
   const int sms = device_sm_count();
@@ -951,6 +1042,7 @@ extern "C" int loner_mlp_dgrad(const loner_net_t* n, const void* packed, const f
   const int sms = device_sm_count();
   BwdArgs b;
   b.net = net; b.packed = (const uint8_t*)packed; b.pos = pos; b.rays = rays; b.z = z_vals; b.S = S; b.P = P;
+  b.s_shift = (S > 0 && (S & (S - 1)) == 0) ? __builtin_ctz((unsigned)S) : -1;
   b.tiles = tiles; b.d_sigma = d_sigma; b.masks = (const uint8_t*)acts + tiles * act_tile_bytes(net);
   b.dz = (uint8_t*)scratch; b.gscale = grad_scale; b.d_pos = d_pos;
   const int64_t pairs = (tiles + 1) / 2;

@@ -51,3 +51,9 @@ print(json.dumps({k: round(v, 4) for k, v in res.items()}))
 print("fwd TF/s stash %.0f infer %.0f | stash GB %.2f dz GB %.2f" % (
     f_fwd * P / res["mlp_fwd_stash"] / 1e9, f_fwd * P / res["mlp_fwd_infer"] / 1e9,
     net.act_bytes(P) / 1e9, (net.bwd_scratch_bytes(P)) / 1e9))
+buf = torch.empty(10 * 1024**3 // 4, device=dev, dtype=torch.float32)
+t = timeit(lambda: buf.fill_(1.0))
+print("pure write (fill_) 10 GiB: %.3f ms -> %.2f TB/s" % (t, 10 * 1024**3 / t / 1e9))
+src = torch.empty(5 * 1024**3 // 4, device=dev, dtype=torch.float32)
+t = timeit(lambda: buf[: src.numel()].copy_(src))
+print("copy 5 GiB -> 5 GiB: %.3f ms -> %.2f TB/s (read+write)" % (t, 10 * 1024**3 / t / 1e9))
