@@ -167,6 +167,14 @@ __device__ __forceinline__ void set_bit_if_pos(uint32_t& bits, float v) {
       : "f"(v), "n"(1u << kBit));
 }
 
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
                "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
@@ -179,7 +187,7 @@ __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
 // two 32-byte sectors: chunks 2m and 2m+1 share a sector, swapped when the row's swizzle is odd.
 // xs = (row & 7) << 4.
 template <class F>
-__device__ __forceinline__ void store_slab(uint8_t* srow, uint8_t* grow, uint32_t xs, int col0, F&& pack) {
+__device__ __forceinline__ void store_slab(uint32_t srow, uint8_t* grow, uint32_t xs, int col0, F&& pack) {
   const bool odd = (xs & 16u) != 0u;
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
@@ -189,9 +197,9 @@ __device__ __forceinline__ void store_slab(uint8_t* srow, uint8_t* grow, uint32_
     const int c0 = col0 + m * 16;                                        // first column of chunk 2m'
     const uint32_t cb_off = (uint32_t)(c0 >> 6) * kBlk;
     const uint32_t j0 = ((uint32_t)(c0 & 63) >> 3) << 4;                  // logical chunk byte offset (even chunk)
-    if (srow != nullptr) {
-      *reinterpret_cast<uint4*>(srow + cb_off + (j0 ^ xs)) = *reinterpret_cast<uint4*>(a);
-      *reinterpret_cast<uint4*>(srow + cb_off + ((j0 + 16u) ^ xs)) = *reinterpret_cast<uint4*>(b);
+    if (srow != 0u) {
+      sts128(srow + cb_off + (j0 ^ xs), a[0], a[1], a[2], a[3]);
+      sts128(srow + cb_off + ((j0 + 16u) ^ xs), b[0], b[1], b[2], b[3]);
     }
     if (grow != nullptr) {
       uint32_t w[8];
@@ -203,12 +211,12 @@ __device__ __forceinline__ void store_slab(uint8_t* srow, uint8_t* grow, uint32_
 }
 
 // Half a slab: 16 columns = chunks (2m, 2m+1) = one 32-byte sector of the image.  hh[8] = packed half2.
-__device__ __forceinline__ void store16(uint8_t* srow, uint8_t* grow, uint32_t xs, int c0, const uint32_t (&hh)[8]) {
+__device__ __forceinline__ void store16(uint32_t srow, uint8_t* grow, uint32_t xs, int c0, const uint32_t (&hh)[8]) {
   const uint32_t cb_off = (uint32_t)(c0 >> 6) * kBlk;
   const uint32_t j0 = ((uint32_t)(c0 & 63) >> 3) << 4;
-  if (srow != nullptr) {
-    *reinterpret_cast<uint4*>(srow + cb_off + (j0 ^ xs)) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-    *reinterpret_cast<uint4*>(srow + cb_off + ((j0 + 16u) ^ xs)) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+  if (srow != 0u) {
+    sts128(srow + cb_off + (j0 ^ xs), hh[0], hh[1], hh[2], hh[3]);
+    sts128(srow + cb_off + ((j0 + 16u) ^ xs), hh[4], hh[5], hh[6], hh[7]);
   }
   if (grow != nullptr) {
     const bool odd = (xs & 16u) != 0u;
@@ -223,15 +231,15 @@ __device__ __forceinline__ void store16(uint8_t* srow, uint8_t* grow, uint32_t x
 // (32-byte sectors).  Runs AFTER the tile has been handed to the MMA warp, so that store back-pressure
 // from HBM never sits between an epilogue and the next layer's tensor-core work.
 template <int kCols>
-__device__ __forceinline__ void copy_out(const uint8_t* srow, uint8_t* grow, uint32_t xs, int col_begin) {
+__device__ __forceinline__ void copy_out(uint32_t srow, uint8_t* grow, uint32_t xs, int col_begin) {
   const bool odd = (xs & 16u) != 0u;
 #pragma unroll
   for (int i = 0; i < kCols / 16; ++i) {
     const int c0 = col_begin + i * 16;
     const uint32_t cb_off = (uint32_t)(c0 >> 6) * kBlk;
     const uint32_t j0 = ((uint32_t)(c0 & 63) >> 3) << 4;
-    const uint4 a = *reinterpret_cast<const uint4*>(srow + cb_off + (j0 ^ xs));
-    const uint4 b = *reinterpret_cast<const uint4*>(srow + cb_off + ((j0 + 16u) ^ xs));
+    const uint4 a = lds128(srow + cb_off + (j0 ^ xs));
+    const uint4 b = lds128(srow + cb_off + ((j0 + 16u) ^ xs));
     const uint4 lo = odd ? b : a, hi = odd ? a : b;
     const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     st_global_256(grow + cb_off + (j0 ^ (xs & 0x60u)), w);
@@ -264,18 +272,23 @@ __device__ __forceinline__ void drain_cols(uint32_t acc, Proc&& proc) {
 struct RowIn {
   float v[7];   // pos mode: x,y,z ; ray mode: z, o[3], d[3]
 };
+__device__ __forceinline__ float ldg_now(const float* p) {   // volatile: issued where written, not sunk to its use
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ RowIn load_row(const float* pos, const float* rays, const float* z, int S, int s_shift,
                                           int64_t gs) {
   RowIn r;
   if (pos) {
-    r.v[0] = pos[gs * 3 + 0]; r.v[1] = pos[gs * 3 + 1]; r.v[2] = pos[gs * 3 + 2];
+    r.v[0] = ldg_now(pos + gs * 3 + 0); r.v[1] = ldg_now(pos + gs * 3 + 1); r.v[2] = ldg_now(pos + gs * 3 + 2);
     r.v[3] = r.v[4] = r.v[5] = r.v[6] = 0.f;
   } else {
     const int64_t ray = s_shift >= 0 ? (gs >> s_shift) : (int64_t)((uint64_t)gs / (uint32_t)S);
     const float* R = rays + ray * LONER_RAY_COLS;
-    r.v[0] = z[gs];
+    r.v[0] = ldg_now(z + gs);
 #pragma unroll
-    for (int a = 0; a < 6; ++a) r.v[1 + a] = R[a];
+    for (int a = 0; a < 6; ++a) r.v[1 + a] = ldg_now(R + a);
   }
   return r;
 }
@@ -318,7 +331,7 @@ __device__ __forceinline__ void freq_pair(float x, float scale, float& s, float&
 // Writes encoded features [32*half, 32*half+32) of row r (column block 0 of `sA`): features
 // [0, 6F) are sin/cos pairs ordered [dim][freq][sin,cos], [6F, Epad) = 1.0 (tcnn pads the encoded
 // width to 16 with ones), rest 0.  (dim0, f0) = position of feature pair 16*half, precomputed.
-__device__ __forceinline__ void encode_row(uint8_t* sA, uint8_t* grow, int r, int half, const float (&x)[3],
+__device__ __forceinline__ void encode_row(uint32_t sA, uint8_t* grow, int r, int half, const float (&x)[3],
                                            const Net& net, int dim0, int f0) {
   int dim = dim0, f = f0;
   float scale = (float)(1 << f0);
@@ -343,7 +356,10 @@ __device__ __forceinline__ void encode_row(uint8_t* sA, uint8_t* grow, int r, in
       ++f; scale *= 2.0f;
       if (f == net.F) { f = 0; scale = 1.0f; ++dim; }
     }
-    *reinterpret_cast<uint4*>(sA + r * 128 + ((cj ^ (r & 7)) * 16)) = *reinterpret_cast<uint4*>(h);
+    {
+      const uint32_t* hw0 = reinterpret_cast<const uint32_t*>(h);
+      sts128(sA + r * 128 + ((cj ^ (r & 7)) * 16), hw0[0], hw0[1], hw0[2], hw0[3]);
+    }
     if (grow != nullptr) {                 // chunks cj (even) and cj+1 share one 32-byte sector of the image
       const uint32_t* hw = reinterpret_cast<const uint32_t*>(h);
       if ((c & 1) == 0) {
@@ -429,8 +445,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
     const int h = (e & 7) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    uint8_t* sA = sm.tileA[t];
-    uint8_t* srow = sA + row * 128;
+    const uint32_t sA = smem_u32(sm.tileA[t]);
+    const uint32_t srow = sA + row * 128;
     const uint32_t xs = (uint32_t)(row & 7) << 4;
     constexpr int kCols = W / 2;                      // columns per thread
     const uint32_t acc = tmem + t * 256 + ((uint32_t)(q * 32) << 16) + h * kCols;
@@ -606,8 +622,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
     const int h = (e & 7) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    uint8_t* sG = sm.tileA[t];
-    uint8_t* srow = sG + row * 128;
+    const uint32_t srow = smem_u32(sm.tileA[t]) + row * 128;
     const uint32_t xs = (uint32_t)(row & 7) << 4;
     constexpr int kCols = W / 2;
     const uint32_t acc_row = tmem + t * 256 + ((uint32_t)(q * 32) << 16);

@@ -1,0 +1,35 @@
+"""models.ray_sampling of the reference (/root/reference/src/models/ray_sampling.py) on the fused
+sampler kernels (loner_sample_uniform / loner_sample_ogm)."""
+import torch
+
+from loner_b200 import ops
+
+
+class UniformRaySampler():
+    def __init__(self):
+        self._calls = 0
+        self.seed = 0
+
+    def get_samples(self, rays, N_samples, perturb):
+        self._calls += 1
+        with torch.no_grad():
+            return ops.sample_uniform(rays.detach().contiguous().float(), N_samples, perturb, None,
+                                      seed=self.seed * 1000003 + self._calls)
+
+
+class OccGridRaySampler():
+    def __init__(self):
+        self._occ_gamma = None
+        self._calls = 0
+        self.seed = 0
+
+    def update_occ_grid(self, occ_gamma):
+        self._occ_gamma = occ_gamma
+
+    def get_samples(self, rays, N_samples, perturb):
+        self._calls += 1
+        g = self._occ_gamma
+        grid = g.detach().reshape(g.shape[-3:]).contiguous().float()
+        with torch.no_grad():
+            return ops.sample_ogm(rays.detach().contiguous().float(), grid, N_samples, perturb, None, None,
+                                  seed=self.seed * 1000003 + self._calls)

@@ -21,7 +21,7 @@ from dataclasses import dataclass, field
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import ops, parallel
 
 
 def axis_angle_to_matrix(aa: torch.Tensor) -> torch.Tensor:
@@ -119,6 +119,9 @@ class MappingEngine:
         self.timers = None          # name -> [(start_event, end_event)] when bench.py profiles sections
         self._wcache = {}
         self._pose_cache = None
+        self._exchange = None
+        self._z_all = None
+        self._last_d_poses12 = None
         self._counters = torch.zeros(2, device=self.dev, dtype=torch.int32)
         self._loss_acc = torch.zeros(4, device=self.dev, dtype=torch.float32)
 
@@ -196,40 +199,40 @@ class MappingEngine:
         self._pose_cache = None if optimize_poses else (key, p12.detach().contiguous())
         return p12
 
-    def _allreduce(self, t):
-        if self.world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-
     # ---------------------------------------------------------------- the step
     def step(self, window, n_per_kf, optimize_poses=False, injected=None, want_outputs=False):
         """One mapping iteration over `window` (keyframe ids), n_per_kf rays per keyframe on THIS rank.
         injected: optional dict(ray_point, u1, u2, noise) for parity tests.  Returns the loss (0-dim
         device tensor, no host sync)."""
         cfg = self.cfg
-        K = len(window)
         if injected is not None and "ray_point" in injected:
             ray_point = injected["ray_point"].to(self.dev)
             ray_kf = self._window_consts(window, n_per_kf)["ray_kf"]
         else:
             ray_kf, ray_point = self._pick_rays(window, n_per_kf)
         poses12 = self._poses12(window, optimize_poses)
+        p12 = poses12.detach().contiguous()
         counters = self._counters.zero_()
-        rays, depths, flags = ops.ray_build(self.points, ray_kf, ray_point, poses12.detach().contiguous(),
-                                            cfg.shift, cfg.scale, cfg.ray_range, counters)
+        rays, depths, flags = ops.ray_build(self.points, ray_kf, ray_point, p12, cfg.shift, cfg.scale,
+                                            cfg.ray_range, counters)
         self.launches += 1
-        self._allreduce(counters)
-        out = self._step_on_rays(rays, depths, flags, counters, optimize_poses, injected, want_outputs)
-        if optimize_poses and out["d_rays"] is not None:
-            d_poses12 = ops.ray_build_bwd(self.points, ray_kf, ray_point, poses12.detach().contiguous(), cfg.shift,
-                                          cfg.scale, cfg.ray_range, out["d_rays"])
+        parallel.allreduce_counts(counters)
+        loss_acc, d_rays = self._forward_backward(rays, depths, flags, counters, optimize_poses, injected,
+                                                  want_outputs)
+        d_poses12 = None
+        if optimize_poses:
+            d_poses12 = ops.ray_build_bwd(self.points, ray_kf, ray_point, p12, cfg.shift, cfg.scale, cfg.ray_range,
+                                          d_rays)
             self.launches += 1
-            self._allreduce(d_poses12)
+        loss = self._exchange_and_update(loss_acc, counters, d_poses12)
+        if d_poses12 is not None:
             for p in self.poses6:
                 p.grad = None
-            poses12.backward(d_poses12)
+            poses12.backward(self._last_d_poses12)
             if self.pose_opt is not None:
                 self.pose_opt.step()
-        return out["loss"]
+        self._occupancy_update(rays, depths)
+        return loss
 
     def step_from_host(self, rays_host, depths_host):
         """The reference-facing call (Optimizer.compute_loss + backward + Adam, optimizer.py:340-380)
@@ -243,11 +246,13 @@ class MappingEngine:
         opaque = valid & (depths > 0) & ~(depths > far)
         flags = (valid.to(torch.uint8) + 2 * opaque.to(torch.uint8)).contiguous()
         counters = torch.stack([valid.sum(), opaque.sum()]).to(torch.int32)
-        self._allreduce(counters)
-        out = self._step_on_rays(rays, depths, flags, counters, False, None, False)
-        return float(out["loss"].item())
+        parallel.allreduce_counts(counters)
+        loss_acc, _ = self._forward_backward(rays, depths, flags, counters, False, None, False)
+        loss = self._exchange_and_update(loss_acc, counters, None)
+        self._occupancy_update(rays, depths)
+        return float(loss.item())
 
-    def _step_on_rays(self, rays, depths, flags, counters, optimize_poses, injected, want_outputs):
+    def _forward_backward(self, rays, depths, flags, counters, optimize_poses, injected, want_outputs):
         cfg = self.cfg
         N, S = rays.shape[0], cfg.n_samples
         gscale = ops.default_grad_scale(N * self.world, S, cfg.los_lambda)
@@ -256,12 +261,12 @@ class MappingEngine:
         d_rays = torch.zeros(N, ops.RAY_COLS, device=self.dev, dtype=torch.float32) if optimize_poses else None
         outs = []
         seed = (cfg.seed * 1000003 + self.global_step * 7919 + 13) & 0x7FFFFFFFFFFF
-        z_all = [] if (self.global_step % cfg.occ_every == 0 and cfg.sampler == "OGM") else None
+        keep_z = self.global_step % cfg.occ_every == 0 and cfg.sampler == "OGM"
+        self._z_all = [] if keep_z else None
         for c0 in range(0, N, cfg.chunk_rays):
             c1 = min(N, c0 + cfg.chunk_rays)
             r, dpt, fl = rays[c0:c1], depths[c0:c1], flags[c0:c1]
-            n = c1 - c0
-            P = n * S
+            P = (c1 - c0) * S
             inj = injected or {}
             u1 = inj["u1"][c0:c1].contiguous().to(self.dev) if "u1" in inj else None
             u2 = inj["u2"][c0:c1].contiguous().to(self.dev) if "u2" in inj else None
@@ -288,40 +293,55 @@ class MappingEngine:
             if optimize_poses:
                 ops.points_bwd(d_pos, z, d_rays[c0:c1])
                 self.launches += 1
-            if z_all is not None:
-                z_all.append(z)
+            if keep_z:
+                self._z_all.append(z)
             if want_outputs:
                 res["z_vals"] = z
                 res["sigma"] = sigma
                 outs.append(res)
-        # gradient exchange: one flat buffer (MLP grads | 4 loss sums)
+        self.last = dict(outs=outs, rays=rays, depths=depths, flags=flags)
+        return loss_acc, d_rays
+
+    def _exchange_and_update(self, loss_acc, counters, d_poses12):
+        """ONE all-reduce of [MLP grads | pose grads | 4 loss sums], then Adam + fp16 repack."""
+        cfg = self.cfg
         if self.world > 1:
-            flat = torch.cat([self.d_params, loss_acc])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            self.d_params.copy_(flat[:-4])
-            loss_acc = flat[-4:]
+            shapes = [tuple(self.d_params.shape), tuple(d_poses12.shape) if d_poses12 is not None else (0,), (4,)]
+            if self._exchange is None or self._exchange.shapes != shapes:
+                self._exchange = parallel.FlatExchange(shapes, self.dev)
+            g, gp, acc = self._exchange.reduce([self.d_params,
+                                                d_poses12 if d_poses12 is not None else self.d_params[:0], loss_acc])
+            self.d_params.copy_(g)
+            loss_acc = acc.clone()
+            if d_poses12 is not None:
+                d_poses12 = gp.clone()
+        self._last_d_poses12 = d_poses12
         self.adam_t += 1
         with self._sec("adam_pack"):
             ops.adam_step(self.params, self.d_params, self.exp_avg, self.exp_avg_sq, self.adam_t, cfg.lrate_sigma_mlp)
             ops.mlp_pack(self.net, self.params, self.packed)
         self.launches += 2
-        # occupancy grid every occ_every global steps (optimizer.py:382-384)
-        if z_all is not None:
+        cnt = counters.to(torch.float32)
+        loss = (cfg.depthloss_lambda * loss_acc[0] / cnt[1] + cfg.los_lambda * loss_acc[1] / (cnt[0] * cfg.n_samples)
+                + loss_acc[2] / cnt[1])
+        self.last.update(loss_acc=loss_acc, counters=counters, depth_eps=loss_acc[3] / cnt[0])
+        return loss
+
+    def _occupancy_update(self, rays, depths):
+        """Every occ_every global steps (optimizer.py:382-384): scatter the pseudo-gradient, SGD step."""
+        cfg = self.cfg
+        if self._z_all is not None:
             self.d_grid.zero_()
-            for ci, c0 in enumerate(range(0, N, cfg.chunk_rays)):
-                c1 = min(N, c0 + cfg.chunk_rays)
-                ops.ogm_grad(rays[c0:c1], z_all[ci], depths[c0:c1], cfg.scale, cfg.voxel_size, self.d_grid)
+            for ci, c0 in enumerate(range(0, rays.shape[0], cfg.chunk_rays)):
+                c1 = min(rays.shape[0], c0 + cfg.chunk_rays)
+                ops.ogm_grad(rays[c0:c1], self._z_all[ci], depths[c0:c1], cfg.scale, cfg.voxel_size, self.d_grid)
                 self.launches += 1
-            self._allreduce(self.d_grid)
+            if self.world > 1:
+                dist.all_reduce(self.d_grid, op=dist.ReduceOp.SUM)
             ops.sgd_step(self.grid, self.d_grid, cfg.occ_lr)
             self.launches += 1
+            self._z_all = None
         self.global_step += 1
-        cnt = counters.to(torch.float32)
-        loss = (cfg.depthloss_lambda * loss_acc[0] / cnt[1] + cfg.los_lambda * loss_acc[1] / (cnt[0] * S)
-                + loss_acc[2] / cnt[1])
-        self.last = dict(loss_acc=loss_acc, counters=counters, depth_eps=loss_acc[3] / cnt[0], outs=outs,
-                         rays=rays, depths=depths, flags=flags)
-        return dict(loss=loss, d_rays=d_rays)
 
     # ---------------------------------------------------------------- inference (test mode)
     @torch.no_grad()

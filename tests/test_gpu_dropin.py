@@ -1,0 +1,102 @@
+"""GPU: the drop-in `models.*` API (Model.forward -> dict, autograd to params and rays) against the
+oracle on a deterministic configuration (perturb = 0, raw_noise_std = 0, uniform sampler)."""
+import importlib
+import sys
+import types
+
+import pytest
+import torch
+
+from golden_util import Case
+from gpu_util import norm_relerr, relerr
+from oracle import loner_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+class _Cfg(dict):
+    def __getattr__(self, k):
+        v = self[k]
+        return _Cfg(v) if isinstance(v, dict) else v
+
+
+def _model_cfg(c, S):
+    return _Cfg(model_type="nerf_decoupled", num_colors=3, ray_range=list(c.ray_range),
+                nerf_config=dict(enable_view_dependence=True,
+                                 pos_encoding_sigma=dict(otype="Frequency", n_frequencies=10),
+                                 sigma_network=dict(otype="CutlassMLP", activation="ReLU", output_activation="None",
+                                                    n_neurons=c.W, n_hidden_layers=c.L),
+                                 pos_encoding_intensity=dict(otype="HashGrid"), dir_encoding_intensity=dict(otype="SphericalHarmonics"),
+                                 intensity_network=dict(otype="FullyFusedMLP")),
+                render=dict(N_samples_train=S, N_samples_test=S, retraw=True, perturb=0.0, white_bkgd=False,
+                            raw_noise_std=0.0, chunk=100, netchunk=0))
+
+
+def test_model_forward_backward_matches_oracle():
+    from loner_b200 import dropin
+    path = dropin.install()
+    try:
+        mt = importlib.import_module("models.model_tcnn")
+        rs = importlib.import_module("models.ray_sampling")
+        ls = importlib.import_module("models.losses")
+        c = Case("kf2_4x256_fp16")
+        S = 128
+        model = mt.Model(_model_cfg(c, S)).cuda()
+        with torch.no_grad():
+            model.nerf_model._model_sigma.params.copy_(c.params)
+        sampler = rs.UniformRaySampler()
+        rays_cpu = torch.from_numpy(c.g["rays"])
+        depths = torch.from_numpy(c.g["depths"])
+        rays = rays_cpu.cuda().requires_grad_(True)
+        model.freeze_rgb_head(True)
+        assert len(model.get_sigma_parameters()) == 1 and len(model.get_rgb_parameters()) == 0
+        res = model(rays, sampler, c.scale, camera=False, return_variance=True)
+        assert set(res) == {"rgb_fine", "depth_fine", "weights_fine", "opacity_fine", "variance", "samples_fine",
+                            "points_fine"}
+        n = rays.shape[0]
+        assert res["weights_fine"].shape == (n, S) and res["points_fine"].shape == (n, S, 3)
+        # the reference's loss arithmetic (optimizer.py:470-580) with torch ops on the device tensors
+        s = res["samples_fine"] * c.scale
+        G = (depths.cuda() * c.scale)[:, None]
+        w = res["weights_fine"]
+        eps = torch.full((n, 1), 1.5, device="cuda")
+        w_gt = ls.get_weights_gt(s, G, eps)
+        loss = (0.005 * ((res["depth_fine"][:, None] * c.scale - G) ** 2).mean() + 1000.0 * (w - w_gt).abs().mean()
+                + (res["opacity_fine"] - 1).abs().mean())
+        loss.backward()
+        # oracle
+        p = c.params.clone().requires_grad_(True)
+        r = rays_cpu.clone().requires_grad_(True)
+        z = orc.uniform_samples(r.detach(), S, 0.0, None)
+        o = orc.render_rays(r, z, p, c.spec, torch.zeros(n, S))
+        w_gt_o = orc.get_weights_gt((z * c.scale), depths[:, None] * c.scale, torch.full((n, 1), 1.5))
+        loss_o = (0.005 * ((o["depth_fine"][:, None] * c.scale - depths[:, None] * c.scale) ** 2).mean()
+                  + 1000.0 * (o["weights_fine"] - w_gt_o).abs().mean() + (o["opacity_fine"] - 1).abs().mean())
+        loss_o.backward()
+        errs = dict(z=float((res["samples_fine"].cpu() - z).abs().max()), depth=relerr(res["depth_fine"], o["depth_fine"]),
+                    weights=relerr(res["weights_fine"], o["weights_fine"]), variance=relerr(res["variance"], o["variance"]),
+                    loss=abs(float(loss) - float(loss_o)) / float(loss_o),
+                    gparams=norm_relerr(model.nerf_model._model_sigma.params.grad, p.grad),
+                    grays=norm_relerr(rays.grad[:, :6], r.grad[:, :6]))
+        print("dropin: " + " ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+        assert errs["z"] < 1e-6 and errs["depth"] < 1e-4 and errs["weights"] < 2e-4 and errs["loss"] < 1e-4
+        assert errs["gparams"] < 2e-2 and errs["grays"] < 5e-2
+        # state_dict round trip and torch.optim.Adam on the flat parameter (optimizer.py:263-267)
+        sd = model.state_dict()
+        assert "nerf_model._model_sigma.params" in sd
+        opt = torch.optim.Adam([{"params": model.get_sigma_parameters(), "lr": 0.01}])
+        before = model.nerf_model._model_sigma.params.detach().clone()
+        opt.step()
+        assert not torch.equal(before, model.nerf_model._model_sigma.params.detach())
+        res2 = model(rays.detach(), sampler, c.scale, camera=False, return_variance=True)   # repacked weights
+        assert not torch.equal(res2["depth_fine"], res["depth_fine"])
+        # occupancy-guided sampler through the same API
+        og = rs.OccGridRaySampler()
+        og.update_occ_grid(c.grid.cuda())
+        zz = og.get_samples(rays.detach(), S, 1.0)
+        assert zz.shape == (n, S) and bool((zz[:, 1:] >= zz[:, :-1]).all())
+    finally:
+        sys.path.remove(path)
+        for m in list(sys.modules):
+            if m == "models" or m.startswith("models."):
+                del sys.modules[m]
