@@ -51,7 +51,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled every 20 ms from before the warm-up until after the
+    timed region; only samples whose timestamp falls inside the timed region are reported (nvidia-smi
+    needs ~0.3 s to start, longer than a short timed region)."""
 
     def __init__(self, index):
         self.index = index
@@ -59,12 +61,12 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+        q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -73,32 +75,43 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nme, val in zip(names, f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nme)
-        sm.sort()
+
+        def collect(lines):
+            sm, mx, pw, reasons = [], [], [], set()
+            for _, ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for nme, val in zip(names, f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nme)
+            sm.sort()
+            return sm, mx, pw, reasons
+
+        inside = [x for x in self.lines if t0 is not None and t0 <= x[0] <= t1 + 0.03]
+        window = "timed region"
+        if not inside:
+            inside, window = self.lines, "warm-up + timed region (timed region shorter than the sampling period)"
+        sm, mx, pw, reasons = collect(inside)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 def build_engine(wl, device, seed):
@@ -179,7 +192,7 @@ def cpu_port_rays_per_sec(wl, n_rays, iters, warmup, tune=True):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -229,22 +242,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for _ in range(max(args.warmup, 3)):
         e.step(window, n_per_kf, optimize_poses=wl["poses"])
     barrier()
     e.timers = {}
     launches0 = e.launches
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     t_start.record()
     for _ in range(args.steps):
         loss = e.step(window, n_per_kf, optimize_poses=wl["poses"])
     t_end.record()
     barrier()
-    clock_info = clocks.stop() if rank == 0 else None
+    wall1 = time.time()
+    clock_info = clocks.stop(wall0, wall1) if rank == 0 else None
     ms = torch.tensor([t_start.elapsed_time(t_end)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -246,6 +246,16 @@ __device__ __forceinline__ void copy_out(uint32_t srow, uint8_t* grow, uint32_t 
   }
 }
 
+// Linear, fully coalesced copy of a finished tile image (contiguous in shared memory and in HBM) by
+// the 256 threads of an epilogue group: every warp instruction moves 512 contiguous bytes.
+__device__ __forceinline__ void copy_image(uint32_t simg, uint8_t* gimg, int bytes, int gtid) {
+  for (int off = gtid * 16; off < bytes; off += kGroupThreads * 16) {
+    const uint4 v = lds128(simg + off);
+    asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(gimg + off), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+  }
+}
+
 // Drains kCols accumulator columns of this thread's TMEM lane in 16-column loads, keeping the next
 // load in flight while `proc(i, v)` works on the current one (tcgen05.ld latency is ~300-450 clk,
 // tests/gpu_probe.py).
@@ -480,6 +490,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
         mbar_wait(sm.acc_full[t], par_acc);
         par_acc ^= 1u;
         tc_fence_after();
+        if (kStash && l > 0) group_bar(t);    // everyone's copy of the previous image has left sA
         float sig0 = 0.f, sig1 = 0.f;
         uint32_t mbits[kCols / 32];
 #pragma unroll
@@ -529,7 +540,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
           group_bar(t);
           if (h == 0 && in) a.sigma[gs] = sig + part[row];
         }
-        if (kStash && grow != nullptr) copy_out<kCols>(srow, grow, xs, h * kCols);
+        if (kStash) {
+          if (!last) group_bar(t);            // (the last layer already met at the sigma barrier)
+          if (active) copy_image(sA, a.acts + tile * act_tile_bytes(net) + kBlk + (int64_t)l * kNb * kBlk, kNb * kBlk,
+                                 (e & 7) * 32 + lane);
+        }
       }
     }
   }
@@ -622,7 +637,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
     const int h = (e & 7) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const uint32_t srow = smem_u32(sm.tileA[t]) + row * 128;
+    const uint32_t stile = smem_u32(sm.tileA[t]);
+    const uint32_t srow = stile + row * 128;
     const uint32_t xs = (uint32_t)(row & 7) << 4;
     constexpr int kCols = W / 2;
     const uint32_t acc_row = tmem + t * 256 + ((uint32_t)(q * 32) << 16);
@@ -637,6 +653,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
       const bool in = active && gs < a.P;
       const uint32_t* mtile = reinterpret_cast<const uint32_t*>(a.masks + (active ? tile : 0) * mask_tile_bytes(net));
       uint8_t* gtile = active ? a.dz + tile * dz_tile_bytes(net) + row * 128 : nullptr;
+      group_bar(t);                           // the previous tile's last image copy has left the buffer
       RowIn rin;
       if (want_dx && h == 0) rin = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, in ? gs : a.P - 1);
       {  // dZ_L = d_sigma * w_out * relu'(Z_L)
@@ -656,11 +673,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
       }
       fence_async_smem();
       mbar_arrive(sm.a_ready[t]);
-      if (gtile) copy_out<kCols>(srow, gtile + (int64_t)(net.L - 1) * kNb * kBlk, xs, h * kCols);
+      group_bar(t);
+      if (active) copy_image(stile, a.dz + tile * dz_tile_bytes(net) + (int64_t)(net.L - 1) * kNb * kBlk, kNb * kBlk,
+                             (e & 7) * 32 + lane);
       for (int l = net.L - 1; l >= l_lo; --l) {
         mbar_wait(sm.acc_full[t], par_acc);
         par_acc ^= 1u;
         tc_fence_after();
+        group_bar(t);                         // everyone's copy of the previous image has left the tile buffer
         if (l >= 1) {
           // dZ_l = dA_l * relu'(Z_l)  -> fp16 image (next GEMM's A operand in smem, wgrad's B operand in HBM)
           const uint32_t* mrow = mtile + ((int64_t)(l - 1) * kTile + row) * kWords + h * (kCols / 32);
@@ -685,7 +705,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
             fence_async_smem();
             mbar_arrive(sm.a_ready[t]);
           }
-          if (grow) copy_out<kCols>(srow, grow, xs, h * kCols);
+          group_bar(t);
+          if (active) copy_image(stile, a.dz + tile * dz_tile_bytes(net) + (int64_t)(l - 1) * kNb * kBlk, kNb * kBlk,
+                                 (e & 7) * 32 + lane);
         } else if (h == 0) {
           // l == 0: dEnc [128 x Epad] -> d_pos through the sin/cos encoding (lower-half warps only)
           float x[3];
