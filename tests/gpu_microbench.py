@@ -33,6 +33,8 @@ res["sample_ogm"] = timeit(lambda: ops.sample_ogm(rays, grid, S, 1.0, None, None
 acts = torch.empty(net.act_bytes(P), device=dev, dtype=torch.uint8)
 sigma = torch.empty(P, device=dev)
 res["mlp_fwd_stash"] = timeit(lambda: ops.mlp_fwd(net, packed, P, rays=rays, z=z, stash=True, sigma=sigma, acts=acts))
+if os.environ.get("MB_ONLY") == "fwd":
+    print(json.dumps({k: round(v, 4) for k, v in res.items()})); sys.exit(0)
 res["mlp_fwd_infer"] = timeit(lambda: ops.mlp_fwd(net, packed, P, rays=rays, z=z, stash=False, sigma=sigma))
 depths = torch.full((N,), 0.3, device=dev)
 flags = torch.full((N,), 3, dtype=torch.uint8, device=dev)
