@@ -114,6 +114,23 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def ncu_traffic_bytes(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full
+    capture (profiles/r1_ncu_summary.csv, C2 workload); None if absent."""
+    import csv
+    path = os.path.join(REPO, "profiles", "r1_ncu_summary.csv")
+    if not os.path.exists(path):
+        return None
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    for r in rows[2:]:
+        if kernel_substr in r[ki]:
+            return float(r[ri]) * mult.get(units[ri], 1.0) + float(r[wi]) * mult.get(units[wi], 1.0)
+    return None
+
+
 def build_engine(wl, device, seed):
     from loner_b200 import engine as eng
     from loner_b200 import synth
@@ -287,6 +304,22 @@ def main():
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_rps = N * world * e2e_steps / (float(ms2.item()) * 1e-3)
 
+    # ---- forward-only (test-mode render: sampler + MLP inference + volume render), same rays
+    rays_d = e.last["rays"]
+    for _ in range(3):
+        e.render(rays_d, seed=1)
+    barrier()
+    fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fa.record()
+    for _ in range(e2e_steps):
+        e.render(rays_d, seed=2)
+    fb.record()
+    barrier()
+    ms3 = torch.tensor([fa.elapsed_time(fb)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+    fwd_ms = float(ms3.item()) / e2e_steps
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -305,8 +338,12 @@ def main():
             kern[k]["tflops"] = round(flops[k] * per_chunk / (t * 1e-3) / 1e12, 1)
     dom = max((k for k in sections if k in flops), key=lambda k: sections[k])
     achieved = flops[dom] * per_chunk / (sections[dom] * 1e-3) / 1e12
+    traffic = ncu_traffic_bytes(dom) if args.workload == "c2" else None
     roofline = {"kernel": dom, "bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["tflops_sustained"],
-                "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops_sustained"], 4), "traffic": None,
+                "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops_sustained"], 4), "traffic": traffic,
+                "traffic_note": "DRAM bytes of one launch from profiles/r1_ncu_summary.csv (ncu --set full); the "
+                                "algorithmic HBM need of this kernel is 8 B/sample, the rest is the activation "
+                                "stash the backward design requires (DESIGN.md section 4)",
                 "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                 "algorithmic_flops_per_sample": flops[dom], "samples_per_launch": per_chunk,
                 "step": {"algorithmic_tflop_per_step": round(f_train * P / 1e12, 3),
@@ -319,7 +356,11 @@ def main():
             "data": "synthetic", "config": config, "loss": loss_val, "clocks": clock_info,
             "e2e": {"value": e2e_rps, "unit": "rays/s", "h2d_bytes_per_step": int(rays_h.numel() * 4 + depths_h.numel() * 4),
                     "d2h_bytes_per_step": 4, "api": "MappingEngine.step_from_host(rays[N,13], depths[N]) (pinned host)"},
-            "gpu_launches": launches, "roofline": roofline}
+            "gpu_launches": launches, "roofline": roofline,
+            "forward_only": {"rays_per_s": N * world / (fwd_ms * 1e-3), "ms": fwd_ms,
+                             "tflops": round(f_fwd * P / (fwd_ms * 1e-3) / 1e12, 1),
+                             "frac_of_sustained_peak": round(f_fwd * P / (fwd_ms * 1e-3) / 1e12 / peaks["tflops_sustained"], 4),
+                             "what": "MappingEngine.render: OGM sampler + MLP inference + volume render, no stash"}}
     if not args.no_cpu_baseline:
         n = args.cpu_sample_rays
         rps, med = cpu_port_rays_per_sec(wl, n, 3, 1)

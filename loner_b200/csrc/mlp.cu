@@ -1041,8 +1041,8 @@ extern "C" int loner_mlp_fwd(const loner_net_t* n, const void* packed, const flo
                              const float* z_vals, int32_t S, int64_t P, float* sigma, void* acts, void* stream) {
   Net net;
   if (!net_from(n, net)) return LONER_E_UNSUPPORTED;
-  if (!packed || !sigma || P < 0 || (!pos && (!rays || !z_vals || S <= 0))) return LONER_E_BAD_ARG;
   if (P == 0) return LONER_OK;
+  if (!packed || !sigma || P < 0 || (!pos && (!rays || !z_vals || S <= 0))) return LONER_E_BAD_ARG;
   FwdArgs a;
   a.net = net; a.packed = (const uint8_t*)packed; a.pos = pos; a.rays = rays; a.z = z_vals; a.S = S; a.P = P;
   a.s_shift = (S > 0 && (S & (S - 1)) == 0) ? __builtin_ctz((unsigned)S) : -1;
@@ -1073,8 +1073,8 @@ extern "C" int loner_mlp_dgrad(const loner_net_t* n, const void* packed, const f
   Net net;
   int rc = bwd_common(n, net, packed, acts, scratch, P);
   if (rc) return rc;
-  if (!d_sigma || !(grad_scale > 0.f) || (d_pos && !pos && (!rays || !z_vals || S <= 0))) return LONER_E_BAD_ARG;
   if (P == 0) return LONER_OK;
+  if (!d_sigma || !(grad_scale > 0.f) || (d_pos && !pos && (!rays || !z_vals || S <= 0))) return LONER_E_BAD_ARG;
   const int64_t tiles = n_tiles(P);
   const int sms = device_sm_count();
   BwdArgs b;
@@ -1097,8 +1097,8 @@ extern "C" int loner_mlp_wgrad(const loner_net_t* n, const void* packed, int64_t
   Net net;
   int rc = bwd_common(n, net, packed, acts, scratch, P);
   if (rc) return rc;
-  if (!d_sigma || !d_params || !(grad_scale > 0.f)) return LONER_E_BAD_ARG;
   if (P == 0) return LONER_OK;
+  if (!d_sigma || !d_params || !(grad_scale > 0.f)) return LONER_E_BAD_ARG;
   const int64_t tiles = n_tiles(P);
   const int sms = device_sm_count();
   cudaStream_t st = (cudaStream_t)stream;

@@ -66,8 +66,8 @@ ogm_grad_kernel(const float* __restrict__ rays, const float* __restrict__ z_vals
 extern "C" int loner_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
                                int32_t step, float lr, float beta1, float beta2, float eps, float grad_unscale,
                                void* stream) {
-  if (!params || !grads || !exp_avg || !exp_avg_sq || count < 0 || step < 1) return LONER_E_BAD_ARG;
   if (count == 0) return LONER_OK;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || count < 0 || step < 1) return LONER_E_BAD_ARG;
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   unsigned blocks = (unsigned)((count + 255) / 256);
@@ -79,8 +79,8 @@ extern "C" int loner_adam_step(float* params, const float* grads, float* exp_avg
 }
 
 extern "C" int loner_sgd_step(float* x, const float* g, int64_t count, float lr, void* stream) {
-  if (!x || !g || count < 0) return LONER_E_BAD_ARG;
   if (count == 0) return LONER_OK;
+  if (!x || !g || count < 0) return LONER_E_BAD_ARG;
   unsigned blocks = (unsigned)((count + 255) / 256);
   if (blocks > 2368) blocks = 2368;
   loner::sgd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, g, count, lr);
@@ -90,8 +90,8 @@ extern "C" int loner_sgd_step(float* x, const float* g, int64_t count, float lr,
 
 extern "C" int loner_ogm_grad(const float* rays, const float* z_vals, const float* depths, int64_t n, int32_t S,
                               float scale, int32_t V, float* d_grid, void* stream) {
-  if (!rays || !z_vals || !depths || !d_grid || n < 0 || S <= 0 || V <= 0) return LONER_E_BAD_ARG;
   if (n == 0) return LONER_OK;
+  if (!rays || !z_vals || !depths || !d_grid || n < 0 || S <= 0 || V <= 0) return LONER_E_BAD_ARG;
   const int64_t total = n * S;
   loner::ogm_grad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rays, z_vals, depths, n, S,
                                                                                             scale, V, d_grid);

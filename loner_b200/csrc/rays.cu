@@ -158,9 +158,9 @@ extern "C" int loner_ray_build(const void* points, const int32_t* ray_kf, const 
                                const float* poses, int32_t K, const float* shift3_host, float scale, float r0,
                                float r1, float* rays, float* depths, uint8_t* flags, int32_t* counters,
                                void* stream) {
+  if (n == 0) return LONER_OK;
   if (!points || !ray_kf || !ray_point || !poses || !shift3_host || !rays || !depths || !flags || n < 0 || K <= 0)
     return LONER_E_BAD_ARG;
-  if (n == 0) return LONER_OK;
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   loner::ray_build_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
@@ -173,9 +173,9 @@ extern "C" int loner_ray_build(const void* points, const int32_t* ray_kf, const 
 extern "C" int loner_ray_build_bwd(const void* points, const int32_t* ray_kf, const int64_t* ray_point, int64_t n,
                                    const float* poses, int32_t K, const float* shift3_host, float scale,
                                    float r1, const float* d_rays, float* d_poses, void* stream) {
+  if (n == 0) return LONER_OK;
   if (!points || !ray_kf || !ray_point || !poses || !shift3_host || !d_rays || !d_poses || n < 0 || K <= 0 || K > 1024)
     return LONER_E_BAD_ARG;
-  if (n == 0) return LONER_OK;
   const int threads = 256;
   const unsigned blocks = (unsigned)((n + threads - 1) / threads);
   loner::ray_build_bwd_kernel<<<blocks, threads, K * 12 * sizeof(float), (cudaStream_t)stream>>>(
@@ -187,8 +187,8 @@ extern "C" int loner_ray_build_bwd(const void* points, const int32_t* ray_kf, co
 
 extern "C" int loner_points_bwd(const float* d_pos, const float* z_vals, int64_t n, int32_t S, float* d_rays,
                                 void* stream) {
-  if (!d_pos || !z_vals || !d_rays || n < 0 || S <= 0) return LONER_E_BAD_ARG;
   if (n == 0) return LONER_OK;
+  if (!d_pos || !z_vals || !d_rays || n < 0 || S <= 0) return LONER_E_BAD_ARG;
   const int threads = 256;
   const unsigned blocks = (unsigned)((n * 32 + threads - 1) / threads);
   loner::points_bwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_pos, z_vals, n, S, d_rays);

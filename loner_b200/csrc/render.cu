@@ -287,8 +287,8 @@ static int render_smem(int S, size_t* out) {
 extern "C" int loner_render_fwd(const float* sigma, const float* z_vals, const float* rays, int64_t n, int32_t S,
                                 const float* noise, float raw_noise_std, uint64_t seed, float* weights,
                                 float* depth, float* opacity, float* variance, void* stream) {
-  if (!sigma || !z_vals || !rays || n < 0 || S < 2) return LONER_E_BAD_ARG;
   if (n == 0) return LONER_OK;
+  if (!sigma || !z_vals || !rays || n < 0 || S < 2) return LONER_E_BAD_ARG;
   size_t smem;
   if (!render_smem(S, &smem)) return LONER_E_UNSUPPORTED;
   auto k = loner::render_kernel<0>;
@@ -308,9 +308,9 @@ extern "C" int loner_render_loss(const float* sigma, const float* z_vals, const 
                                  const float* loss_cfg7_host, float* loss_acc, float* weights, float* depth,
                                  float* opacity, float* variance, float* eps_dyn, float* d_sigma, float* d_rays,
                                  void* stream) {
+  if (n == 0) return LONER_OK;
   if (!sigma || !z_vals || !rays || !depths || !counts || !loss_cfg7_host || !loss_acc || !d_sigma || n < 0 || S < 2)
     return LONER_E_BAD_ARG;
-  if (n == 0) return LONER_OK;
   size_t smem;
   if (!render_smem(S, &smem)) return LONER_E_UNSUPPORTED;
   auto k = loner::render_kernel<1>;
@@ -329,8 +329,8 @@ extern "C" int loner_render_bwd(const float* sigma, const float* z_vals, const f
                                 const float* noise, float raw_noise_std, uint64_t seed, const float* g_weights,
                                 const float* g_depth, const float* g_opacity, const float* g_variance,
                                 float* d_sigma, float* d_rays, void* stream) {
-  if (!sigma || !z_vals || !rays || !d_sigma || n < 0 || S < 2) return LONER_E_BAD_ARG;
   if (n == 0) return LONER_OK;
+  if (!sigma || !z_vals || !rays || !d_sigma || n < 0 || S < 2) return LONER_E_BAD_ARG;
   size_t smem;
   if (!render_smem(S, &smem)) return LONER_E_UNSUPPORTED;
   auto k = loner::render_bwd_kernel;

@@ -179,8 +179,8 @@ sample_ogm_kernel(const float* __restrict__ rays, int64_t n, int S, int H, int H
 
 extern "C" int loner_sample_uniform(const float* rays, int64_t n, int32_t S, float perturb, const float* u,
                                     uint64_t seed, float* z_vals, void* stream) {
-  if (!rays || !z_vals || n < 0 || S < 2) return LONER_E_BAD_ARG;
   if (n == 0) return LONER_OK;
+  if (!rays || !z_vals || n < 0 || S < 2) return LONER_E_BAD_ARG;
   const int64_t total = n * S;
   loner::sample_uniform_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       rays, n, S, perturb, u, seed, z_vals);
@@ -191,9 +191,9 @@ extern "C" int loner_sample_uniform(const float* rays, int64_t n, int32_t S, flo
 extern "C" int loner_sample_ogm(const float* rays, int64_t n, int32_t S, float perturb, const float* grid,
                                 int32_t V, const float* u1, const float* u2, uint64_t seed, float* z_vals,
                                 void* stream) {
+  if (n == 0) return LONER_OK;
   if (!rays || !grid || !z_vals || n < 0 || V <= 0) return LONER_E_BAD_ARG;
   if (S < 8 || (S & 1)) return LONER_E_UNSUPPORTED;   // needs H-2 >= 2 weights
-  if (n == 0) return LONER_OK;
   const int H = S / 2;
   int Hp = 32;
   while (Hp < H) Hp <<= 1;
