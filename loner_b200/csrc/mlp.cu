@@ -14,6 +14,7 @@
 //   async copies (cp.async.bulk) of contiguous ranges; no tensor maps.
 //   Accumulators live in TMEM (tcgen05.mma, one issuing thread), epilogues read them back with
 //   tcgen05.ld.
+#include <cstdlib>
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -325,6 +326,7 @@ struct FwdArgs {
   float* sigma;          // [P]
   uint8_t* acts;         // activation stash or null
   uint8_t* masks;        // relu bit masks or null
+  int bulk;              // stash images leave through cp.async.bulk (1) or a thread copy (0)
 };
 
 // sin/cos(pi * 2^f * x).  2^f * x is exact in fp32, and so is its reduction r to [-1, 1]; sin(pi r) and
@@ -457,6 +459,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
     const int row = q * 32 + lane;
     const uint32_t sA = smem_u32(sm.tileA[t]);
     const uint32_t srow = sA + row * 128;
+    const bool elected = ((e & 7) == 0) && lane == 0;
     const uint32_t xs = (uint32_t)(row & 7) << 4;
     constexpr int kCols = W / 2;                      // columns per thread
     const uint32_t acc = tmem + t * 256 + ((uint32_t)(q * 32) << 16) + h * kCols;
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
       const int64_t gs = tile * kTile + row;
       const bool in = active && gs < a.P;
       uint8_t* gtile = (kStash && active) ? a.acts + tile * act_tile_bytes(net) + row * 128 : nullptr;
-      if (kStash) group_bar(t);     // the other column-half's copy-out of the previous tile is done with sA
+      if (kStash) { if (a.bulk && elected) bulk_wait_read0(); group_bar(t); }   // previous image has left sA
       {
         float x[3];
         row_pos01(pos_mode, nxt, x);
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
         mbar_wait(sm.acc_full[t], par_acc);
         par_acc ^= 1u;
         tc_fence_after();
-        if (kStash && l > 0) group_bar(t);    // everyone's copy of the previous image has left sA
+        if (kStash && l > 0) { if (a.bulk && elected) bulk_wait_read0(); group_bar(t); }   // previous image has left sA
         float sig0 = 0.f, sig1 = 0.f;
         uint32_t mbits[kCols / 32];
 #pragma unroll
@@ -536,17 +539,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
           fence_async_smem();
           mbar_arrive(sm.a_ready[t]);
         } else {
+          if (kStash) fence_async_smem();       // A_L in sA becomes visible to the bulk-copy engine
           if (h == 1) part[row] = sig;
           group_bar(t);
           if (h == 0 && in) a.sigma[gs] = sig + part[row];
         }
         if (kStash) {
           if (!last) group_bar(t);            // (the last layer already met at the sigma barrier)
-          if (active) copy_image(sA, a.acts + tile * act_tile_bytes(net) + kBlk + (int64_t)l * kNb * kBlk, kNb * kBlk,
-                                 (e & 7) * 32 + lane);
+          uint8_t* gimg = a.acts + tile * act_tile_bytes(net) + kBlk + (int64_t)l * kNb * kBlk;
+          if (active && !a.bulk) copy_image(sA, gimg, kNb * kBlk, (e & 7) * 32 + lane);
+          if (active && a.bulk && elected) { bulk_s2g(gimg, sA, (uint32_t)(kNb * kBlk)); bulk_commit(); }
         }
       }
     }
+    if (kStash && a.bulk && elected) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -568,6 +574,7 @@ struct BwdArgs {
   const float* d_sigma;
   const uint8_t* masks;
   uint8_t* dz;           // dZ stash [tiles][L][nb*16 KB]
+  int bulk;
   float gscale;
   float* d_pos;          // [P,3] or null
 };
@@ -639,6 +646,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
     const int row = q * 32 + lane;
     const uint32_t stile = smem_u32(sm.tileA[t]);
     const uint32_t srow = stile + row * 128;
+    const bool elected = ((e & 7) == 0) && lane == 0;
     const uint32_t xs = (uint32_t)(row & 7) << 4;
     constexpr int kCols = W / 2;
     const uint32_t acc_row = tmem + t * 256 + ((uint32_t)(q * 32) << 16);
@@ -653,6 +661,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
       const bool in = active && gs < a.P;
       const uint32_t* mtile = reinterpret_cast<const uint32_t*>(a.masks + (active ? tile : 0) * mask_tile_bytes(net));
       uint8_t* gtile = active ? a.dz + tile * dz_tile_bytes(net) + row * 128 : nullptr;
+      if (a.bulk && elected) bulk_wait_read0();
       group_bar(t);                           // the previous tile's last image copy has left the buffer
       RowIn rin;
       if (want_dx && h == 0) rin = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, in ? gs : a.P - 1);
@@ -674,12 +683,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
       fence_async_smem();
       mbar_arrive(sm.a_ready[t]);
       group_bar(t);
-      if (active) copy_image(stile, a.dz + tile * dz_tile_bytes(net) + (int64_t)(net.L - 1) * kNb * kBlk, kNb * kBlk,
-                             (e & 7) * 32 + lane);
+      {
+        uint8_t* gimg = a.dz + tile * dz_tile_bytes(net) + (int64_t)(net.L - 1) * kNb * kBlk;
+        if (active && !a.bulk) copy_image(stile, gimg, kNb * kBlk, (e & 7) * 32 + lane);
+        if (active && a.bulk && elected) { bulk_s2g(gimg, stile, (uint32_t)(kNb * kBlk)); bulk_commit(); }
+      }
       for (int l = net.L - 1; l >= l_lo; --l) {
         mbar_wait(sm.acc_full[t], par_acc);
         par_acc ^= 1u;
         tc_fence_after();
+        if (a.bulk && elected) bulk_wait_read0();
         group_bar(t);                         // everyone's copy of the previous image has left the tile buffer
         if (l >= 1) {
           // dZ_l = dA_l * relu'(Z_l)  -> fp16 image (next GEMM's A operand in smem, wgrad's B operand in HBM)
@@ -701,13 +714,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
             store16(srow, nullptr, xs, h * kCols + i * 16, hh);
           });
           tc_fence_before();
-          if (feeds_gemm) {
-            fence_async_smem();
-            mbar_arrive(sm.a_ready[t]);
-          }
+          fence_async_smem();
+          if (feeds_gemm) mbar_arrive(sm.a_ready[t]);
           group_bar(t);
-          if (active) copy_image(stile, a.dz + tile * dz_tile_bytes(net) + (int64_t)(l - 1) * kNb * kBlk, kNb * kBlk,
-                                 (e & 7) * 32 + lane);
+          {
+            uint8_t* gimg = a.dz + tile * dz_tile_bytes(net) + (int64_t)(l - 1) * kNb * kBlk;
+            if (active && !a.bulk) copy_image(stile, gimg, kNb * kBlk, (e & 7) * 32 + lane);
+            if (active && a.bulk && elected) { bulk_s2g(gimg, stile, (uint32_t)(kNb * kBlk)); bulk_commit(); }
+          }
         } else if (h == 0) {
           // l == 0: dEnc [128 x Epad] -> d_pos through the sin/cos encoding (lower-half warps only)
           float x[3];
@@ -746,6 +760,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
         }
       }
     }
+    if (a.bulk && elected) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -1047,6 +1062,7 @@ extern "C" int loner_mlp_fwd(const loner_net_t* n, const void* packed, const flo
   a.net = net; a.packed = (const uint8_t*)packed; a.pos = pos; a.rays = rays; a.z = z_vals; a.S = S; a.P = P;
   a.s_shift = (S > 0 && (S & (S - 1)) == 0) ? __builtin_ctz((unsigned)S) : -1;
   a.tiles = n_tiles(P); a.sigma = sigma; a.acts = (uint8_t*)acts;
+  { const char* m = getenv("LONER_STASH"); a.bulk = (m && m[0] == 'c') ? 0 : 1; }
   a.masks = acts ? (uint8_t*)acts + a.tiles * act_tile_bytes(net) : nullptr;
   const int sms = device_sm_count();
   const int64_t pairs = (a.tiles + 1) / 2;
@@ -1082,6 +1098,7 @@ extern "C" int loner_mlp_dgrad(const loner_net_t* n, const void* packed, const f
   b.s_shift = (S > 0 && (S & (S - 1)) == 0) ? __builtin_ctz((unsigned)S) : -1;
   b.tiles = tiles; b.d_sigma = d_sigma; b.masks = (const uint8_t*)acts + tiles * act_tile_bytes(net);
   b.dz = (uint8_t*)scratch; b.gscale = grad_scale; b.d_pos = d_pos;
+  { const char* m = getenv("LONER_STASH"); b.bulk = (m && m[0] == 'c') ? 0 : 1; }
   const int64_t pairs = (tiles + 1) / 2;
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem);
