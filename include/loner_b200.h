@@ -114,14 +114,15 @@ int loner_render_bwd(const float* sigma, const float* z_vals, const float* rays,
 /* ---- a13+a15+a16+a17  fused raw2outputs + JS dynamic margin + L1_JS loss, forward AND
  * backward in one pass (mapping/optimizer.py:437-595, models/losses.py:29-51).
  * counts: device int32[2] = global (#valid rays, #opaque rays) — the loss normalisers.
- * loss_cfg: {scale_factor, min_depth_eps, min_js, max_js, alpha, los_lambda, depthloss_lambda}.
+ * loss_cfg: {scale_factor, min_depth_eps, min_js, max_js, alpha, los_lambda, depthloss_lambda,
+ *            l2 (0: L1_* losses, 1: L2_*), fixed_eps (> 0 selects the *_LOS fixed margin)}.
  * loss_acc: device float[4] += {sum sq depth err, sum |w-w_gt|, sum |opacity-1|, sum eps_dyn}.
  * Outputs weights/depth/opacity/variance/eps_dyn may be NULL.  d_sigma [n,S]; d_rays [n,13] +=
  * (columns 3..5 through |d| and column 12 through far; the path through the network input is
  * loner_mlp_bwd's d_pos). */
 int loner_render_loss(const float* sigma, const float* z_vals, const float* rays, const float* depths,
                       const uint8_t* flags, int64_t n, int32_t S, const float* noise, float raw_noise_std,
-                      uint64_t seed, const int32_t* counts, const float* loss_cfg7_host, float* loss_acc,
+                      uint64_t seed, const int32_t* counts, const float* loss_cfg9_host, float* loss_acc,
                       float* weights, float* depth, float* opacity, float* variance, float* eps_dyn,
                       float* d_sigma, float* d_rays, void* stream);
 

@@ -21,6 +21,8 @@ struct RayCtx {
 
 struct LossCfg {
   float scale, eps_min, min_js, max_js, alpha, los_lambda, depth_lambda;
+  int l2;            // 0: L1 on the weights (L1_JS / L1_LOS), 1: MSE (L2_JS / L2_LOS)   optimizer.py:568-574
+  float fixed_eps;   // > 0: *_LOS variants use this margin instead of the JS dynamic one  optimizer.py:516-523
 };
 
 __device__ __forceinline__ float noise_at(const float* noise, float std, const Philox& rng, int64_t idx) {
@@ -181,7 +183,7 @@ render_kernel(const float* __restrict__ sigma, const float* __restrict__ z_vals,
   float js = 0.5f * kl_gauss(G, s0, mm, sm) + 0.5f * kl_gauss(mean, stdv, mm, sm);
   if (js < cfg.min_js) js = 0.f;
   if (js > cfg.max_js) js = cfg.max_js;
-  const float eps = cfg.eps_min * (1.0f + cfg.alpha * js);
+  const float eps = cfg.fixed_eps > 0.f ? cfg.fixed_eps : cfg.eps_min * (1.0f + cfg.alpha * js);
   if (eps_out && lane == 0) eps_out[ray] = eps;
 
   // target weights (losses.py:29-51), unnormalised sum first
@@ -207,7 +209,8 @@ render_kernel(const float* __restrict__ sigma, const float* __restrict__ z_vals,
   float l1 = 0.f;
   for (int s = lane; s < S; s += 32) {
     const float t = opaque ? wgt_raw(z_vals[base + s] * scale) / wn : 0.f;
-    l1 += fabsf(c.w[s] - t);
+    const float df = c.w[s] - t;
+    l1 += cfg.l2 ? df * df : fabsf(df);
   }
   l1 = warp_sum(l1);
   if (lane == 0) {
@@ -219,7 +222,7 @@ render_kernel(const float* __restrict__ sigma, const float* __restrict__ z_vals,
     const float zi = z_vals[base + s];
     const float t = opaque ? wgt_raw(zi * scale) / wn : 0.f;
     const float df = c.w[s] - t;
-    const float sgn = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+    const float sgn = cfg.l2 ? 2.0f * df : (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
     return k_los * sgn + k_depth * (zi - far) + k_opac;
   };
   const float g_norm = ray_backward(z_vals, base, S, dnorm, lane, c, gw, d_sigma);
@@ -294,7 +297,7 @@ extern "C" int loner_render_fwd(const float* sigma, const float* z_vals, const f
   auto k = loner::render_kernel<0>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const unsigned blocks = (unsigned)((n + loner::kRenderWarps - 1) / loner::kRenderWarps);
-  loner::LossCfg cfg{1.f, 0.5f, 1.f, 10.f, 1.f, 0.f, 0.f};
+  loner::LossCfg cfg{1.f, 0.5f, 1.f, 10.f, 1.f, 0.f, 0.f, 0, 0.f};
   k<<<blocks, loner::kRenderWarps * 32, smem, (cudaStream_t)stream>>>(
       sigma, z_vals, rays, nullptr, nullptr, n, S, noise, raw_noise_std, seed, nullptr, cfg, nullptr, weights, depth,
       opacity, variance, nullptr, nullptr, nullptr);
@@ -305,19 +308,19 @@ extern "C" int loner_render_fwd(const float* sigma, const float* z_vals, const f
 extern "C" int loner_render_loss(const float* sigma, const float* z_vals, const float* rays, const float* depths,
                                  const uint8_t* flags, int64_t n, int32_t S, const float* noise,
                                  float raw_noise_std, uint64_t seed, const int32_t* counts,
-                                 const float* loss_cfg7_host, float* loss_acc, float* weights, float* depth,
+                                 const float* loss_cfg9_host, float* loss_acc, float* weights, float* depth,
                                  float* opacity, float* variance, float* eps_dyn, float* d_sigma, float* d_rays,
                                  void* stream) {
   if (n == 0) return LONER_OK;
-  if (!sigma || !z_vals || !rays || !depths || !counts || !loss_cfg7_host || !loss_acc || !d_sigma || n < 0 || S < 2)
+  if (!sigma || !z_vals || !rays || !depths || !counts || !loss_cfg9_host || !loss_acc || !d_sigma || n < 0 || S < 2)
     return LONER_E_BAD_ARG;
   size_t smem;
   if (!render_smem(S, &smem)) return LONER_E_UNSUPPORTED;
   auto k = loner::render_kernel<1>;
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const unsigned blocks = (unsigned)((n + loner::kRenderWarps - 1) / loner::kRenderWarps);
-  const float* c = loss_cfg7_host;
-  loner::LossCfg cfg{c[0], c[1], c[2], c[3], c[4], c[5], c[6]};
+  const float* c = loss_cfg9_host;
+  loner::LossCfg cfg{c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7] != 0.f ? 1 : 0, c[8]};
   k<<<blocks, loner::kRenderWarps * 32, smem, (cudaStream_t)stream>>>(
       sigma, z_vals, rays, depths, flags, n, S, noise, raw_noise_std, seed, counts, cfg, loss_acc, weights, depth,
       opacity, variance, eps_dyn, d_sigma, d_rays);

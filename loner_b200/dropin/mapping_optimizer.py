@@ -1,0 +1,190 @@
+"""FusedOptimizer: the reference's `Optimizer` contract (/root/reference/src/mapping/optimizer.py:74-192)
+on top of the fused device-resident step (loner_b200.engine.MappingEngine).
+
+`Mapper` constructs `Optimizer(settings.optimizer, calibration, world_cube, 0, use_gt_poses, lidar_only,
+enable_sky_segmentation)` (mapping/mapper.py:63) and calls `iterate_optimizer(active_window)` per keyframe
+(mapper.py:104); this class takes the same arguments, reads the same settings keys, follows the same
+keyframe / iteration schedule (optimizer.py:144-269) and exposes the attributes the mapper reads
+(`_model`, `_optimizer`, `_occupancy_grid_model`, `_occupancy_grid_optimizer`, `_global_step`,
+`_keyframe_count`, mapper.py:108-175).  To use it:
+
+    import mapping.optimizer as mo
+    from loner_b200.dropin.mapping_optimizer import FusedOptimizer
+    mo.Optimizer = FusedOptimizer            # before Mapper is constructed
+
+Keyframes are duck-typed: `.get_lidar_scan()` (with `ray_directions [3,M]`, `distances [M]`),
+`.get_lidar_pose().get_pose_tensor()` ([6] = t, axis-angle), `.is_anchored`, `.get_time()`.
+"""
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+
+from loner_b200 import engine as eng
+
+
+@dataclass
+class OptimizationSettings:
+    """Same fields as the reference's container (optimizer.py:42-61)."""
+    num_iterations: int = 1
+    freeze_poses: bool = False
+    latest_kf_only: bool = False
+    freeze_sigma_mlp: bool = False
+    freeze_rgb_mlp: bool = False
+
+    @staticmethod
+    def from_dict(d):
+        return OptimizationSettings(d.get("num_iterations", 1), d.get("freeze_poses", False),
+                                    d.get("latest_kf_only", False), d.get("freeze_sigma_mlp", False),
+                                    d.get("freeze_rgb_mlp", False))
+
+
+class _ParamView(nn.Module):
+    """Checkpoint surface: `state_dict()` with the reference's key names."""
+
+    def __init__(self, key, tensor):
+        super().__init__()
+        self._key, self._t = key, tensor
+
+    def state_dict(self, *a, **kw):
+        return {self._key: self._t.detach().clone()}
+
+    def load_state_dict(self, sd, strict=True):
+        self._t.copy_(sd[self._key].reshape(self._t.shape))
+
+
+class _OptState:
+    def __init__(self, engine):
+        self._e = engine
+
+    def state_dict(self):
+        e = self._e
+        return {"exp_avg": e.exp_avg.detach().clone(), "exp_avg_sq": e.exp_avg_sq.detach().clone(), "step": e.adam_t}
+
+
+class FusedOptimizer:
+    def __init__(self, settings, calibration, world_cube, device, use_gt_poses=False, lidar_only=True,
+                 enable_sky_segmentation=True):
+        if not lidar_only:
+            raise NotImplementedError("camera supervision is disabled in the reference (optimizer.py:433-434)")
+        self._settings = settings
+        self._calibration = calibration
+        self._device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self._use_gt_poses = use_gt_poses
+        self._lidar_only = lidar_only
+        self._optimization_settings = OptimizationSettings()
+        mc = settings.model_config
+        self._model_config = mc
+        self._scale_factor = world_cube.scale_factor
+        m = mc.model
+        nc = m.nerf_config
+        enc, net = nc["pos_encoding_sigma"], nc["sigma_network"]
+        if enc["otype"] != "Frequency":
+            raise NotImplementedError("sigma-head encoding %r: only Frequency is implemented" % enc["otype"])
+        if mc.loss.loss_selection != "L1_JS":
+            raise NotImplementedError("loss_selection %r: only L1_JS is fused (the reference default)" % mc.loss.loss_selection)
+        sampler = settings.samples_selection.strategy
+        if sampler not in ("OGM", "UNIFORM"):
+            raise RuntimeError(f"Can't find samples_selection strategy: {sampler}")
+        if settings.rays_selection.strategy != "RANDOM":
+            raise NotImplementedError("rays_selection %r: only RANDOM is fused" % settings.rays_selection.strategy)
+        cfg = eng.EngineConfig(
+            scale=float(world_cube.scale_factor), shift=tuple(float(x) for x in world_cube.shift),
+            ray_range=tuple(float(x) for x in m.ray_range),
+            n_frequencies=int(enc.get("n_frequencies", 10)), n_neurons=int(net["n_neurons"]),
+            n_hidden_layers=int(net["n_hidden_layers"]), n_samples=int(m.render.N_samples_train),
+            perturb=float(m.render.perturb), raw_noise_std=float(m.render.raw_noise_std), sampler=sampler,
+            voxel_size=int(m.occ_model.voxel_size), occ_lr=float(m.occ_model.lr), occ_every=int(m.occ_model.N_iters_acc),
+            min_depth_eps=float(mc.loss.min_depth_eps), min_js=float(mc.loss.JS_loss.min_js_score),
+            max_js=float(mc.loss.JS_loss.max_js_score), js_alpha=float(mc.loss.JS_loss.alpha),
+            los_lambda=float(mc.loss.los_lambda), depthloss_lambda=float(mc.loss.depthloss_lambda),
+            lrate_sigma_mlp=float(mc.train.lrate_sigma_mlp), lrate_pose=float(mc.train.lrate_pose),
+            chunk_rays=min(int(m.render.chunk), 8192))
+        self._engine = eng.MappingEngine(cfg, device=self._device)
+        self._model = _ParamView("nerf_model._model_sigma.params", self._engine.params)
+        self._occupancy_grid_model = _ParamView("occupancy_grid", self._engine.grid)
+        self._optimizer = _OptState(self._engine)
+        self._occupancy_grid_optimizer = _OptState(self._engine)
+        self._keyframe_count = 0
+        self._global_step = 0
+        self._keyframe_schedule = settings["keyframe_schedule"]
+        self._num_lidar_samples = settings.num_samples.lidar
+        self._kf_ids = {}
+        self._depth_eps = None
+        self._progress_bar = None
+
+    # ------------------------------------------------------------------ schedule (optimizer.py:144-156)
+    def iterate_optimizer(self, keyframe_window, optimizer_settings=None):
+        cumulative = 0
+        for item in self._keyframe_schedule:
+            kf_count, iteration_schedule = item["num_keyframes"], item["iteration_schedule"]
+            cumulative += kf_count
+            if cumulative >= self._keyframe_count + 1 or kf_count == -1:
+                break
+        result = self._do_iterate_optimizer(keyframe_window, iteration_schedule, optimizer_settings=optimizer_settings)
+        self._keyframe_count += 1
+        return result
+
+    def _register(self, kf):
+        k = self._kf_ids.get(id(kf))
+        if k is None:
+            scan = kf.get_lidar_scan()
+            k = self._engine.add_keyframe(scan.ray_directions, scan.distances, kf.get_lidar_pose().get_pose_tensor())
+            self._kf_ids[id(kf)] = k
+        else:   # the tracker / previous phases may have moved the pose
+            self._engine.poses6[k].data.copy_(kf.get_lidar_pose().get_pose_tensor().detach().to(self._device))
+            self._engine._pose_cache = None
+        return k
+
+    def _do_iterate_optimizer(self, keyframe_window, iteration_schedule, profiler=None, optimizer_settings=None):
+        if len(keyframe_window) == 1:
+            keyframe_window[0].is_anchored = True
+        if len(iteration_schedule) > 1 and self._settings.skip_pose_refinement:
+            iteration_schedule = iteration_schedule[1:]
+        if optimizer_settings is not None:
+            iteration_schedule = [None]
+        losses = []
+        for it_cfg in iteration_schedule:
+            o = self._optimization_settings
+            if optimizer_settings is None:
+                o.freeze_poses = it_cfg["freeze_poses"] or self._settings.freeze_poses or self._use_gt_poses
+                o.latest_kf_only = it_cfg["latest_kf_only"] if "latest_kf_only" in it_cfg else False
+                o.freeze_rgb_mlp = it_cfg["freeze_rgb_mlp"]
+                o.freeze_sigma_mlp = it_cfg["freeze_sigma_mlp"]
+                o.num_iterations = it_cfg["num_iterations"]
+            else:
+                self._optimization_settings = o = optimizer_settings
+            o.freeze_poses = o.freeze_poses or self._settings.freeze_poses or self._use_gt_poses
+            optimize_poses = not o.freeze_poses
+            active = keyframe_window
+            if o.latest_kf_only:
+                active = [max(keyframe_window, key=lambda kf: float(kf.get_time()))]
+            ids = [self._register(kf) for kf in active]
+            free = {k for kf, k in zip(active, ids) if not kf.is_anchored}
+            if not (optimize_poses or not o.freeze_sigma_mlp):
+                continue                                                 # nothing to optimise (should_enable_lidar)
+            self._engine.new_phase(optimize_poses and len(free) > 0, train_map=not o.freeze_sigma_mlp, pose_ids=free)
+            phase_losses = []
+            for _ in range(o.num_iterations):
+                loss = self._engine.step(ids, self._num_lidar_samples, optimize_poses=optimize_poses and len(free) > 0)
+                phase_losses.append(loss)
+                self._global_step += 1
+            self._depth_eps = float(self._engine.last["depth_eps"])
+            # hand the optimised poses back to the keyframes (their tensors are what the mapper emits)
+            for kf, k in zip(active, ids):
+                if k in free and optimize_poses:
+                    kf.get_lidar_pose().get_pose_tensor().data.copy_(self._engine.poses6[k].detach().to(
+                        kf.get_lidar_pose().get_pose_tensor().device))
+            losses.append(torch.stack(phase_losses).detach())
+        if losses:
+            last = losses[-1]
+            if not torch.isfinite(last).all():
+                raise AssertionError("NaN Loss Encountered")                # optimizer.py:590
+        return losses
+
+    def should_enable_lidar(self):
+        o = self._optimization_settings
+        return not o.freeze_sigma_mlp or not o.freeze_poses
+
+    def should_enable_camera(self):
+        return False

@@ -73,6 +73,11 @@ class EngineConfig:
     js_alpha: float = 1.0
     los_lambda: float = 1000.0
     depthloss_lambda: float = 0.005
+    loss_selection: str = "L1_JS"       # L1_JS | L2_JS | L1_LOS | L2_LOS   (optimizer.py:497-532,568-574)
+    depth_eps: float = 3.0              # *_LOS: fixed / decaying margin (optimizer.py:516-521)
+    decay_depth_eps: bool = True
+    depth_eps_decay_rate: float = 0.95
+    depth_eps_decay_steps: float = 1.0
     # train (default_model_config.yaml:27-31)
     lrate_sigma_mlp: float = 0.01
     lrate_pose: float = 0.001
@@ -80,9 +85,18 @@ class EngineConfig:
     chunk_rays: int = 8192
     seed: int = 0
 
-    def loss_cfg7(self):
+    def loss_cfg(self, iteration_idx=0):
+        """The 9 floats loner_render_loss takes; *_LOS margins follow optimizer.py:516-521."""
+        if self.loss_selection not in ("L1_JS", "L2_JS", "L1_LOS", "L2_LOS"):
+            raise ValueError(f"Can't use unknown Loss {self.loss_selection}")
+        fixed = 0.0
+        if self.loss_selection.endswith("LOS"):
+            fixed = self.depth_eps
+            if self.decay_depth_eps:
+                fixed = max(self.depth_eps * self.depth_eps_decay_rate ** (iteration_idx / self.depth_eps_decay_steps),
+                            self.min_depth_eps)
         return [self.scale, self.min_depth_eps, self.min_js, self.max_js, self.js_alpha, self.los_lambda,
-                self.depthloss_lambda]
+                self.depthloss_lambda, 1.0 if self.loss_selection.startswith("L2") else 0.0, fixed]
 
 
 class MappingEngine:
@@ -119,6 +133,8 @@ class MappingEngine:
         self.timers = None          # name -> [(start_event, end_event)] when bench.py profiles sections
         self._wcache = {}
         self._pose_cache = None
+        self.phase_iteration = 0
+        self.train_map = True       # False = "tracking" phase: poses only, MLP frozen (freeze_sigma_mlp)
         self._exchange = None
         self._z_all = None
         self._last_d_poses12 = None
@@ -136,15 +152,19 @@ class MappingEngine:
         self._pose_cache = None
         return len(self.poses6) - 1
 
-    def new_phase(self, optimize_poses: bool):
-        """A new Adam per optimisation phase, as the reference does (optimizer.py:257-267)."""
+    def new_phase(self, optimize_poses: bool, train_map: bool = True, pose_ids=None):
+        """A new Adam per optimisation phase, as the reference does (optimizer.py:257-267).
+        pose_ids: keyframes whose pose is optimised (default: all but the anchored keyframe 0)."""
+        self.train_map = bool(train_map)
+        self.phase_iteration = 0            # `iteration_idx` of optimizer.py:276 (drives the *_LOS decay)
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
         self.adam_t = 0
         self.pose_opt = None
         self._pose_cache = None
         for k, p in enumerate(self.poses6):
-            p.requires_grad_(bool(optimize_poses and k > 0))     # keyframe 0 is anchored
+            free = (k > 0) if pose_ids is None else (k in pose_ids)     # keyframe 0 is anchored by default
+            p.requires_grad_(bool(optimize_poses and free))
         if optimize_poses:
             leaves = [p for p in self.poses6 if p.requires_grad]
             if leaves:
@@ -280,7 +300,7 @@ class MappingEngine:
             with self._sec("mlp_fwd"):
                 sigma, _ = ops.mlp_fwd(self.net, self.packed, P, rays=r, z=z, stash=True, acts=acts)
             with self._sec("render_loss"):
-                res = ops.render_loss(sigma, z, r, dpt, fl, counters, cfg.loss_cfg7(), noise=noise,
+                res = ops.render_loss(sigma, z, r, dpt, fl, counters, cfg.loss_cfg(self.phase_iteration), noise=noise,
                                       raw_noise_std=cfg.raw_noise_std, seed=seed + c0 + 1, loss_acc=loss_acc,
                                       want_outputs=want_outputs, d_rays=d_rays[c0:c1] if optimize_poses else None)
             scratch = self._buf("scratch", self.net.bwd_scratch_bytes(P))
@@ -316,11 +336,13 @@ class MappingEngine:
             if d_poses12 is not None:
                 d_poses12 = gp.clone()
         self._last_d_poses12 = d_poses12
-        self.adam_t += 1
-        with self._sec("adam_pack"):
-            ops.adam_step(self.params, self.d_params, self.exp_avg, self.exp_avg_sq, self.adam_t, cfg.lrate_sigma_mlp)
-            ops.mlp_pack(self.net, self.params, self.packed)
-        self.launches += 2
+        if self.train_map:
+            self.adam_t += 1
+            with self._sec("adam_pack"):
+                ops.adam_step(self.params, self.d_params, self.exp_avg, self.exp_avg_sq, self.adam_t,
+                              cfg.lrate_sigma_mlp)
+                ops.mlp_pack(self.net, self.params, self.packed)
+            self.launches += 2
         cnt = counters.to(torch.float32)
         loss = (cfg.depthloss_lambda * loss_acc[0] / cnt[1] + cfg.los_lambda * loss_acc[1] / (cnt[0] * cfg.n_samples)
                 + loss_acc[2] / cnt[1])
@@ -342,6 +364,7 @@ class MappingEngine:
             self.launches += 1
             self._z_all = None
         self.global_step += 1
+        self.phase_iteration += 1
 
     # ---------------------------------------------------------------- inference (test mode)
     @torch.no_grad()

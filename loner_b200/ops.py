@@ -164,7 +164,7 @@ def render_bwd(sigma, z, rays, noise, raw_noise_std, seed, g_weights, g_depth, g
     return d_sigma, d_rays
 
 
-def render_loss(sigma, z, rays, depths, flags, counts, loss_cfg7, noise=None, raw_noise_std=1.0, seed=0,
+def render_loss(sigma, z, rays, depths, flags, counts, loss_cfg, noise=None, raw_noise_std=1.0, seed=0,
                 loss_acc=None, want_outputs=True, d_rays=None):
     """Returns dict(loss_acc[4], d_sigma, d_rays, and optionally weights/depth/opacity/variance/eps)."""
     n, S = z.shape
@@ -182,7 +182,7 @@ def render_loss(sigma, z, rays, depths, flags, counts, loss_cfg7, noise=None, ra
     d_sigma = torch.empty(n, S, device=dev, dtype=torch.float32)
     if d_rays is None:
         d_rays = torch.zeros(n, RAY_COLS, device=dev, dtype=torch.float32)
-    cfg = L.host_floats(loss_cfg7)
+    cfg = L.host_floats(list(loss_cfg) + [0.0] * (9 - len(loss_cfg)))
     L.check(L.load().loner_render_loss(L.ptr(_f32(sigma)), L.ptr(_f32(z)), L.ptr(_f32(rays)), L.ptr(_f32(depths)),
                                        L.ptr(flags), n, S, L.ptr(noise), float(raw_noise_std), seed, L.ptr(counts),
                                        cfg, L.ptr(loss_acc), L.ptr(w), L.ptr(dpt), L.ptr(opa), L.ptr(var), L.ptr(eps),

@@ -181,6 +181,8 @@ class LossCfg:
     alpha: float = 1.0
     los_lambda: float = 1000.0
     depthloss_lambda: float = 0.005
+    loss_selection: str = "L1_JS"      # L1_JS | L2_JS | L1_LOS | L2_LOS
+    fixed_eps: float = 3.0             # the *_LOS margin for this iteration (optimizer.py:516-521)
 
 
 def _kl(m1, s1, m2, s2):
@@ -228,10 +230,13 @@ def compute_loss(rays, depths, res, scale, cfg: LossCfg):
     js_c = js.detach().clone()
     js_c[js_c < cfg.min_js] = 0
     js_c[js_c > cfg.max_js] = cfg.max_js
-    eps_dyn = (cfg.min_depth_eps * (1 + cfg.alpha * js_c))[:, None]
+    if cfg.loss_selection.endswith("JS"):
+        eps_dyn = (cfg.min_depth_eps * (1 + cfg.alpha * js_c))[:, None]            # optimizer.py:497-503
+    else:
+        eps_dyn = torch.full_like(G, cfg.fixed_eps)                                  # optimizer.py:516-523
     w_gt = get_weights_gt(s.detach(), G, eps_dyn)
     w_gt[~opaque, :] = 0
-    los = F.l1_loss(w, w_gt)
+    los = F.l1_loss(w, w_gt) if cfg.loss_selection.startswith("L1") else F.mse_loss(w, w_gt)   # optimizer.py:568-574
     opacity_loss = (res["opacity_fine"][opaque] - 1).abs().mean()
     loss = cfg.depthloss_lambda * depth_loss + cfg.los_lambda * los + opacity_loss
     return dict(loss=loss, depth_loss=depth_loss, los_loss=los, opacity_loss=opacity_loss,

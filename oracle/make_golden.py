@@ -36,6 +36,8 @@ CASES = {
     "kf2_4x256_fp16": dict(geom="canteen", K=2, n=128, S=256, L=4, W=256, grid="trained", prec="fp16", poses=True, rows=64),
     "kf2_4x256_fp32": dict(geom="canteen", K=2, n=128, S=256, L=4, W=256, grid="trained", prec="fp32", poses=True, rows=64),
     "kf2_2x128_fp16": dict(geom="garden", K=2, n=128, S=128, L=2, W=128, grid="trained", prec="fp16", poses=True, rows=64),
+    "kf2_2x128_l2js": dict(geom="garden", K=2, n=128, S=128, L=2, W=128, grid="trained", prec="fp16", poses=True, rows=64, loss="L2_JS"),
+    "kf2_2x128_l1los": dict(geom="garden", K=2, n=128, S=128, L=2, W=128, grid="trained", prec="fp16", poses=True, rows=64, loss="L1_LOS"),
     "quad_4x256_fp16": dict(geom="quad", K=2, n=128, S=512, L=4, W=256, grid="trained", prec="fp16", poses=True, rows=32),
 }
 N_BEAMS, N_AZ = 16, 256   # 4,096-point scans keep the fixtures' regeneration cheap
@@ -52,7 +54,7 @@ def case_randoms(seed, n_per_kf, K, M, n_rays, S):
     return idx, u1, u2, noise
 
 
-def build_reference_optimizer(ns, geom, S, L, W, tmpdir):
+def build_reference_optimizer(ns, geom, S, L, W, tmpdir, loss="L1_JS"):
     s = rh.load_settings()
     g = synth.GEOMETRY[geom]
     opt_s = s["mapper"]["optimizer"]
@@ -60,6 +62,7 @@ def build_reference_optimizer(ns, geom, S, L, W, tmpdir):
     mc["data"]["ray_range"] = list(g["ray_range"])
     mc["model"]["ray_range"] = list(g["ray_range"])
     mc["model"]["render"]["N_samples_train"] = S
+    mc["loss"]["loss_selection"] = loss
     nc = mc["model"]["nerf_config"]
     nc["pos_encoding_sigma"] = {"otype": "Frequency", "n_frequencies": 10}
     nc["sigma_network"] = {"otype": "CutlassMLP" if W > 128 else "FullyFusedMLP", "activation": "ReLU",
@@ -77,7 +80,7 @@ def run_case(name, c, seed=1234):
     tcnn_standin.PRECISION["mode"] = c["prec"]
     torch.manual_seed(0)
     with tempfile.TemporaryDirectory() as tmp:
-        opt, wc, settings = build_reference_optimizer(ns, c["geom"], c["S"], c["L"], c["W"], tmp)
+        opt, wc, settings = build_reference_optimizer(ns, c["geom"], c["S"], c["L"], c["W"], tmp, c.get("loss", "L1_JS"))
         g = synth.GEOMETRY[c["geom"]]
         scans, poses = synth.make_window(c["geom"], c["K"], seed=7, n_beams=N_BEAMS, n_azimuth=N_AZ)
         M = scans[0].distances.shape[0]
@@ -131,7 +134,7 @@ def run_case(name, c, seed=1234):
             meta=np.array([seed, c["K"], c["n"], c["S"], c["L"], c["W"], N_BEAMS, N_AZ, n_rays], dtype=np.int64),
             geom=np.array(c["geom"]), grid=np.array(c["grid"]), prec=np.array(c["prec"]),
             scale=np.float32(float(wc.scale_factor)), shift=wc.shift.numpy().astype(np.float32),
-            params_seed=np.int64(1337),
+            params_seed=np.int64(1337), loss_selection=np.array(c.get("loss", "L1_JS")),
             rays=rays.detach().numpy(), depths=depths.numpy(),
             z_vals=res["samples_fine"][:rows].detach().numpy(),
             weights=res["weights_fine"][:rows].detach().numpy(),

@@ -55,13 +55,16 @@ class Case:
         else:
             self.grid = torch.zeros(1, 1, 100, 100, 100)
         self.pose_grads = "grad_poses" in self.g.files
+        self.loss_selection = str(self.g["loss_selection"]) if "loss_selection" in self.g.files else "L1_JS"
+        # iteration_idx = 0 in the fixtures: the *_LOS margin is depth_eps * 0.95**0 = 3.0 (default_model_config.yaml:51-55)
+        self.loss_cfg = orc.LossCfg(loss_selection=self.loss_selection, fixed_eps=3.0)
 
     def run_oracle(self):
         params = self.params.clone().requires_grad_(True)
         poses6 = [p.clone().requires_grad_(self.pose_grads and k > 0) for k, p in enumerate(self.poses6)]
         rays, depths, res, out = orc.mapping_iteration(
             self.scans, poses6, self.idx, params, self.spec, self.grid, self.S, self.scale, self.shift,
-            self.ray_range, 1.0, self.u1, self.u2, self.noise, orc.LossCfg())
+            self.ray_range, 1.0, self.u1, self.u2, self.noise, self.loss_cfg)
         out["loss"].backward()
         s = res["samples_fine"].detach() * self.scale
         G = depths.reshape(-1, 1) * self.scale

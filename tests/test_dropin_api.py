@@ -69,3 +69,17 @@ def test_dropin_imports_without_a_gpu():
         for m in list(sys.modules):
             if m == "models" or m.startswith("models."):
                 del sys.modules[m]
+
+
+@pytest.mark.refonly
+def test_fused_optimizer_has_the_reference_constructor_and_entry_points():
+    from oracle import ref_harness as rh
+    ns = rh.import_reference()
+    from loner_b200.dropin.mapping_optimizer import FusedOptimizer, OptimizationSettings
+    ref = ns.optimizer.Optimizer
+    assert _params(ref.__init__) == _params(FusedOptimizer.__init__)
+    assert _params(ref.iterate_optimizer) == _params(FusedOptimizer.iterate_optimizer)
+    assert _params(ref._do_iterate_optimizer) == _params(FusedOptimizer._do_iterate_optimizer)
+    import dataclasses
+    assert [f.name for f in dataclasses.fields(ns.optimizer.OptimizationSettings)] == \
+        [f.name for f in dataclasses.fields(OptimizationSettings)]

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 
 def _engine_for(c: Case, sampler="OGM"):
     cfg = eng.EngineConfig(scale=c.scale, shift=tuple(c.shift.tolist()), ray_range=c.ray_range, n_frequencies=10,
-                           n_neurons=c.W, n_hidden_layers=c.L, n_samples=c.S, sampler=sampler)
+                           n_neurons=c.W, n_hidden_layers=c.L, n_samples=c.S, sampler=sampler,
+                           loss_selection=c.loss_selection)
     e = eng.MappingEngine(cfg, params=c.params)
     e.grid.copy_(c.grid[0, 0])
     for k in range(c.K):
@@ -33,7 +34,8 @@ def _run(c: Case):
     return e, loss, params0
 
 
-@pytest.mark.parametrize("name", ["kf2_4x256_fp16", "quad_4x256_fp16", "kf2_2x128_fp16"])
+@pytest.mark.parametrize("name", ["kf2_4x256_fp16", "quad_4x256_fp16", "kf2_2x128_fp16", "kf2_2x128_l2js",
+                                  "kf2_2x128_l1los"])
 def test_step_matches_reference_fixture(name):
     c = Case(name)
     e, loss, params0 = _run(c)
