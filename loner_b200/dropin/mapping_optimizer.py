@@ -81,13 +81,15 @@ class FusedOptimizer:
         enc, net = nc["pos_encoding_sigma"], nc["sigma_network"]
         if enc["otype"] != "Frequency":
             raise NotImplementedError("sigma-head encoding %r: only Frequency is implemented" % enc["otype"])
-        if mc.loss.loss_selection != "L1_JS":
-            raise NotImplementedError("loss_selection %r: only L1_JS is fused (the reference default)" % mc.loss.loss_selection)
+        if mc.loss.loss_selection not in ("L1_JS", "L2_JS", "L1_LOS", "L2_LOS"):
+            raise ValueError(f"Can't use unknown Loss {mc.loss.loss_selection}")
+        if mc.loss.decay_los_lambda:
+            raise NotImplementedError("decay_los_lambda (off in the reference defaults) is not fused")
         sampler = settings.samples_selection.strategy
         if sampler not in ("OGM", "UNIFORM"):
             raise RuntimeError(f"Can't find samples_selection strategy: {sampler}")
-        if settings.rays_selection.strategy != "RANDOM":
-            raise NotImplementedError("rays_selection %r: only RANDOM is fused" % settings.rays_selection.strategy)
+        if settings.rays_selection.strategy not in ("RANDOM", "FIXED", "MASK"):
+            raise RuntimeError(f"Can't find rays_selection strategy: {settings.rays_selection.strategy}")
         cfg = eng.EngineConfig(
             scale=float(world_cube.scale_factor), shift=tuple(float(x) for x in world_cube.shift),
             ray_range=tuple(float(x) for x in m.ray_range),
@@ -98,6 +100,11 @@ class FusedOptimizer:
             min_depth_eps=float(mc.loss.min_depth_eps), min_js=float(mc.loss.JS_loss.min_js_score),
             max_js=float(mc.loss.JS_loss.max_js_score), js_alpha=float(mc.loss.JS_loss.alpha),
             los_lambda=float(mc.loss.los_lambda), depthloss_lambda=float(mc.loss.depthloss_lambda),
+            loss_selection=mc.loss.loss_selection, depth_eps=float(mc.loss.get("depth_eps", 3.0)),
+            decay_depth_eps=bool(mc.loss.get("decay_depth_eps", True)),
+            depth_eps_decay_rate=float(mc.loss.get("depth_eps_decay_rate", 0.95)),
+            depth_eps_decay_steps=float(mc.loss.get("depth_eps_decay_steps", 1)),
+            rays_selection=settings.rays_selection.strategy,
             lrate_sigma_mlp=float(mc.train.lrate_sigma_mlp), lrate_pose=float(mc.train.lrate_pose),
             chunk_rays=min(int(m.render.chunk), 8192))
         self._engine = eng.MappingEngine(cfg, device=self._device)
@@ -129,7 +136,8 @@ class FusedOptimizer:
         k = self._kf_ids.get(id(kf))
         if k is None:
             scan = kf.get_lidar_scan()
-            k = self._engine.add_keyframe(scan.ray_directions, scan.distances, kf.get_lidar_pose().get_pose_tensor())
+            k = self._engine.add_keyframe(scan.ray_directions, scan.distances, kf.get_lidar_pose().get_pose_tensor(),
+                                          mask=getattr(scan, "mask", None))
             self._kf_ids[id(kf)] = k
         else:   # the tracker / previous phases may have moved the pose
             self._engine.poses6[k].data.copy_(kf.get_lidar_pose().get_pose_tensor().detach().to(self._device))

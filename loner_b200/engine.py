@@ -82,6 +82,7 @@ class EngineConfig:
     lrate_sigma_mlp: float = 0.01
     lrate_pose: float = 0.001
     # engine
+    rays_selection: str = "RANDOM"      # RANDOM | FIXED | MASK   (optimizer.py:286-296)
     chunk_rays: int = 8192
     seed: int = 0
 
@@ -122,6 +123,7 @@ class MappingEngine:
         self.points = None
         self.kf_offsets = []
         self.kf_sizes = []
+        self.kf_masks = []
         self.poses6 = []            # list of [6] leaf tensors on device
         self.pose_opt = None
         self.gen = torch.Generator(device=self.dev)
@@ -142,7 +144,9 @@ class MappingEngine:
         self._loss_acc = torch.zeros(4, device=self.dev, dtype=torch.float32)
 
     # ---------------------------------------------------------------- keyframes
-    def add_keyframe(self, ray_directions, distances, pose6):
+    def add_keyframe(self, ray_directions, distances, pose6, mask=None):
+        """mask: optional bool [M] (LidarScan.mask) used by rays_selection = MASK."""
+        self.kf_masks.append(None if mask is None else mask.nonzero(as_tuple=True)[0].to(self.dev))
         pts = ops.pack_points(ray_directions, distances).to(self.dev)
         off = 0 if self.points is None else self.points.shape[0]
         self.points = pts if self.points is None else torch.cat([self.points, pts])
@@ -206,8 +210,23 @@ class MappingEngine:
 
     def _pick_rays(self, window, n_per_kf):
         c = self._window_consts(window, n_per_kf)
-        u = torch.rand(len(window), n_per_kf, device=self.dev, generator=self.gen)
-        idx = torch.minimum((u * c["sizes"]).long(), c["maxi"])
+        strategy = self.cfg.rays_selection
+        if strategy == "RANDOM":                      # torch.randint(len(scan), (n,))          optimizer.py:288
+            u = torch.rand(len(window), n_per_kf, device=self.dev, generator=self.gen)
+            idx = torch.minimum((u * c["sizes"]).long(), c["maxi"])
+        elif strategy == "FIXED":                     # torch.arange(n)                          optimizer.py:293-294
+            idx = torch.arange(n_per_kf, device=self.dev)[None, :].expand(len(window), n_per_kf)
+        elif strategy == "MASK":                      # random picks among scan.mask.nonzero()   optimizer.py:289-292
+            rows = []
+            for k in window:
+                m = self.kf_masks[k]
+                if m is None:
+                    raise RuntimeError("rays_selection MASK needs add_keyframe(..., mask=...)")
+                u = torch.rand(n_per_kf, device=self.dev, generator=self.gen)
+                rows.append(m[torch.clamp((u * m.numel()).long(), max=m.numel() - 1)])
+            idx = torch.stack(rows)
+        else:
+            raise RuntimeError(f"Can't find rays_selection strategy: {strategy}")
         return c["ray_kf"], (idx + c["offs"]).reshape(-1)
 
     def _poses12(self, window, optimize_poses):

@@ -100,3 +100,26 @@ def test_full_size_step_properties():
         outs.append(dp)
     err = float((outs[0] + outs[1] - outs[2]).norm() / outs[2].norm())
     assert err < 2e-3, err                                            # fp16 rounding of the scaled gradients only
+
+
+def test_ray_selection_strategies():
+    """FIXED = arange(n), MASK = random picks among the scan mask (optimizer.py:286-296)."""
+    wc = synth.world_cube("canteen")
+    scans, poses = synth.make_window("canteen", 1, seed=0, n_beams=16, n_azimuth=256)
+    M = scans[0].distances.shape[0]
+    mask = torch.zeros(M, dtype=torch.bool)
+    mask[100:164] = True
+    for strategy in ("FIXED", "MASK", "RANDOM"):
+        cfg = eng.EngineConfig(scale=wc.scale_factor, shift=wc.shift, ray_range=(1.0, 50.0), n_neurons=128,
+                               n_hidden_layers=2, n_samples=64, rays_selection=strategy)
+        e = eng.MappingEngine(cfg)
+        e.add_keyframe(scans[0].ray_directions, scans[0].distances, synth.axis_angle_from_yaw_pose(poses[0]), mask=mask)
+        _, rp = e._pick_rays([0], 256)
+        if strategy == "FIXED":
+            assert torch.equal(rp.cpu(), torch.arange(256))
+        elif strategy == "MASK":
+            assert int(rp.min()) >= 100 and int(rp.max()) < 164
+        else:
+            assert int(rp.min()) >= 0 and int(rp.max()) < M and rp.unique().numel() > 200
+        loss = e.step([0], 256)
+        assert torch.isfinite(loss)
