@@ -682,12 +682,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
       }
       fence_async_smem();
       mbar_arrive(sm.a_ready[t]);
-      group_bar(t);
-      {
-        uint8_t* gimg = a.dz + tile * dz_tile_bytes(net) + (int64_t)(net.L - 1) * kNb * kBlk;
-        if (active && !a.bulk) copy_image(stile, gimg, kNb * kBlk, (e & 7) * 32 + lane);
-        if (active && a.bulk && elected) { bulk_s2g(gimg, stile, (uint32_t)(kNb * kBlk)); bulk_commit(); }
-      }
+      // (the dZ_L image is NOT stashed: wgrad rebuilds it from the masks, d_sigma and w_out)
       for (int l = net.L - 1; l >= l_lo; --l) {
         mbar_wait(sm.acc_full[t], par_acc);
         par_acc ^= 1u;
@@ -776,20 +771,29 @@ struct WgradArgs {
   const uint8_t* dz;
   int64_t tiles;
   float* partials;           // [items][K_l*N_l]
+  // dZ_L = relu'(Z_L) * d_sigma * w_out is rank-1 times a bit mask: the CTAs of layer L-1 rebuild its
+  // image in shared memory from these instead of reading 64 KB/tile that dgrad would have to write.
+  const uint8_t* masks;
+  const float* d_sigma;
+  const float* wout;         // [W] fp32 values of the fp16-rounded output weights (packed image)
+  float gscale;
+  int64_t P;
   int item_begin[9];         // first item of each layer (prefix), item_begin[L] = total
   int64_t part_off[9];       // float offset of each layer's first partial
 };
 
 constexpr int kWgStages = 3;
 constexpr int kWgStageBytes = 65536;    // 64 samples: A half (<= 32 KB) | dZ half (<= 32 KB)
-constexpr int kWgThreads = 192;
-constexpr int kWgSmem = 1024 + kWgStages * kWgStageBytes + 1024;
+constexpr int kWgThreads = 320;     // warp 0 producer, warp 1 MMA, warps 2-5 epilogue (+ generators), warps 6-9 generators
+constexpr int kWgGen = 256;         // generator threads
+constexpr int kWgSmem = 1024 + kWgStages * kWgStageBytes + 2048;
 
 __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + kWgStages * kWgStageBytes);
+  float* s_wout = reinterpret_cast<float*>(base + kWgStages * kWgStageBytes);          // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_wout + 256);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
   const Net net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -807,12 +811,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
   auto empty_bar = [&](int s) { return smem_u32(&bars[kWgStages + s]); };
   const uint32_t done_bar = smem_u32(&bars[2 * kWgStages]);
 
+  const bool gen_y = (l == net.L - 1);           // this CTA rebuilds dZ_L instead of loading it
   if (warp == 0) tmem_alloc<512>(smem_u32(s_tmem));
   if (tid == 32) {
-    for (int s = 0; s < kWgStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(full_bar(s), gen_y ? 1 + kWgGen : 1); mbar_init(empty_bar(s), 1); }
     mbar_init(done_bar, 1);
     fence_mbar_init();
   }
+  for (int j = tid; j < net.W; j += kWgThreads) s_wout[j] = a.wout[j];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -835,11 +841,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
       const int64_t tile = t0 + (i >> 1);
       const int hf = (int)(i & 1);
       const uint32_t dstA = smem_u32(base + s * kWgStageBytes), dstY = dstA + 32768;
-      mbar_expect_tx(full_bar(s), bytesA + bytesY);
+      mbar_expect_tx(full_bar(s), gen_y ? bytesA : bytesA + bytesY);
       const uint8_t* srcA = a.acts + tile * act_tile_bytes(net) + actA_off + hf * 8192;
       const uint8_t* srcY = a.dz + tile * dz_tile_bytes(net) + dzY_off + hf * 8192;
       for (int cb = 0; cb < nbA; ++cb) bulk_g2s(dstA + cb * 8192, srcA + (int64_t)cb * kBlk, 8192, full_bar(s));
-      for (int cb = 0; cb < nbY; ++cb) bulk_g2s(dstY + cb * 8192, srcY + (int64_t)cb * kBlk, 8192, full_bar(s));
+      if (!gen_y)
+        for (int cb = 0; cb < nbY; ++cb) bulk_g2s(dstY + cb * 8192, srcY + (int64_t)cb * kBlk, 8192, full_bar(s));
     }
   } else if (tid == 32) {
     // ---- MMA issuer.  Both operands MN-major: 64-element MN blocks 8 KB apart (LBO), 8-sample
@@ -868,7 +875,52 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
     umma_commit(done_bar);
   }
   __syncwarp();
-  if (warp >= 2) {
+  if (warp >= 2 && gen_y) {
+    // ---- generators (8 warps; four of them are the epilogue warps, idle during the main loop):
+    // thread = (row of the 64-sample half tile, quarter of the columns)
+    const int g = tid - 64;                       // 0..255
+    const int r = g >> 2, qc = g & 3;
+    const int cpt = net.W / 4;                    // columns per thread: 64 (W=256) or 32 (W=128)
+    const int mwords = net.W / 32;
+    for (int64_t i = 0; i < n_half; ++i) {
+      const int s = (int)(i % kWgStages);
+      const uint32_t ph = (uint32_t)((i / kWgStages) & 1);
+      const int64_t tile = t0 + (i >> 1);
+      const int row = (int)(i & 1) * 64 + r;      // row inside the 128-sample tile
+      const int64_t gs = tile * kTile + row;
+      const float ds = gs < a.P ? __ldg(a.d_sigma + gs) * a.gscale : 0.f;
+      const uint32_t* mrow = reinterpret_cast<const uint32_t*>(a.masks + tile * mask_tile_bytes(net)) +
+                             ((int64_t)(net.L - 1) * kTile + row) * mwords + qc * (cpt / 32);
+      const uint32_t mw0 = __ldg(mrow), mw1 = (cpt > 32) ? __ldg(mrow + 1) : 0u;
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      const uint32_t sY = smem_u32(base + s * kWgStageBytes) + 32768 + (uint32_t)r * 128;
+      const uint32_t xs = (uint32_t)(r & 7) << 4;
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        if (it * 32 < cpt) {
+          const uint32_t bits = it == 0 ? mw0 : mw1;
+          const int col0 = qc * cpt + it * 32;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i0 = ch * 8 + 2 * e;
+              const float2 w2 = *reinterpret_cast<const float2*>(s_wout + col0 + i0);
+              const float g0 = ((bits >> i0) & 1u) ? ds * w2.x : 0.f;
+              const float g1 = ((bits >> (i0 + 1)) & 1u) ? ds * w2.y : 0.f;
+              w[e] = cvt_sat_h2(g0, g1);
+            }
+            const int c0 = col0 + ch * 8;
+            sts128(sY + (uint32_t)(c0 >> 6) * 8192u + ((((uint32_t)(c0 & 63) >> 3) << 4) ^ xs), w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(full_bar(s));
+    }
+  }
+  if (warp >= 2 && warp < 6) {
     // ---- epilogue: TMEM -> partial sums in [out n][in k] order (the flat params order)
     mbar_wait(done_bar, 0);
     tc_fence_after();
@@ -1124,6 +1176,8 @@ extern "C" int loner_mlp_wgrad(const loner_net_t* n, const void* packed, int64_t
   const WgradPlan plan = plan_wgrad(net);
   WgradArgs w;
   w.net = net; w.acts = (const uint8_t*)acts; w.dz = dz; w.tiles = tiles; w.partials = partials;
+  w.masks = (const uint8_t*)acts + tiles * act_tile_bytes(net); w.d_sigma = d_sigma;
+  w.wout = reinterpret_cast<const float*>((const uint8_t*)packed + packed_wout_off(net)); w.gscale = grad_scale; w.P = P;
   for (int i = 0; i <= net.L; ++i) { w.item_begin[i] = plan.item_begin[i]; w.part_off[i] = plan.part_off[i]; }
   cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
   mlp_wgrad_kernel<<<(unsigned)plan.total_items, kWgThreads, kWgSmem, st>>>(w);
