@@ -96,57 +96,65 @@ __global__ void pack_kernel(Net net, const float* __restrict__ params, uint8_t* 
 // ------------------------------------------------------------------------------------------
 // Shared pieces of the two pipelined kernels (forward, dgrad).
 //
-// One CTA per SM, 576 threads:  warp 0 = weight producer (bulk copies into a 3-slot ring),
-// warp 1 = MMA issuer, warps 2-9 = epilogue group of tile X, warps 10-17 = epilogue group of tile Y
-// (two warps per TMEM lane quarter, each owning half of the columns).
-// Two tiles of 128 samples are in flight with one 256-column TMEM accumulator each; the MMA order
-// inside a layer is X[c0,c1] Y[c0,c1] X[c2,c3] Y[c2,c3] so that every 32 KB weight chunk is read
-// from L2 once per tile PAIR and X's epilogue overlaps Y's last MMAs (and vice versa).
-constexpr int kPipeThreads = 576;
+// One CTA per SM, 320 threads:  warp 0 = weight producer (bulk copies into a 3-slot ring),
+// warp 1 = MMA issuer, warps 2-9 = epilogue (two warps per TMEM lane quarter, each owning half of the
+// columns).  Two tiles of 128 samples are in flight with one 256-column TMEM accumulator each; inside
+// a layer the MMAs of tile X (all K chunks) are followed by those of tile Y, and all eight epilogue
+// warps drain X, then Y.  X's epilogue therefore has the whole of Y's tensor time to finish (and vice
+// versa): the layer period is max(2 T_mma, T_mma + E) for an epilogue time E per tile.  The weight
+// chunks are fetched once per TILE (from L2; sharing them between the tiles would force the order
+// X[c0,c1] Y[c0,c1] X[c2,c3] Y[c2,c3] and the period max(2 T_mma, 2E + T_mma), measured 1.5x slower).
+// Ten warps leave 168 registers per thread: three 32-column TMEM buffers, i.e. 4-8 KB per warp in
+// flight (tests/gpu_probe.py: 8 warps reach 99 / 140 B/clk with one / two 4 KB loads in flight).
+constexpr int kPipeThreads = 320;
 constexpr int kGroupThreads = 256;
 constexpr int kRingSlots = 3;
 constexpr int kSlotBytes = 32768;
 constexpr int kPipeSmem = 2 * 65536 + kRingSlots * kSlotBytes + 2304;
 
+// Shared-memory map of the two pipelined kernels.  Everything is an ADDRESS COMPUTATION (no arrays of
+// pointers): a table indexed by a run-time slot number would live in local memory, and local loads
+// miss the (tiny, 28 KB) L1 behind a saturated HBM.
 struct PipeSmem {
-  uint8_t* tileA[2];
-  uint8_t* ring;
-  float* wout;        // [256]
-  float* part;        // [2][128] per-row partial sums handed from the upper column half to the lower
-  uint32_t w_full[kRingSlots], w_empty[kRingSlots], a_ready[2], acc_full[2];
-  uint32_t* tmem_slot;
+  uint8_t* base;
+  uint32_t base_u32;
+  __device__ __forceinline__ uint8_t* tileA_ptr(int t) const { return base + t * 65536; }
+  __device__ __forceinline__ uint32_t tileA(int t) const { return base_u32 + (uint32_t)t * 65536u; }
+  __device__ __forceinline__ uint32_t ring(uint32_t slot) const { return base_u32 + 131072u + slot * (uint32_t)kSlotBytes; }
+  __device__ __forceinline__ float* wout() const { return reinterpret_cast<float*>(base + 131072 + kRingSlots * kSlotBytes); }
+  __device__ __forceinline__ float* part() const { return wout() + 256; }   // [2][128] per-row partial sums (upper -> lower column half)
+  __device__ __forceinline__ uint32_t bars() const { return base_u32 + 131072u + kRingSlots * kSlotBytes + 2048u; }
+  __device__ __forceinline__ uint32_t w_full(uint32_t i) const { return bars() + 8u * i; }
+  __device__ __forceinline__ uint32_t w_empty(uint32_t i) const { return bars() + 8u * (kRingSlots + i); }
+  __device__ __forceinline__ uint32_t a_ready(int t) const { return bars() + 8u * (2 * kRingSlots + t); }
+  __device__ __forceinline__ uint32_t acc_full(int t) const { return bars() + 8u * (2 * kRingSlots + 2 + t); }
+  __device__ __forceinline__ uint32_t* tmem_slot() const {
+    return reinterpret_cast<uint32_t*>(base + 131072 + kRingSlots * kSlotBytes + 2048 + 8 * (2 * kRingSlots + 4));
+  }
 };
 
 __device__ __forceinline__ PipeSmem carve(uint8_t* base) {
   PipeSmem p;
-  p.tileA[0] = base;
-  p.tileA[1] = base + 65536;
-  p.ring = base + 131072;
-  p.wout = reinterpret_cast<float*>(base + 131072 + kRingSlots * kSlotBytes);
-  p.part = p.wout + 256;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(p.part + 256);
-  for (int i = 0; i < kRingSlots; ++i) { p.w_full[i] = smem_u32(&bars[i]); p.w_empty[i] = smem_u32(&bars[kRingSlots + i]); }
-  p.a_ready[0] = smem_u32(&bars[2 * kRingSlots]); p.a_ready[1] = smem_u32(&bars[2 * kRingSlots + 1]);
-  p.acc_full[0] = smem_u32(&bars[2 * kRingSlots + 2]); p.acc_full[1] = smem_u32(&bars[2 * kRingSlots + 3]);
-  p.tmem_slot = reinterpret_cast<uint32_t*>(&bars[2 * kRingSlots + 4]);
+  p.base = base;
+  p.base_u32 = smem_u32(base);
   return p;
 }
 
 __device__ __forceinline__ void pipe_init(const PipeSmem& sm, int tid, int warp, const float* wout_src, int W) {
-  if (warp == 1) tmem_alloc<512>(smem_u32(sm.tmem_slot));
+  if (warp == 1) tmem_alloc<512>(smem_u32(sm.tmem_slot()));
   if (tid == 0) {
-    for (int i = 0; i < kRingSlots; ++i) { mbar_init(sm.w_full[i], 1); mbar_init(sm.w_empty[i], 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(sm.a_ready[t], kGroupThreads); mbar_init(sm.acc_full[t], 1); }
+    for (int i = 0; i < kRingSlots; ++i) { mbar_init(sm.w_full(i), 1); mbar_init(sm.w_empty(i), 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(sm.a_ready(t), kGroupThreads); mbar_init(sm.acc_full(t), 1); }
     fence_mbar_init();
   }
-  for (int j = tid; j < W; j += kPipeThreads) sm.wout[j] = wout_src[j];
+  for (int j = tid; j < W; j += kPipeThreads) sm.wout()[j] = wout_src[j];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
 }
 
-__device__ __forceinline__ void group_bar(int group) {
-  asm volatile("bar.sync %0, 256;" ::"r"(group + 1) : "memory");
+__device__ __forceinline__ void epi_bar() {   // the 256 epilogue threads
+  asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
 // two fp32 -> packed half2 (lo = a, hi = b) with ReLU folded into the conversion
@@ -160,122 +168,67 @@ __device__ __forceinline__ uint32_t cvt_sat_h2(float a, float b) {   // saturate
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
-// bits |= (v > 0) << kBit in two instructions (FSETP + predicated LOP3)
-template <int kBit>
-__device__ __forceinline__ void set_bit_if_pos(uint32_t& bits, float v) {
-  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, 0f00000000;\n\t@p or.b32 %0, %0, %2;\n\t}"
-      : "+r"(bits)
-      : "f"(v), "n"(1u << kBit));
+
+// ReLU mask word of 32 columns given as 16 packed half2 (post-ReLU, so "active" = non-zero fp16 output,
+// which is what tcnn's backward tests too).  Bit p = column 2p, bit 16+p = column 2p+1: one HSET2 and
+// one LOP3 per PAIR of columns.  mask_bit(bits, c) is the inverse mapping.
+__device__ __forceinline__ uint32_t relu_mask_word(const uint32_t (&hh)[16]) {
+  uint32_t m = 0u;
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    uint32_t gt;
+    asm("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(gt) : "r"(hh[p]), "r"(0u));
+    m |= gt & ((1u << p) | (1u << (16 + p)));
+  }
+  return m;
+}
+__device__ __forceinline__ bool mask_bit(uint32_t bits, int c) {   // c = column within the 32-column word
+  return ((bits >> ((c >> 1) + 16 * (c & 1))) & 1u) != 0u;
 }
 
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
-               : "memory");
+
+// 32 columns (16 packed half2) of this thread's row into the swizzled tile image in shared memory.
+// srow = the row's base inside the tile, xs = (row & 7) << 4, col0 = first column (multiple of 32).
+__device__ __forceinline__ void store32(uint32_t srow, uint32_t xs, int col0, const uint32_t (&hh)[16]) {
+  const uint32_t cb_off = (uint32_t)(col0 >> 6) * kBlk;
+  const uint32_t j0 = ((uint32_t)(col0 & 63) >> 3) << 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    sts128(srow + cb_off + ((j0 + 16u * k) ^ xs), hh[4 * k], hh[4 * k + 1], hh[4 * k + 2], hh[4 * k + 3]);
 }
 
-// One 32-column slab of an epilogue: `pack(i)` yields the packed half2 of this row's columns
-// (col0+i, col0+i+1).  The four 16-byte chunks go to the shared-memory tile image (`srow` = the
-// row's base inside the tile, or null) and/or straight to the image in HBM (`grow`, or null) as
-// two 32-byte sectors: chunks 2m and 2m+1 share a sector, swapped when the row's swizzle is odd.
-// xs = (row & 7) << 4.
-template <class F>
-__device__ __forceinline__ void store_slab(uint32_t srow, uint8_t* grow, uint32_t xs, int col0, F&& pack) {
-  const bool odd = (xs & 16u) != 0u;
-#pragma unroll
-  for (int m = 0; m < 2; ++m) {
-    uint32_t a[4], b[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { a[e] = pack(m * 16 + 2 * e); b[e] = pack(m * 16 + 8 + 2 * e); }
-    const int c0 = col0 + m * 16;                                        // first column of chunk 2m'
-    const uint32_t cb_off = (uint32_t)(c0 >> 6) * kBlk;
-    const uint32_t j0 = ((uint32_t)(c0 & 63) >> 3) << 4;                  // logical chunk byte offset (even chunk)
-    if (srow != 0u) {
-      sts128(srow + cb_off + (j0 ^ xs), a[0], a[1], a[2], a[3]);
-      sts128(srow + cb_off + ((j0 + 16u) ^ xs), b[0], b[1], b[2], b[3]);
-    }
-    if (grow != nullptr) {
-      uint32_t w[8];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { w[e] = odd ? b[e] : a[e]; w[4 + e] = odd ? a[e] : b[e]; }
-      st_global_256(grow + cb_off + (j0 ^ (xs & 0x60u)), w);
-    }
-  }
-}
-
-// Half a slab: 16 columns = chunks (2m, 2m+1) = one 32-byte sector of the image.  hh[8] = packed half2.
-__device__ __forceinline__ void store16(uint32_t srow, uint8_t* grow, uint32_t xs, int c0, const uint32_t (&hh)[8]) {
-  const uint32_t cb_off = (uint32_t)(c0 >> 6) * kBlk;
-  const uint32_t j0 = ((uint32_t)(c0 & 63) >> 3) << 4;
-  if (srow != 0u) {
-    sts128(srow + cb_off + (j0 ^ xs), hh[0], hh[1], hh[2], hh[3]);
-    sts128(srow + cb_off + ((j0 + 16u) ^ xs), hh[4], hh[5], hh[6], hh[7]);
-  }
-  if (grow != nullptr) {
-    const bool odd = (xs & 16u) != 0u;
-    uint32_t w[8];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { w[e] = odd ? hh[4 + e] : hh[e]; w[4 + e] = odd ? hh[e] : hh[4 + e]; }
-    st_global_256(grow + cb_off + (j0 ^ (xs & 0x60u)), w);
-  }
-}
-
-// Copies this thread's kCols columns of its row from the shared-memory tile image to the image in HBM
-// (32-byte sectors).  Runs AFTER the tile has been handed to the MMA warp, so that store back-pressure
-// from HBM never sits between an epilogue and the next layer's tensor-core work.
-template <int kCols>
-__device__ __forceinline__ void copy_out(uint32_t srow, uint8_t* grow, uint32_t xs, int col_begin) {
-  const bool odd = (xs & 16u) != 0u;
-#pragma unroll
-  for (int i = 0; i < kCols / 16; ++i) {
-    const int c0 = col_begin + i * 16;
-    const uint32_t cb_off = (uint32_t)(c0 >> 6) * kBlk;
-    const uint32_t j0 = ((uint32_t)(c0 & 63) >> 3) << 4;
-    const uint4 a = lds128(srow + cb_off + (j0 ^ xs));
-    const uint4 b = lds128(srow + cb_off + ((j0 + 16u) ^ xs));
-    const uint4 lo = odd ? b : a, hi = odd ? a : b;
-    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    st_global_256(grow + cb_off + (j0 ^ (xs & 0x60u)), w);
-  }
-}
-
-// Linear, fully coalesced copy of a finished tile image (contiguous in shared memory and in HBM) by
-// the 256 threads of an epilogue group: every warp instruction moves 512 contiguous bytes.
-__device__ __forceinline__ void copy_image(uint32_t simg, uint8_t* gimg, int bytes, int gtid) {
-  for (int off = gtid * 16; off < bytes; off += kGroupThreads * 16) {
-    const uint4 v = lds128(simg + off);
-    asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(gimg + off), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                 : "memory");
-  }
-}
-
-// Drains kCols accumulator columns of this thread's TMEM lane in 16-column loads, keeping the next
-// load in flight while `proc(i, v)` works on the current one (tcgen05.ld latency is ~300-450 clk,
-// tests/gpu_probe.py).
+// Drains kCols accumulator columns of this thread's TMEM lane in 32-column loads.  128 columns: two
+// loads are issued before the first wait and the third / fourth go out while the first / second are
+// being processed, so 4-8 KB per warp stay in flight (tcgen05.wait::ld waits for ALL outstanding
+// loads, hence the grouping).  pin32() keeps the compiler from moving uses above the issue points.
 template <int kCols, class Proc>
-__device__ __forceinline__ void drain_cols(uint32_t acc, Proc&& proc) {
-  uint32_t va[16], vb[16];
-  tmem_ld16(acc, va);
-  tmem_ld_wait16(va);
-#pragma unroll
-  for (int i = 0; i < kCols / 16; ++i) {
-    if (i & 1) {
-      if (i + 1 < kCols / 16) { tmem_ld16(acc + (i + 1) * 16, va); pin16(vb); }
-      proc(i, vb);
-      if (i + 1 < kCols / 16) tmem_ld_wait16(va);
-    } else {
-      if (i + 1 < kCols / 16) { tmem_ld16(acc + (i + 1) * 16, vb); pin16(va); }
-      proc(i, va);
-      if (i + 1 < kCols / 16) tmem_ld_wait16(vb);
-    }
+__device__ __forceinline__ void drain32(uint32_t acc, Proc&& proc) {
+  static_assert(kCols == 64 || kCols == 128, "column halves of W = 128 / 256");
+  uint32_t b0[32], b1[32];
+  tmem_ld32(acc, b0);
+  tmem_ld32(acc + 32, b1);
+  tmem_ld_wait();
+  pin32(b0);
+  pin32(b1);
+  if constexpr (kCols == 128) {
+    uint32_t b2[32], b3[32];
+    tmem_ld32(acc + 64, b2);
+    pin32(b0);
+    proc(0, b0);
+    tmem_ld32(acc + 96, b3);
+    pin32(b1);
+    proc(1, b1);
+    tmem_ld_wait();
+    pin32(b2);
+    pin32(b3);
+    proc(2, b2);
+    proc(3, b3);
+  } else {
+    proc(0, b0);
+    proc(1, b1);
   }
 }
 
@@ -326,7 +279,8 @@ struct FwdArgs {
   float* sigma;          // [P]
   uint8_t* acts;         // activation stash or null
   uint8_t* masks;        // relu bit masks or null
-  int bulk;              // stash images leave through cp.async.bulk (1) or a thread copy (0)
+  int share_w;           // weight chunks serve both tiles of a pair (1) or are fetched per tile (0)
+  int x4;                // MMAs issued four per asm statement
 };
 
 // sin/cos(pi * 2^f * x).  2^f * x is exact in fp32, and so is its reduction r to [-1, 1]; sin(pi r) and
@@ -343,11 +297,10 @@ __device__ __forceinline__ void freq_pair(float x, float scale, float& s, float&
 // Writes encoded features [32*half, 32*half+32) of row r (column block 0 of `sA`): features
 // [0, 6F) are sin/cos pairs ordered [dim][freq][sin,cos], [6F, Epad) = 1.0 (tcnn pads the encoded
 // width to 16 with ones), rest 0.  (dim0, f0) = position of feature pair 16*half, precomputed.
-__device__ __forceinline__ void encode_row(uint32_t sA, uint8_t* grow, int r, int half, const float (&x)[3],
-                                           const Net& net, int dim0, int f0) {
+__device__ __forceinline__ void encode_row(uint32_t sA, int r, int half, const float (&x)[3], const Net& net,
+                                           int dim0, int f0) {
   int dim = dim0, f = f0;
   float scale = (float)(1 << f0);
-  uint32_t keep[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int cj = half * 4 + c;
@@ -368,23 +321,8 @@ __device__ __forceinline__ void encode_row(uint32_t sA, uint8_t* grow, int r, in
       ++f; scale *= 2.0f;
       if (f == net.F) { f = 0; scale = 1.0f; ++dim; }
     }
-    {
-      const uint32_t* hw0 = reinterpret_cast<const uint32_t*>(h);
-      sts128(sA + r * 128 + ((cj ^ (r & 7)) * 16), hw0[0], hw0[1], hw0[2], hw0[3]);
-    }
-    if (grow != nullptr) {                 // chunks cj (even) and cj+1 share one 32-byte sector of the image
-      const uint32_t* hw = reinterpret_cast<const uint32_t*>(h);
-      if ((c & 1) == 0) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) keep[e] = hw[e];
-      } else {
-        const bool odd = (r & 1) != 0;
-        uint32_t w[8];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { w[e] = odd ? hw[e] : keep[e]; w[4 + e] = odd ? keep[e] : hw[e]; }
-        st_global_256(grow + (((cj - 1) ^ (r & 6)) * 16), w);
-      }
-    }
+    const uint32_t* hw = reinterpret_cast<const uint32_t*>(h);
+    sts128(sA + r * 128 + ((cj ^ (r & 7)) * 16), hw[0], hw[1], hw[2], hw[3]);
   }
 }
 
@@ -396,7 +334,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
   const Net net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pipe_init(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W);
-  const uint32_t tmem = *sm.tmem_slot;
+  const uint32_t tmem = *sm.tmem_slot();
   const int64_t pairs = (a.tiles + 1) / 2;
   constexpr int kNb = W / 64;
   constexpr uint32_t kChunkBytes = kNb * 8192;      // 64 K-rows x W out-features, fp16
@@ -409,12 +347,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
       for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
         for (int l = 0; l < net.L; ++l) {
           const int nch = (l == 0) ? 1 : kNb;
-          for (int c = 0; c < nch; ++c, ++g) {
-            const uint32_t slot = g % kRingSlots, use = g / kRingSlots;
-            if (use > 0) mbar_wait(sm.w_empty[slot], (use - 1) & 1);
-            mbar_expect_tx(sm.w_full[slot], kChunkBytes);
-            bulk_g2s(smem_u32(sm.ring + slot * kSlotBytes), fimg + fwd_off(net, l) + (int64_t)c * kChunkBytes,
-                     kChunkBytes, sm.w_full[slot]);
+          const int reps = a.share_w ? 1 : 2;      // chunks fetched once per tile PAIR, or once per tile
+          for (int t = 0; t < reps; ++t) {
+            for (int c = 0; c < nch; ++c, ++g) {
+              const uint32_t slot = g % kRingSlots, use = g / kRingSlots;
+              if (use > 0) mbar_wait(sm.w_empty(slot), (use - 1) & 1);
+              mbar_expect_tx(sm.w_full(slot), kChunkBytes);
+              bulk_g2s(sm.ring(slot), fimg + fwd_off(net, l) + (int64_t)c * kChunkBytes, kChunkBytes, sm.w_full(slot));
+            }
           }
         }
       }
@@ -423,136 +363,146 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
     if (lane == 0) {
       // ---------------- MMA issuer
       constexpr uint32_t idesc = make_idesc_f16(128, W, 0, 1);
-      uint32_t g_base = 0, par_a[2] = {0u, 0u};
+      uint32_t g = 0, par_a = 0u;
       for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
         for (int l = 0; l < net.L; ++l) {
           const int nch = (l == 0) ? 1 : kNb;
           const int ksteps0 = (l == 0) ? net.Epad / 16 : 4;   // layer 0 contracts over Epad (<= 64) features
-          for (int c0 = 0; c0 < nch; c0 += 2) {
-            const int c1 = min(c0 + 2, nch);
+          // share_w: X[c0,c1] Y[c0,c1] X[c2,c3] Y[c2,c3], a chunk serves both tiles; else X[all] Y[all]
+          const int cstep = a.share_w ? 2 : nch;
+          for (int c0 = 0; c0 < nch; c0 += cstep) {
+            const int c1 = min(c0 + cstep, nch);
             for (int t = 0; t < 2; ++t) {
-              if (c0 == 0) { mbar_wait(sm.a_ready[t], par_a[t]); par_a[t] ^= 1u; tc_fence_after(); }
+              if (c0 == 0) { mbar_wait(sm.a_ready(t), par_a); tc_fence_after(); }
               for (int c = c0; c < c1; ++c) {
-                const uint32_t g = g_base + c, slot = g % kRingSlots;
-                if (t == 0) { mbar_wait(sm.w_full[slot], (g / kRingSlots) & 1); tc_fence_after(); }
-                const uint32_t sa = smem_u32(sm.tileA[t]) + c * kBlk, sb = smem_u32(sm.ring + slot * kSlotBytes);
-                for (int ks = 0; ks < ksteps0; ++ks) {
-                  const uint64_t ad = make_desc_sw128(sa + ks * 32, 16, 1024);
-                  const uint64_t bd = make_desc_sw128(sb + ks * 2048, 8192, 1024);
-                  umma_f16(tmem + t * 256, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                const uint32_t gc = a.share_w ? g + c : g + t * nch + c, slot = gc % kRingSlots;
+                if (t == 0 || !a.share_w) { mbar_wait(sm.w_full(slot), (gc / kRingSlots) & 1); tc_fence_after(); }
+                const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
+                const uint32_t release = (t == 1 || !a.share_w) ? sm.w_empty(slot) : 0u;
+                if (ksteps0 == 4 && a.x4) {
+                  umma_f16_x4<2, 128>(tmem + t * 256, desc_lo_sw128(sa, 16), desc_hi_sw128(1024), desc_lo_sw128(sb, 8192),
+                                      desc_hi_sw128(1024), idesc, c > 0 ? 1u : 0u, release);
+                } else {
+                  for (int ks = 0; ks < ksteps0; ++ks) {
+                    const uint64_t ad = make_desc_sw128(sa + ks * 32, 16, 1024);
+                    const uint64_t bd = make_desc_sw128(sb + ks * 2048, 8192, 1024);
+                    umma_f16(tmem + t * 256, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                  }
+                  if (release) umma_commit(release);
                 }
-                if (t == 1) umma_commit(sm.w_empty[slot]);     // both tiles have consumed this chunk
               }
-              if (c1 == nch) umma_commit(sm.acc_full[t]);
+              if (c1 == nch) umma_commit(sm.acc_full(t));
             }
           }
-          g_base += nch;
+          g += a.share_w ? nch : 2 * nch;
+          par_a ^= 1u;
         }
       }
     }
   } else {
-    // ---------------- epilogue groups: thread = (sample row, column half)
+    // ---------------- epilogue warps: thread = (sample row, column half); tile X, then tile Y.
+    // Stash mode: every finished image (A_0 .. A_L) leaves its tile buffer as ONE bulk copy issued by
+    // the elected thread after the step's barrier.  The elected thread waits for the reads of all
+    // earlier copies BEFORE that barrier, and the steps alternate X, Y, X, ... - so whenever a step
+    // starts writing a tile buffer, the copy issued from it two steps ago has been read out.
     const int e = warp - 2;
-    const int t = e >> 3;
-    const int h = (e & 7) >> 2;
+    const int h = e >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const uint32_t sA = smem_u32(sm.tileA[t]);
-    const uint32_t srow = sA + row * 128;
-    const bool elected = ((e & 7) == 0) && lane == 0;
+    const bool elected = (e == 0) && lane == 0;
     const uint32_t xs = (uint32_t)(row & 7) << 4;
     constexpr int kCols = W / 2;                      // columns per thread
-    const uint32_t acc = tmem + t * 256 + ((uint32_t)(q * 32) << 16) + h * kCols;
-    float* part = sm.part + t * 128;
+    const uint32_t acc_base = tmem + ((uint32_t)(q * 32) << 16) + h * kCols;
     uint32_t par_acc = 0;
     const int enc_dim0 = (16 * h) / net.F, enc_f0 = (16 * h) % net.F;
     const bool pos_mode = a.pos != nullptr;
-    auto row_index = [&](int64_t pair) {
+    auto row_index = [&](int64_t pair, int t) {
       int64_t gs = (2 * pair + t) * kTile + row;
       return gs < a.P ? gs : a.P - 1;
     };
-    RowIn nxt = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, row_index(blockIdx.x));
+    RowIn nxt[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) nxt[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, row_index(blockIdx.x, t));
     for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
-      const int64_t tile = 2 * pair + t;
-      const bool active = tile < a.tiles;
-      const int64_t gs = tile * kTile + row;
-      const bool in = active && gs < a.P;
-      uint8_t* gtile = (kStash && active) ? a.acts + tile * act_tile_bytes(net) + row * 128 : nullptr;
-      if (kStash) { if (a.bulk && elected) bulk_wait_read0(); group_bar(t); }   // previous image has left sA
-      {
-        float x[3];
-        row_pos01(pos_mode, nxt, x);
-        encode_row(sA, gtile, row, h, x, net, enc_dim0, enc_f0);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int64_t tile = 2 * pair + t;
+        const bool active = tile < a.tiles;
+        const uint32_t sA = sm.tileA(t);
+        {
+          float x[3];
+          row_pos01(pos_mode, nxt[t], x);
+          encode_row(sA, row, h, x, net, enc_dim0, enc_f0);
+        }
+        fence_async_smem();
+        if (kStash && elected) bulk_wait_read0();
+        mbar_arrive(sm.a_ready(t));
+        if (pair + gridDim.x < pairs)
+          nxt[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, row_index(pair + gridDim.x, t));
+        if (kStash) {
+          epi_bar();
+          if (elected && active) { bulk_s2g(a.acts + tile * act_tile_bytes(net), sA, (uint32_t)kBlk); bulk_commit(); }
+        }
       }
-      fence_async_smem();
-      mbar_arrive(sm.a_ready[t]);
-      if (pair + gridDim.x < pairs) nxt = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, row_index(pair + gridDim.x));
       for (int l = 0; l < net.L; ++l) {
         const bool last = (l == net.L - 1);
-        uint8_t* grow = gtile ? gtile + kBlk + (int64_t)l * kNb * kBlk : nullptr;
-        mbar_wait(sm.acc_full[t], par_acc);
-        par_acc ^= 1u;
-        tc_fence_after();
-        if (kStash && l > 0) { if (a.bulk && elected) bulk_wait_read0(); group_bar(t); }   // previous image has left sA
-        float sig0 = 0.f, sig1 = 0.f;
-        uint32_t mbits[kCols / 32];
 #pragma unroll
-        for (int it = 0; it < kCols / 32; ++it) mbits[it] = 0u;
-        drain_cols<kCols>(acc, [&](int i, const uint32_t (&v)[16]) {
-          const int col0 = h * kCols + i * 16;
-          if (kStash) {
-            uint32_t b0 = 0u, b1 = 0u;      // two independent chains
-#define LONER_BIT(B, I) set_bit_if_pos<I>(B, __uint_as_float(v[I]));
-            LONER_BIT(b0, 0) LONER_BIT(b1, 8) LONER_BIT(b0, 1) LONER_BIT(b1, 9) LONER_BIT(b0, 2) LONER_BIT(b1, 10)
-            LONER_BIT(b0, 3) LONER_BIT(b1, 11) LONER_BIT(b0, 4) LONER_BIT(b1, 12) LONER_BIT(b0, 5) LONER_BIT(b1, 13)
-            LONER_BIT(b0, 6) LONER_BIT(b1, 14) LONER_BIT(b0, 7) LONER_BIT(b1, 15)
-#undef LONER_BIT
-            mbits[i >> 1] |= (b0 | b1) << ((i & 1) * 16);
-          }
-          uint32_t hh[8];
+        for (int t = 0; t < 2; ++t) {
+          const int64_t tile = 2 * pair + t;
+          const bool active = tile < a.tiles;
+          const int64_t gs = tile * kTile + row;
+          const bool in = active && gs < a.P;
+          const uint32_t sA = sm.tileA(t);
+          const uint32_t srow = sA + row * 128;
+          float* part = sm.part() + t * 128;
+          mbar_wait(sm.acc_full(t), par_acc);
+          tc_fence_after();
+          float sig0 = 0.f, sig1 = 0.f;
+          uint32_t mbits[kCols / 32];
+          drain32<kCols>(acc_base + t * 256, [&](int i, const uint32_t (&v)[32]) {
+            const int col0 = h * kCols + i * 32;
+            uint32_t hh[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) hh[e] = cvt_relu_h2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
-          if (!last || kStash) store16(srow, nullptr, xs, col0, hh);
-          if (last) {
+            for (int p = 0; p < 16; ++p) hh[p] = cvt_relu_h2(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]));
+            if (kStash) mbits[i] = relu_mask_word(hh);
+            if (!last || kStash) store32(srow, xs, col0, hh);
+            if (last) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&hh[e]));
-              const float2 w2 = *reinterpret_cast<const float2*>(sm.wout + col0 + 2 * e);
-              sig0 = fmaf(r2.x, w2.x, sig0);
-              sig1 = fmaf(r2.y, w2.y, sig1);
+              for (int p = 0; p < 16; ++p) {
+                const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&hh[p]));
+                const float2 w2 = *reinterpret_cast<const float2*>(sm.wout() + col0 + 2 * p);
+                sig0 = fmaf(r2.x, w2.x, sig0);
+                sig1 = fmaf(r2.y, w2.y, sig1);
+              }
+            }
+          });
+          const float sig = sig0 + sig1;
+          tc_fence_before();
+          if (kStash && active) {
+            uint32_t* mrow = reinterpret_cast<uint32_t*>(a.masks + tile * mask_tile_bytes(net)) +
+                             ((int64_t)l * kTile + row) * (W / 32) + h * (kCols / 32);
+            if (kCols / 32 == 4) {
+              *reinterpret_cast<uint4*>(mrow) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
+            } else {
+#pragma unroll
+              for (int it = 0; it < kCols / 32; ++it) mrow[it] = mbits[it];
             }
           }
-        });
-        const float sig = sig0 + sig1;
-        tc_fence_before();
-        if (kStash && active) {
-          uint32_t* mrow = reinterpret_cast<uint32_t*>(a.masks + tile * mask_tile_bytes(net)) +
-                           ((int64_t)l * kTile + row) * (W / 32) + h * (kCols / 32);
-          if (kCols / 32 == 4) {
-            *reinterpret_cast<uint4*>(mrow) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
-          } else {
-#pragma unroll
-            for (int it = 0; it < kCols / 32; ++it) mrow[it] = mbits[it];
+          if (!last || kStash) fence_async_smem();     // the image becomes visible to the MMA / bulk-copy engines
+          if (kStash && elected) bulk_wait_read0();
+          if (!last) mbar_arrive(sm.a_ready(t));
+          else if (h == 1) part[row] = sig;
+          if (kStash || last) epi_bar();
+          if (last && h == 0 && in) a.sigma[gs] = sig + part[row];
+          if (kStash && elected && active) {
+            bulk_s2g(a.acts + tile * act_tile_bytes(net) + kBlk + (int64_t)l * kNb * kBlk, sA, (uint32_t)(kNb * kBlk));
+            bulk_commit();
           }
         }
-        if (!last) {
-          fence_async_smem();
-          mbar_arrive(sm.a_ready[t]);
-        } else {
-          if (kStash) fence_async_smem();       // A_L in sA becomes visible to the bulk-copy engine
-          if (h == 1) part[row] = sig;
-          group_bar(t);
-          if (h == 0 && in) a.sigma[gs] = sig + part[row];
-        }
-        if (kStash) {
-          if (!last) group_bar(t);            // (the last layer already met at the sigma barrier)
-          uint8_t* gimg = a.acts + tile * act_tile_bytes(net) + kBlk + (int64_t)l * kNb * kBlk;
-          if (active && !a.bulk) copy_image(sA, gimg, kNb * kBlk, (e & 7) * 32 + lane);
-          if (active && a.bulk && elected) { bulk_s2g(gimg, sA, (uint32_t)(kNb * kBlk)); bulk_commit(); }
-        }
+        par_acc ^= 1u;
       }
     }
-    if (kStash && a.bulk && elected) bulk_wait0();
+    if (kStash && elected) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -574,7 +524,9 @@ struct BwdArgs {
   const float* d_sigma;
   const uint8_t* masks;
   uint8_t* dz;           // dZ stash [tiles][L][nb*16 KB]
-  int bulk;
+  int share_w;
+  int x4;
+  int stash_last;        // 1: the dZ_L image is stashed too; 0: wgrad rebuilds it from masks, d_sigma, w_out
   float gscale;
   float* d_pos;          // [P,3] or null
 };
@@ -587,7 +539,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
   const Net net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pipe_init(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W);
-  const uint32_t tmem = *sm.tmem_slot;
+  const uint32_t tmem = *sm.tmem_slot();
   const int64_t pairs = (a.tiles + 1) / 2;
   const bool want_dx = a.d_pos != nullptr;
   const int l_lo = want_dx ? 0 : 1;        // GEMMs run for l = L-1 .. l_lo : dA_l = dZ_{l+1} * W_l
@@ -599,163 +551,210 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
       for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
         for (int l = net.L - 1; l >= l_lo; --l) {
           const uint32_t bytes = (uint32_t)layer_K(net, l) * 128u;     // one column block: K_l rows x 128 B
-          for (int c = 0; c < kNb; ++c, ++g) {
-            const uint32_t slot = g % kRingSlots, use = g / kRingSlots;
-            if (use > 0) mbar_wait(sm.w_empty[slot], (use - 1) & 1);
-            mbar_expect_tx(sm.w_full[slot], bytes);
-            bulk_g2s(smem_u32(sm.ring + slot * kSlotBytes), a.packed + packed_off(net, l) + (int64_t)c * bytes, bytes,
-                     sm.w_full[slot]);
+          const int reps = a.share_w ? 1 : 2;
+          for (int t = 0; t < reps; ++t) {
+            for (int c = 0; c < kNb; ++c, ++g) {
+              const uint32_t slot = g % kRingSlots, use = g / kRingSlots;
+              if (use > 0) mbar_wait(sm.w_empty(slot), (use - 1) & 1);
+              mbar_expect_tx(sm.w_full(slot), bytes);
+              bulk_g2s(sm.ring(slot), a.packed + packed_off(net, l) + (int64_t)c * bytes, bytes, sm.w_full(slot));
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      uint32_t g_base = 0, par_a[2] = {0u, 0u};
+      uint32_t g = 0, par_a = 0u;
       for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
         for (int l = net.L - 1; l >= l_lo; --l) {
           const uint32_t idesc = make_idesc_f16(128, layer_K(net, l), 0, 0);
-          for (int c0 = 0; c0 < kNb; c0 += 2) {
-            const int c1 = min(c0 + 2, kNb);
+          const int cstep = a.share_w ? 2 : kNb;
+          for (int c0 = 0; c0 < kNb; c0 += cstep) {
+            const int c1 = min(c0 + cstep, kNb);
             for (int t = 0; t < 2; ++t) {
-              if (c0 == 0) { mbar_wait(sm.a_ready[t], par_a[t]); par_a[t] ^= 1u; tc_fence_after(); }
+              if (c0 == 0) { mbar_wait(sm.a_ready(t), par_a); tc_fence_after(); }
               for (int c = c0; c < c1; ++c) {
-                const uint32_t g = g_base + c, slot = g % kRingSlots;
-                if (t == 0) { mbar_wait(sm.w_full[slot], (g / kRingSlots) & 1); tc_fence_after(); }
-                const uint32_t sa = smem_u32(sm.tileA[t]) + c * kBlk, sb = smem_u32(sm.ring + slot * kSlotBytes);
+                const uint32_t gc = a.share_w ? g + c : g + t * kNb + c, slot = gc % kRingSlots;
+                if (t == 0 || !a.share_w) { mbar_wait(sm.w_full(slot), (gc / kRingSlots) & 1); tc_fence_after(); }
+                const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
+                const uint32_t release = (t == 1 || !a.share_w) ? sm.w_empty(slot) : 0u;
+                if (a.x4) {
+                  umma_f16_x4<2, 2>(tmem + t * 256, desc_lo_sw128(sa, 16), desc_hi_sw128(1024), desc_lo_sw128(sb, 16),
+                                    desc_hi_sw128(1024), idesc, c > 0 ? 1u : 0u, release);
+                } else {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t ad = make_desc_sw128(sa + ks * 32, 16, 1024);
-                  const uint64_t bd = make_desc_sw128(sb + ks * 32, 16, 1024);
-                  umma_f16(tmem + t * 256, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                  for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t ad = make_desc_sw128(sa + ks * 32, 16, 1024);
+                    const uint64_t bd = make_desc_sw128(sb + ks * 32, 16, 1024);
+                    umma_f16(tmem + t * 256, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                  }
+                  if (release) umma_commit(release);
                 }
-                if (t == 1) umma_commit(sm.w_empty[slot]);
               }
-              if (c1 == kNb) umma_commit(sm.acc_full[t]);
+              if (c1 == kNb) umma_commit(sm.acc_full(t));
             }
           }
-          g_base += kNb;
+          g += a.share_w ? kNb : 2 * kNb;
+          par_a ^= 1u;
         }
       }
     }
   } else {
+    // ---------------- epilogue warps: thread = (sample row, column half); tile X, then tile Y
+    // (same step / barrier / bulk-copy protocol as the forward kernel).
     const int e = warp - 2;
-    const int t = e >> 3;
-    const int h = (e & 7) >> 2;
+    const int h = e >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const uint32_t stile = smem_u32(sm.tileA[t]);
-    const uint32_t srow = stile + row * 128;
-    const bool elected = ((e & 7) == 0) && lane == 0;
+    const bool elected = (e == 0) && lane == 0;
     const uint32_t xs = (uint32_t)(row & 7) << 4;
     constexpr int kCols = W / 2;
-    const uint32_t acc_row = tmem + t * 256 + ((uint32_t)(q * 32) << 16);
-    const uint32_t acc = acc_row + h * kCols;
-    uint32_t par_acc = 0;
     constexpr int kWords = W / 32;
+    constexpr int kMw = kCols / 32;
+    const uint32_t acc_row = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t par_acc = 0;
     const bool pos_mode = a.pos != nullptr;
-    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
-      const int64_t tile = 2 * pair + t;
-      const bool active = tile < a.tiles;
-      const int64_t gs = tile * kTile + row;
-      const bool in = active && gs < a.P;
-      const uint32_t* mtile = reinterpret_cast<const uint32_t*>(a.masks + (active ? tile : 0) * mask_tile_bytes(net));
-      uint8_t* gtile = active ? a.dz + tile * dz_tile_bytes(net) + row * 128 : nullptr;
-      if (a.bulk && elected) bulk_wait_read0();
-      group_bar(t);                           // the previous tile's last image copy has left the buffer
-      RowIn rin;
-      if (want_dx && h == 0) rin = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, in ? gs : a.P - 1);
-      {  // dZ_L = d_sigma * w_out * relu'(Z_L)
-        const float ds = in ? a.d_sigma[gs] * a.gscale : 0.f;
-        const uint32_t* mrow = mtile + ((int64_t)(net.L - 1) * kTile + row) * kWords + h * (kCols / 32);
+    // mask words of (tile, layer index m) for this thread's row and column half
+    auto load_masks = [&](int64_t tile, int m, uint32_t (&mw)[kMw]) {
+      const float* mrow = reinterpret_cast<const float*>(a.masks + (tile < a.tiles ? tile : 0) * mask_tile_bytes(net)) +
+                          ((int64_t)m * kTile + row) * kWords + h * kMw;
 #pragma unroll
-        for (int it = 0; it < kCols / 32; ++it) {
-          const uint32_t bits = mrow[it];
+      for (int it = 0; it < kMw; ++it) mw[it] = __float_as_uint(ldg_now(mrow + it));
+    };
+    auto load_ds = [&](int64_t tile) {
+      const int64_t gs = tile * kTile + row;
+      return (tile < a.tiles && gs < a.P) ? ldg_now(a.d_sigma + gs) * a.gscale : 0.f;
+    };
+    uint32_t mw[2][kMw];      // masks of the NEXT step of each tile, fetched one step ahead
+    float ds[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) { load_masks(2 * (int64_t)blockIdx.x + t, net.L - 1, mw[t]); ds[t] = load_ds(2 * (int64_t)blockIdx.x + t); }
+    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+      RowIn rin[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int64_t tile = 2 * pair + t;
+        const bool active = tile < a.tiles;
+        const int64_t gs = tile * kTile + row;
+        const bool in = active && gs < a.P;
+        const uint32_t stile = sm.tileA(t);
+        const uint32_t srow = stile + row * 128;
+        if (want_dx && h == 0) rin[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, in ? gs : a.P - 1);
+        // dZ_L = d_sigma * w_out * relu'(Z_L)
+#pragma unroll
+        for (int it = 0; it < kMw; ++it) {
+          const uint32_t bits = mw[t][it];
           const int col0 = h * kCols + it * 32;
-          store_slab(srow, nullptr, xs, col0, [&](int i0) {
-            const float2 w2 = *reinterpret_cast<const float2*>(sm.wout + col0 + i0);
-            const float g0 = ((bits >> i0) & 1u) ? ds * w2.x : 0.f;
-            const float g1 = ((bits >> (i0 + 1)) & 1u) ? ds * w2.y : 0.f;
-            return cvt_sat_h2(g0, g1);
-          });
+          uint32_t hh[16];
+#pragma unroll
+          for (int p = 0; p < 16; ++p) {
+            const float2 w2 = *reinterpret_cast<const float2*>(sm.wout() + col0 + 2 * p);
+            const float g0 = ((bits >> p) & 1u) ? ds[t] * w2.x : 0.f;
+            const float g1 = ((bits >> (16 + p)) & 1u) ? ds[t] * w2.y : 0.f;
+            hh[p] = cvt_sat_h2(g0, g1);
+          }
+          store32(srow, xs, col0, hh);
+        }
+        if (net.L >= 2) {
+          load_masks(tile, net.L - 2, mw[t]);      // for step (t, L-1)
+        } else if (!want_dx) {                     // single hidden layer, no GEMM steps: next pair's first step
+          load_masks(tile + 2 * (int64_t)gridDim.x, net.L - 1, mw[t]);
+          ds[t] = load_ds(tile + 2 * (int64_t)gridDim.x);
+        }
+        fence_async_smem();
+        if (elected) bulk_wait_read0();
+        mbar_arrive(sm.a_ready(t));
+        epi_bar();
+        if (a.stash_last && elected && active) {
+          bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(net.L - 1) * kNb * kBlk, stile, (uint32_t)(kNb * kBlk));
+          bulk_commit();
         }
       }
-      fence_async_smem();
-      mbar_arrive(sm.a_ready[t]);
-      // (the dZ_L image is NOT stashed: wgrad rebuilds it from the masks, d_sigma and w_out)
       for (int l = net.L - 1; l >= l_lo; --l) {
-        mbar_wait(sm.acc_full[t], par_acc);
-        par_acc ^= 1u;
-        tc_fence_after();
-        if (a.bulk && elected) bulk_wait_read0();
-        group_bar(t);                         // everyone's copy of the previous image has left the tile buffer
-        if (l >= 1) {
-          // dZ_l = dA_l * relu'(Z_l)  -> fp16 image (next GEMM's A operand in smem, wgrad's B operand in HBM)
-          const uint32_t* mrow = mtile + ((int64_t)(l - 1) * kTile + row) * kWords + h * (kCols / 32);
-          uint8_t* grow = gtile ? gtile + (int64_t)(l - 1) * kNb * kBlk : nullptr;
-          const bool feeds_gemm = (l - 1 >= l_lo);
-          uint32_t mw[kCols / 32];
 #pragma unroll
-          for (int it = 0; it < kCols / 32; ++it) mw[it] = mrow[it];
-          drain_cols<kCols>(acc, [&](int i, const uint32_t (&v)[16]) {
-            const uint32_t bits = mw[i >> 1] >> ((i & 1) * 16);
-            uint32_t hh[8];
+        for (int t = 0; t < 2; ++t) {
+          const int64_t tile = 2 * pair + t;
+          const bool active = tile < a.tiles;
+          const int64_t gs = tile * kTile + row;
+          const bool in = active && gs < a.P;
+          const uint32_t stile = sm.tileA(t);
+          const uint32_t srow = stile + row * 128;
+          mbar_wait(sm.acc_full(t), par_acc);
+          tc_fence_after();
+          if (l >= 1) {
+            // dZ_l = dA_l * relu'(Z_l)  -> fp16 image (next GEMM's A operand in smem, wgrad's B operand in HBM)
+            const bool feeds_gemm = (l - 1 >= l_lo);
+            drain32<kCols>(acc_row + t * 256 + h * kCols, [&](int i, const uint32_t (&v)[32]) {
+              const uint32_t bits = mw[t][i];
+              uint32_t hh[16];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float g0 = ((bits >> (2 * e)) & 1u) ? __uint_as_float(v[2 * e]) : 0.f;
-              const float g1 = ((bits >> (2 * e + 1)) & 1u) ? __uint_as_float(v[2 * e + 1]) : 0.f;
-              hh[e] = cvt_sat_h2(g0, g1);
-            }
-            store16(srow, nullptr, xs, h * kCols + i * 16, hh);
-          });
-          tc_fence_before();
-          fence_async_smem();
-          if (feeds_gemm) mbar_arrive(sm.a_ready[t]);
-          group_bar(t);
-          {
-            uint8_t* gimg = a.dz + tile * dz_tile_bytes(net) + (int64_t)(l - 1) * kNb * kBlk;
-            if (active && !a.bulk) copy_image(stile, gimg, kNb * kBlk, (e & 7) * 32 + lane);
-            if (active && a.bulk && elected) { bulk_s2g(gimg, stile, (uint32_t)(kNb * kBlk)); bulk_commit(); }
-          }
-        } else if (h == 0) {
-          // l == 0: dEnc [128 x Epad] -> d_pos through the sin/cos encoding (lower-half warps only)
-          float x[3];
-          row_pos01(pos_mode, rin, x);
-          float dx[3] = {0.f, 0.f, 0.f};
-          int dim = 0, f = 0;
-          float scale = 1.0f;
-          for (int it = 0; it * 32 < net.Epad; ++it) {
-            uint32_t v[32];
-            tmem_ld32(acc_row + it * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int pq = 0; pq < 16; ++pq) {
-              if (dim < 3) {
-                const float xv = dim == 0 ? x[0] : (dim == 1 ? x[1] : x[2]);
-                float sn, cs;
-                freq_pair(xv, scale, sn, cs);
-                // d/dx sin(pi 2^f x) = pi 2^f cos, d/dx cos = -pi 2^f sin
-                const float g = (__uint_as_float(v[2 * pq]) * cs - __uint_as_float(v[2 * pq + 1]) * sn) *
-                                (3.14159265358979323846f * scale);
-                if (dim == 0) dx[0] += g; else if (dim == 1) dx[1] += g; else dx[2] += g;
+              for (int p = 0; p < 16; ++p) {
+                const float g0 = ((bits >> p) & 1u) ? __uint_as_float(v[2 * p]) : 0.f;
+                const float g1 = ((bits >> (16 + p)) & 1u) ? __uint_as_float(v[2 * p + 1]) : 0.f;
+                hh[p] = cvt_sat_h2(g0, g1);
               }
-              ++f; scale *= 2.0f;
-              if (f == net.F) { f = 0; scale = 1.0f; ++dim; }
+              store32(srow, xs, h * kCols + i * 32, hh);
+            });
+            tc_fence_before();
+            // masks (and d_sigma) of this tile's next step: layer l-2 of this pair, or the first step of the next pair
+            if (l >= 2) {
+              load_masks(tile, l - 2, mw[t]);
+            } else if (!want_dx) {
+              load_masks(tile + 2 * (int64_t)gridDim.x, net.L - 1, mw[t]);
+              ds[t] = load_ds(tile + 2 * (int64_t)gridDim.x);
             }
+            fence_async_smem();
+            if (elected) bulk_wait_read0();
+            if (feeds_gemm) mbar_arrive(sm.a_ready(t));
+            epi_bar();
+            if (elected && active) {
+              bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(l - 1) * kNb * kBlk, stile, (uint32_t)(kNb * kBlk));
+              bulk_commit();
+            }
+          } else {
+            // l == 0: dEnc [128 x Epad] -> d_pos through the sin/cos encoding (lower-half warps only)
+            if (h == 0) {
+              float x[3];
+              row_pos01(pos_mode, rin[t], x);
+              float dx[3] = {0.f, 0.f, 0.f};
+              int dim = 0, f = 0;
+              float scale = 1.0f;
+              for (int it = 0; it * 32 < net.Epad; ++it) {
+                uint32_t v[32];
+                tmem_ld32(acc_row + t * 256 + it * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int pq = 0; pq < 16; ++pq) {
+                  if (dim < 3) {
+                    const float xv = dim == 0 ? x[0] : (dim == 1 ? x[1] : x[2]);
+                    float sn, cs;
+                    freq_pair(xv, scale, sn, cs);
+                    // d/dx sin(pi 2^f x) = pi 2^f cos, d/dx cos = -pi 2^f sin
+                    const float g = (__uint_as_float(v[2 * pq]) * cs - __uint_as_float(v[2 * pq + 1]) * sn) *
+                                    (3.14159265358979323846f * scale);
+                    if (dim == 0) dx[0] += g; else if (dim == 1) dx[1] += g; else dx[2] += g;
+                  }
+                  ++f; scale *= 2.0f;
+                  if (f == net.F) { f = 0; scale = 1.0f; ++dim; }
+                }
+              }
+              if (in) {
+                const float inv = 0.5f / a.gscale;      // x = (pos + 1) / 2
+                a.d_pos[gs * 3 + 0] = dx[0] * inv;
+                a.d_pos[gs * 3 + 1] = dx[1] * inv;
+                a.d_pos[gs * 3 + 2] = dx[2] * inv;
+              }
+            }
+            tc_fence_before();
+            load_masks(tile + 2 * (int64_t)gridDim.x, net.L - 1, mw[t]);
+            ds[t] = load_ds(tile + 2 * (int64_t)gridDim.x);
           }
-          tc_fence_before();
-          if (in) {
-            const float inv = 0.5f / a.gscale;      // x = (pos + 1) / 2
-            a.d_pos[gs * 3 + 0] = dx[0] * inv;
-            a.d_pos[gs * 3 + 1] = dx[1] * inv;
-            a.d_pos[gs * 3 + 2] = dx[2] * inv;
-          }
-        } else {
-          tc_fence_before();
         }
+        par_acc ^= 1u;
       }
     }
-    if (a.bulk && elected) bulk_wait0();
+    if (elected) bulk_wait0();
   }
   tc_fence_before();
   __syncthreads();
@@ -778,6 +777,7 @@ struct WgradArgs {
   const float* wout;         // [W] fp32 values of the fp16-rounded output weights (packed image)
   float gscale;
   int64_t P;
+  int gen_last;              // 1: CTAs of layer L-1 rebuild dZ_L; 0: they read dgrad's stash of it
   int item_begin[9];         // first item of each layer (prefix), item_begin[L] = total
   int64_t part_off[9];       // float offset of each layer's first partial
 };
@@ -811,10 +811,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
   auto empty_bar = [&](int s) { return smem_u32(&bars[kWgStages + s]); };
   const uint32_t done_bar = smem_u32(&bars[2 * kWgStages]);
 
-  const bool gen_y = (l == net.L - 1);           // this CTA rebuilds dZ_L instead of loading it
+  const bool gen_y = a.gen_last && (l == net.L - 1);   // this CTA rebuilds dZ_L instead of loading it
   if (warp == 0) tmem_alloc<512>(smem_u32(s_tmem));
   if (tid == 32) {
-    for (int s = 0; s < kWgStages; ++s) { mbar_init(full_bar(s), gen_y ? 1 + kWgGen : 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(full_bar(s), gen_y ? 2 : 1); mbar_init(empty_bar(s), 1); }
     mbar_init(done_bar, 1);
     fence_mbar_init();
   }
@@ -882,16 +882,31 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
     const int r = g >> 2, qc = g & 3;
     const int cpt = net.W / 4;                    // columns per thread: 64 (W=256) or 32 (W=128)
     const int mwords = net.W / 32;
+    // inputs of a stage (d_sigma of the row, its mask words) are fetched two stages ahead: their
+    // latency under a saturated HBM is longer than a stage
+    auto fetch = [&](int64_t i, float& ds, uint32_t& m0, uint32_t& m1) {
+      ds = 0.f; m0 = 0u; m1 = 0u;
+      if (i >= n_half) return;
+      const int64_t tile = t0 + (i >> 1);
+      const int row = (int)(i & 1) * 64 + r;
+      const int64_t gs = tile * kTile + row;
+      if (gs < a.P) ds = ldg_now(a.d_sigma + gs) * a.gscale;
+      const float* mrow = reinterpret_cast<const float*>(a.masks + tile * mask_tile_bytes(net)) +
+                          ((int64_t)(net.L - 1) * kTile + row) * mwords + qc * (cpt / 32);
+      m0 = __float_as_uint(ldg_now(mrow));
+      if (cpt > 32) m1 = __float_as_uint(ldg_now(mrow + 1));
+    };
+    float ds_a, ds_b;
+    uint32_t ma0, ma1, mb0, mb1;
+    fetch(0, ds_a, ma0, ma1);
+    fetch(1, ds_b, mb0, mb1);
     for (int64_t i = 0; i < n_half; ++i) {
       const int s = (int)(i % kWgStages);
       const uint32_t ph = (uint32_t)((i / kWgStages) & 1);
-      const int64_t tile = t0 + (i >> 1);
-      const int row = (int)(i & 1) * 64 + r;      // row inside the 128-sample tile
-      const int64_t gs = tile * kTile + row;
-      const float ds = gs < a.P ? __ldg(a.d_sigma + gs) * a.gscale : 0.f;
-      const uint32_t* mrow = reinterpret_cast<const uint32_t*>(a.masks + tile * mask_tile_bytes(net)) +
-                             ((int64_t)(net.L - 1) * kTile + row) * mwords + qc * (cpt / 32);
-      const uint32_t mw0 = __ldg(mrow), mw1 = (cpt > 32) ? __ldg(mrow + 1) : 0u;
+      const float ds = ds_a;
+      const uint32_t mw0 = ma0, mw1 = ma1;
+      ds_a = ds_b; ma0 = mb0; ma1 = mb1;
+      fetch(i + 2, ds_b, mb0, mb1);
       mbar_wait(empty_bar(s), ph ^ 1u);
       const uint32_t sY = smem_u32(base + s * kWgStageBytes) + 32768 + (uint32_t)r * 128;
       const uint32_t xs = (uint32_t)(r & 7) << 4;
@@ -906,9 +921,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int i0 = ch * 8 + 2 * e;
+              const int pr = ch * 4 + e;                   // pair index inside the 32-column mask word
               const float2 w2 = *reinterpret_cast<const float2*>(s_wout + col0 + i0);
-              const float g0 = ((bits >> i0) & 1u) ? ds * w2.x : 0.f;
-              const float g1 = ((bits >> (i0 + 1)) & 1u) ? ds * w2.y : 0.f;
+              const float g0 = ((bits >> pr) & 1u) ? ds * w2.x : 0.f;
+              const float g1 = ((bits >> (16 + pr)) & 1u) ? ds * w2.y : 0.f;
               w[e] = cvt_sat_h2(g0, g1);
             }
             const int c0 = col0 + ch * 8;
@@ -917,7 +933,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
         }
       }
       fence_async_smem();
-      mbar_arrive(full_bar(s));
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // all generator threads have written and fenced
+      if (g == 0) mbar_arrive(full_bar(s));
     }
   }
   if (warp >= 2 && warp < 6) {
@@ -1082,6 +1099,26 @@ extern "C" int64_t loner_mlp_packed_bytes(const loner_net_t* n) {
   return packed_total(net);
 }
 static inline int64_t n_tiles(int64_t P) { return (P + kTile - 1) / kTile; }
+// dZ_L = relu'(Z_L) * d_sigma * w_out can be rebuilt inside wgrad instead of travelling through HBM
+// (LONER_WGRAD_GEN=1); measured slower than reading dgrad's stash, so it is off by default.
+// MMA order of the pipelined kernels.  Default: every tile fetches its own weight chunks (X[all] Y[all]);
+// LONER_MMA_ORDER=pair shares each chunk between the two tiles of a pair (X[c0,c1] Y[c0,c1] X[c2,c3]
+// Y[c2,c3]): half the L2->SM weight traffic, but a tile's epilogue then overlaps only a quarter of the
+// other tile's tensor work.  A/B on the GPU (tests/gpu_ab.py, C2): training forward 2.61 vs 2.75 ms,
+// dgrad 1.90 vs 2.24 ms, inference 1.59 vs 1.57 ms.
+static inline int share_weights() {
+  static const int v = [] { const char* m = getenv("LONER_MMA_ORDER"); return (m && m[0] == 'p') ? 1 : 0; }();
+  return v;
+}
+// LONER_MMA_X4=0 issues the MMAs one asm statement each (A/B: inference 1.77 vs 1.57 ms).
+static inline int mma_x4() {
+  static const int v = [] { const char* m = getenv("LONER_MMA_X4"); return (m && m[0] == '0') ? 0 : 1; }();
+  return v;
+}
+static inline bool wgrad_rebuilds_last() {
+  static const int on = [] { const char* m = getenv("LONER_WGRAD_GEN"); return (m && m[0] == '1') ? 1 : 0; }();
+  return on != 0;
+}
 extern "C" int64_t loner_mlp_act_bytes(const loner_net_t* n, int64_t P) {
   Net net;
   if (!net_from(n, net) || P < 0) return -1;
@@ -1114,8 +1151,9 @@ extern "C" int loner_mlp_fwd(const loner_net_t* n, const void* packed, const flo
   a.net = net; a.packed = (const uint8_t*)packed; a.pos = pos; a.rays = rays; a.z = z_vals; a.S = S; a.P = P;
   a.s_shift = (S > 0 && (S & (S - 1)) == 0) ? __builtin_ctz((unsigned)S) : -1;
   a.tiles = n_tiles(P); a.sigma = sigma; a.acts = (uint8_t*)acts;
-  { const char* m = getenv("LONER_STASH"); a.bulk = (m && m[0] == 'c') ? 0 : 1; }
   a.masks = acts ? (uint8_t*)acts + a.tiles * act_tile_bytes(net) : nullptr;
+  a.share_w = share_weights();
+  a.x4 = mma_x4();
   const int sms = device_sm_count();
   const int64_t pairs = (a.tiles + 1) / 2;
   const unsigned grid = (unsigned)(pairs < sms ? pairs : sms);
@@ -1150,7 +1188,9 @@ extern "C" int loner_mlp_dgrad(const loner_net_t* n, const void* packed, const f
   b.s_shift = (S > 0 && (S & (S - 1)) == 0) ? __builtin_ctz((unsigned)S) : -1;
   b.tiles = tiles; b.d_sigma = d_sigma; b.masks = (const uint8_t*)acts + tiles * act_tile_bytes(net);
   b.dz = (uint8_t*)scratch; b.gscale = grad_scale; b.d_pos = d_pos;
-  { const char* m = getenv("LONER_STASH"); b.bulk = (m && m[0] == 'c') ? 0 : 1; }
+  b.stash_last = wgrad_rebuilds_last() ? 0 : 1;
+  b.share_w = share_weights();
+  b.x4 = mma_x4();
   const int64_t pairs = (tiles + 1) / 2;
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem);
@@ -1176,7 +1216,7 @@ extern "C" int loner_mlp_wgrad(const loner_net_t* n, const void* packed, int64_t
   const WgradPlan plan = plan_wgrad(net);
   WgradArgs w;
   w.net = net; w.acts = (const uint8_t*)acts; w.dz = dz; w.tiles = tiles; w.partials = partials;
-  w.masks = (const uint8_t*)acts + tiles * act_tile_bytes(net); w.d_sigma = d_sigma;
+  w.masks = (const uint8_t*)acts + tiles * act_tile_bytes(net); w.d_sigma = d_sigma; w.gen_last = wgrad_rebuilds_last() ? 1 : 0;
   w.wout = reinterpret_cast<const float*>((const uint8_t*)packed + packed_wout_off(net)); w.gscale = grad_scale; w.P = P;
   for (int i = 0; i <= net.L; ++i) { w.item_begin[i] = plan.item_begin[i]; w.part_off[i] = plan.part_off[i]; }
   cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);

@@ -50,6 +50,7 @@ dp = torch.zeros(net.param_count, device=dev)
 res["mlp_wgrad_all"] = timeit(lambda: ops.mlp_wgrad(net, packed, P, rl["d_sigma"], acts, gs, dp, scratch))
 f_fwd = 2 * (64 * W + (L - 1) * W * W + W)
 print(json.dumps({k: round(v, 4) for k, v in res.items()}))
+if os.environ.get("MB_SHORT"): sys.exit(0)
 print("fwd TF/s stash %.0f infer %.0f | stash GB %.2f dz GB %.2f" % (
     f_fwd * P / res["mlp_fwd_stash"] / 1e9, f_fwd * P / res["mlp_fwd_infer"] / 1e9,
     net.act_bytes(P) / 1e9, (net.bwd_scratch_bytes(P)) / 1e9))
