@@ -110,7 +110,7 @@ constexpr int kPipeThreads = 320;
 constexpr int kGroupThreads = 256;
 constexpr int kRingSlots = 3;
 constexpr int kSlotBytes = 32768;
-constexpr int kPipeSmem = 2 * 65536 + kRingSlots * kSlotBytes + 2304;
+constexpr int kPipeSmem = 2 * 65536 + kRingSlots * kSlotBytes + 2432;
 
 // Shared-memory map of the two pipelined kernels.  Everything is an ADDRESS COMPUTATION (no arrays of
 // pointers): a table indexed by a run-time slot number would live in local memory, and local loads
@@ -128,6 +128,10 @@ struct PipeSmem {
   __device__ __forceinline__ uint32_t w_empty(uint32_t i) const { return bars() + 8u * (kRingSlots + i); }
   __device__ __forceinline__ uint32_t a_ready(int t) const { return bars() + 8u * (2 * kRingSlots + t); }
   __device__ __forceinline__ uint32_t acc_full(int t) const { return bars() + 8u * (2 * kRingSlots + 2 + t); }
+  // encoding table: feature pair p -> {kind, 2^f}; kind 0..2 = input dimension, 3 = padding ones, 4 = zeros
+  __device__ __forceinline__ uint2* enc_tab() const {
+    return reinterpret_cast<uint2*>(base + 131072 + kRingSlots * kSlotBytes + 2176);
+  }
   __device__ __forceinline__ uint32_t* tmem_slot() const {
     return reinterpret_cast<uint32_t*>(base + 131072 + kRingSlots * kSlotBytes + 2048 + 8 * (2 * kRingSlots + 4));
   }
@@ -140,7 +144,8 @@ __device__ __forceinline__ PipeSmem carve(uint8_t* base) {
   return p;
 }
 
-__device__ __forceinline__ void pipe_init(const PipeSmem& sm, int tid, int warp, const float* wout_src, int W) {
+__device__ __forceinline__ void pipe_init(const PipeSmem& sm, int tid, int warp, const float* wout_src, int W,
+                                          const Net& net) {
   if (warp == 1) tmem_alloc<512>(smem_u32(sm.tmem_slot()));
   if (tid == 0) {
     for (int i = 0; i < kRingSlots; ++i) { mbar_init(sm.w_full(i), 1); mbar_init(sm.w_empty(i), 1); }
@@ -148,6 +153,13 @@ __device__ __forceinline__ void pipe_init(const PipeSmem& sm, int tid, int warp,
     fence_mbar_init();
   }
   for (int j = tid; j < W; j += kPipeThreads) sm.wout()[j] = wout_src[j];
+  if (tid >= 64 && tid < 96) {          // features [0, 6F): sin/cos pairs ordered [dim][freq]; [6F, Epad): ones; rest zeros
+    const int p = tid - 64, dim = p / net.F, f = p % net.F;
+    uint2 e;
+    if (dim < 3) e = make_uint2((uint32_t)dim, __float_as_uint((float)(1 << f)));
+    else e = make_uint2(2 * p < net.Epad ? 3u : 4u, 0u);
+    sm.enc_tab()[p] = e;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -172,7 +184,7 @@ __device__ __forceinline__ uint32_t cvt_sat_h2(float a, float b) {   // saturate
 // ReLU mask word of 32 columns given as 16 packed half2 (post-ReLU, so "active" = non-zero fp16 output,
 // which is what tcnn's backward tests too).  Bit p = column 2p, bit 16+p = column 2p+1: one HSET2 and
 // one LOP3 per PAIR of columns.  mask_bit(bits, c) is the inverse mapping.
-__device__ __forceinline__ uint32_t relu_mask_word(const uint32_t (&hh)[16]) {
+__device__ __forceinline__ uint32_t relu_mask_word(const uint32_t* hh) {
   uint32_t m = 0u;
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
@@ -185,6 +197,14 @@ __device__ __forceinline__ uint32_t relu_mask_word(const uint32_t (&hh)[16]) {
 __device__ __forceinline__ bool mask_bit(uint32_t bits, int c) {   // c = column within the 32-column word
   return ((bits >> ((c >> 1) + 16 * (c & 1))) & 1u) != 0u;
 }
+// 0xFFFF in each half of the result whose column (pair kPair of the mask word) is active: the two bits
+// are moved to the sign positions of bytes 1 and 3 and replicated by PRMT (selector nibbles 8|byte).
+template <int kPair>
+__device__ __forceinline__ uint32_t half2_mask(uint32_t bits) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %1, 0xBB99;" : "=r"(m) : "r"(bits << (15 - kPair)));
+  return m;
+}
 
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -192,7 +212,7 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
 
 // 32 columns (16 packed half2) of this thread's row into the swizzled tile image in shared memory.
 // srow = the row's base inside the tile, xs = (row & 7) << 4, col0 = first column (multiple of 32).
-__device__ __forceinline__ void store32(uint32_t srow, uint32_t xs, int col0, const uint32_t (&hh)[16]) {
+__device__ __forceinline__ void store32(uint32_t srow, uint32_t xs, int col0, const uint32_t* hh) {
   const uint32_t cb_off = (uint32_t)(col0 >> 6) * kBlk;
   const uint32_t j0 = ((uint32_t)(col0 & 63) >> 3) << 4;
 #pragma unroll
@@ -280,7 +300,6 @@ struct FwdArgs {
   uint8_t* acts;         // activation stash or null
   uint8_t* masks;        // relu bit masks or null
   int share_w;           // weight chunks serve both tiles of a pair (1) or are fetched per tile (0)
-  int x4;                // MMAs issued four per asm statement
 };
 
 // sin/cos(pi * 2^f * x).  2^f * x is exact in fp32, and so is its reduction r to [-1, 1]; sin(pi r) and
@@ -294,32 +313,25 @@ __device__ __forceinline__ void freq_pair(float x, float scale, float& s, float&
   c = __cosf(a);
 }
 
-// Writes encoded features [32*half, 32*half+32) of row r (column block 0 of `sA`): features
-// [0, 6F) are sin/cos pairs ordered [dim][freq][sin,cos], [6F, Epad) = 1.0 (tcnn pads the encoded
-// width to 16 with ones), rest 0.  (dim0, f0) = position of feature pair 16*half, precomputed.
-__device__ __forceinline__ void encode_row(uint32_t sA, int r, int half, const float (&x)[3], const Net& net,
-                                           int dim0, int f0) {
-  int dim = dim0, f = f0;
-  float scale = (float)(1 << f0);
+// Writes encoded features [32*half, 32*half+32) of row r (column block 0 of `sA`) from the table built
+// by pipe_init (tcnn pads the encoded width to 16 with ones).  A table in shared memory, not per-thread
+// state: the compiler turned the running (dim, f, 2^f) of an unrolled loop into local-memory constants.
+__device__ __forceinline__ void encode_row(uint32_t sA, int r, int half, const float (&x)[3], const uint2* tab) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int cj = half * 4 + c;
     __half2 h[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int pair = cj * 4 + q;            // features 2*pair, 2*pair+1
+      const uint2 e = tab[cj * 4 + q];            // features 2*pair, 2*pair+1
       float s, co;
-      if (dim < 3) {
-        const float xv = dim == 0 ? x[0] : (dim == 1 ? x[1] : x[2]);
-        freq_pair(xv, scale, s, co);
-      } else if (2 * pair < net.Epad) {
-        s = 1.0f; co = 1.0f;
+      if (e.x < 3u) {
+        const float xv = e.x == 0u ? x[0] : (e.x == 1u ? x[1] : x[2]);
+        freq_pair(xv, __uint_as_float(e.y), s, co);
       } else {
-        s = 0.0f; co = 0.0f;
+        s = co = (e.x == 3u) ? 1.0f : 0.0f;
       }
       h[q] = __floats2half2_rn(s, co);
-      ++f; scale *= 2.0f;
-      if (f == net.F) { f = 0; scale = 1.0f; ++dim; }
     }
     const uint32_t* hw = reinterpret_cast<const uint32_t*>(h);
     sts128(sA + r * 128 + ((cj ^ (r & 7)) * 16), hw[0], hw[1], hw[2], hw[3]);
@@ -333,70 +345,66 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
   const PipeSmem sm = carve(smem_raw);
   const Net net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pipe_init(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W);
+  pipe_init(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W, net);
   const uint32_t tmem = *sm.tmem_slot();
   const int64_t pairs = (a.tiles + 1) / 2;
   constexpr int kNb = W / 64;
   constexpr uint32_t kChunkBytes = kNb * 8192;      // 64 K-rows x W out-features, fp16
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------- producer: one contiguous bulk copy per 64-row weight chunk
-      const uint8_t* fimg = a.packed + packed_fwd_base(net);
-      uint32_t g = 0;
-      for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
-        for (int l = 0; l < net.L; ++l) {
-          const int nch = (l == 0) ? 1 : kNb;
-          const int reps = a.share_w ? 1 : 2;      // chunks fetched once per tile PAIR, or once per tile
-          for (int t = 0; t < reps; ++t) {
-            for (int c = 0; c < nch; ++c, ++g) {
-              const uint32_t slot = g % kRingSlots, use = g / kRingSlots;
-              if (use > 0) mbar_wait(sm.w_empty(slot), (use - 1) & 1);
-              mbar_expect_tx(sm.w_full(slot), kChunkBytes);
-              bulk_g2s(sm.ring(slot), fimg + fwd_off(net, l) + (int64_t)c * kChunkBytes, kChunkBytes, sm.w_full(slot));
-            }
+    // ---------------- producer (whole warp, converged): one contiguous bulk copy per 64-row weight chunk
+    const uint8_t* fimg = a.packed + packed_fwd_base(net);
+    uint32_t g = 0;
+    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+      for (int l = 0; l < net.L; ++l) {
+        const int nch = (l == 0) ? 1 : kNb;
+        const int reps = a.share_w ? 1 : 2;      // chunks fetched once per tile PAIR, or once per tile
+        for (int t = 0; t < reps; ++t) {
+          for (int c = 0; c < nch; ++c, ++g) {
+            const uint32_t slot = g % kRingSlots, use = g / kRingSlots;
+            if (use > 0) mbar_wait_warp(sm.w_empty(slot), (use - 1) & 1);
+            mbar_expect_tx_warp(sm.w_full(slot), kChunkBytes);
+            bulk_g2s_warp(sm.ring(slot), fimg + fwd_off(net, l) + (int64_t)c * kChunkBytes, kChunkBytes, sm.w_full(slot));
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer
-      constexpr uint32_t idesc = make_idesc_f16(128, W, 0, 1);
-      uint32_t g = 0, par_a = 0u;
-      for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
-        for (int l = 0; l < net.L; ++l) {
-          const int nch = (l == 0) ? 1 : kNb;
-          const int ksteps0 = (l == 0) ? net.Epad / 16 : 4;   // layer 0 contracts over Epad (<= 64) features
-          // share_w: X[c0,c1] Y[c0,c1] X[c2,c3] Y[c2,c3], a chunk serves both tiles; else X[all] Y[all]
-          const int cstep = a.share_w ? 2 : nch;
-          for (int c0 = 0; c0 < nch; c0 += cstep) {
-            const int c1 = min(c0 + cstep, nch);
-            for (int t = 0; t < 2; ++t) {
-              if (c0 == 0) { mbar_wait(sm.a_ready(t), par_a); tc_fence_after(); }
-              for (int c = c0; c < c1; ++c) {
-                const uint32_t gc = a.share_w ? g + c : g + t * nch + c, slot = gc % kRingSlots;
-                if (t == 0 || !a.share_w) { mbar_wait(sm.w_full(slot), (gc / kRingSlots) & 1); tc_fence_after(); }
-                const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
-                const uint32_t release = (t == 1 || !a.share_w) ? sm.w_empty(slot) : 0u;
-                if (ksteps0 == 4 && a.x4) {
-                  umma_f16_x4<2, 128>(tmem + t * 256, desc_lo_sw128(sa, 16), desc_hi_sw128(1024), desc_lo_sw128(sb, 8192),
-                                      desc_hi_sw128(1024), idesc, c > 0 ? 1u : 0u, release);
-                } else {
-                  for (int ks = 0; ks < ksteps0; ++ks) {
-                    const uint64_t ad = make_desc_sw128(sa + ks * 32, 16, 1024);
-                    const uint64_t bd = make_desc_sw128(sb + ks * 2048, 8192, 1024);
-                    umma_f16(tmem + t * 256, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-                  }
-                  if (release) umma_commit(release);
+    // ---------------- MMA issuer (whole warp, converged; one lane is elected inside each asm statement)
+    constexpr uint32_t idesc = make_idesc_f16(128, W, 0, 1);
+    uint32_t g = 0, par_a = 0u;
+    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+      for (int l = 0; l < net.L; ++l) {
+        const int nch = (l == 0) ? 1 : kNb;
+        const int ksteps0 = (l == 0) ? net.Epad / 16 : 4;   // layer 0 contracts over Epad (<= 64) features
+        // share_w: X[c0,c1] Y[c0,c1] X[c2,c3] Y[c2,c3], a chunk serves both tiles; else X[all] Y[all]
+        const int cstep = a.share_w ? 2 : nch;
+        for (int c0 = 0; c0 < nch; c0 += cstep) {
+          const int c1 = min(c0 + cstep, nch);
+          for (int t = 0; t < 2; ++t) {
+            if (c0 == 0) { mbar_wait_warp(sm.a_ready(t), par_a); tc_fence_after(); }
+            for (int c = c0; c < c1; ++c) {
+              const uint32_t gc = a.share_w ? g + c : g + t * nch + c, slot = gc % kRingSlots;
+              if (t == 0 || !a.share_w) { mbar_wait_warp(sm.w_full(slot), (gc / kRingSlots) & 1); tc_fence_after(); }
+              const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
+              const uint32_t release = (t == 1 || !a.share_w) ? sm.w_empty(slot) : 0u;
+              if (ksteps0 == 4) {
+                umma_f16_x4_warp<2, 128>(tmem + t * 256, desc_lo_sw128(sa, 16), desc_hi_sw128(1024),
+                                         desc_lo_sw128(sb, 8192), desc_hi_sw128(1024), idesc, c > 0 ? 1u : 0u, release);
+              } else {
+                for (int ks = 0; ks < ksteps0; ++ks) {
+                  const uint64_t ad = make_desc_sw128(sa + ks * 32, 16, 1024);
+                  const uint64_t bd = make_desc_sw128(sb + ks * 2048, 8192, 1024);
+                  umma_f16_warp(tmem + t * 256, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
                 }
+                if (release) umma_commit_warp(release);
               }
-              if (c1 == nch) umma_commit(sm.acc_full(t));
             }
+            if (c1 == nch) umma_commit_warp(sm.acc_full(t));
           }
-          g += a.share_w ? nch : 2 * nch;
-          par_a ^= 1u;
         }
+        g += a.share_w ? nch : 2 * nch;
+        par_a ^= 1u;
       }
     }
   } else {
@@ -414,7 +422,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
     constexpr int kCols = W / 2;                      // columns per thread
     const uint32_t acc_base = tmem + ((uint32_t)(q * 32) << 16) + h * kCols;
     uint32_t par_acc = 0;
-    const int enc_dim0 = (16 * h) / net.F, enc_f0 = (16 * h) % net.F;
     const bool pos_mode = a.pos != nullptr;
     auto row_index = [&](int64_t pair, int t) {
       int64_t gs = (2 * pair + t) * kTile + row;
@@ -432,7 +439,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
         {
           float x[3];
           row_pos01(pos_mode, nxt[t], x);
-          encode_row(sA, row, h, x, net, enc_dim0, enc_f0);
+          encode_row(sA, row, h, x, sm.enc_tab());
         }
         fence_async_smem();
         if (kStash && elected) bulk_wait_read0();
@@ -459,17 +466,18 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
           tc_fence_after();
           float sig0 = 0.f, sig1 = 0.f;
           uint32_t mbits[kCols / 32];
-          drain32<kCols>(acc_base + t * 256, [&](int i, const uint32_t (&v)[32]) {
+          drain32<kCols>(acc_base + t * 256, [&](int i, uint32_t (&v)[32]) {
             const int col0 = h * kCols + i * 32;
-            uint32_t hh[16];
+            // packed in place: v[p] <- (v[2p], v[2p+1]); the 16 results stay in the (aligned, consecutive)
+            // registers the TMEM load wrote, so the 128-bit stores need no register shuffling
 #pragma unroll
-            for (int p = 0; p < 16; ++p) hh[p] = cvt_relu_h2(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]));
-            if (kStash) mbits[i] = relu_mask_word(hh);
-            if (!last || kStash) store32(srow, xs, col0, hh);
+            for (int p = 0; p < 16; ++p) v[p] = cvt_relu_h2(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]));
+            if (kStash) mbits[i] = relu_mask_word(v);
+            if (!last || kStash) store32(srow, xs, col0, v);
             if (last) {
 #pragma unroll
               for (int p = 0; p < 16; ++p) {
-                const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&hh[p]));
+                const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&v[p]));
                 const float2 w2 = *reinterpret_cast<const float2*>(sm.wout() + col0 + 2 * p);
                 sig0 = fmaf(r2.x, w2.x, sig0);
                 sig1 = fmaf(r2.y, w2.y, sig1);
@@ -525,79 +533,66 @@ struct BwdArgs {
   const uint8_t* masks;
   uint8_t* dz;           // dZ stash [tiles][L][nb*16 KB]
   int share_w;
-  int x4;
   int stash_last;        // 1: the dZ_L image is stashed too; 0: wgrad rebuilds it from masks, d_sigma, w_out
   float gscale;
   float* d_pos;          // [P,3] or null
 };
 
-template <int W>
+template <int W, bool kDx>
 __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   const PipeSmem sm = carve(smem_raw);
   const Net net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pipe_init(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W);
+  pipe_init(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W, net);
   const uint32_t tmem = *sm.tmem_slot();
   const int64_t pairs = (a.tiles + 1) / 2;
-  const bool want_dx = a.d_pos != nullptr;
+  constexpr bool want_dx = kDx;            // d_pos requested: one more GEMM (layer 0) and the encoding backward
   const int l_lo = want_dx ? 0 : 1;        // GEMMs run for l = L-1 .. l_lo : dA_l = dZ_{l+1} * W_l
   constexpr int kNb = W / 64;              // contraction (out-features of layer l) in 64-wide chunks
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t g = 0;
-      for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
-        for (int l = net.L - 1; l >= l_lo; --l) {
-          const uint32_t bytes = (uint32_t)layer_K(net, l) * 128u;     // one column block: K_l rows x 128 B
-          const int reps = a.share_w ? 1 : 2;
-          for (int t = 0; t < reps; ++t) {
-            for (int c = 0; c < kNb; ++c, ++g) {
-              const uint32_t slot = g % kRingSlots, use = g / kRingSlots;
-              if (use > 0) mbar_wait(sm.w_empty(slot), (use - 1) & 1);
-              mbar_expect_tx(sm.w_full(slot), bytes);
-              bulk_g2s(sm.ring(slot), a.packed + packed_off(net, l) + (int64_t)c * bytes, bytes, sm.w_full(slot));
-            }
+    // ---------------- producer (whole warp, converged)
+    uint32_t g = 0;
+    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+      for (int l = net.L - 1; l >= l_lo; --l) {
+        const uint32_t bytes = (uint32_t)layer_K(net, l) * 128u;     // one column block: K_l rows x 128 B
+        const int reps = a.share_w ? 1 : 2;
+        for (int t = 0; t < reps; ++t) {
+          for (int c = 0; c < kNb; ++c, ++g) {
+            const uint32_t slot = g % kRingSlots, use = g / kRingSlots;
+            if (use > 0) mbar_wait_warp(sm.w_empty(slot), (use - 1) & 1);
+            mbar_expect_tx_warp(sm.w_full(slot), bytes);
+            bulk_g2s_warp(sm.ring(slot), a.packed + packed_off(net, l) + (int64_t)c * bytes, bytes, sm.w_full(slot));
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t g = 0, par_a = 0u;
-      for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
-        for (int l = net.L - 1; l >= l_lo; --l) {
-          const uint32_t idesc = make_idesc_f16(128, layer_K(net, l), 0, 0);
-          const int cstep = a.share_w ? 2 : kNb;
-          for (int c0 = 0; c0 < kNb; c0 += cstep) {
-            const int c1 = min(c0 + cstep, kNb);
-            for (int t = 0; t < 2; ++t) {
-              if (c0 == 0) { mbar_wait(sm.a_ready(t), par_a); tc_fence_after(); }
-              for (int c = c0; c < c1; ++c) {
-                const uint32_t gc = a.share_w ? g + c : g + t * kNb + c, slot = gc % kRingSlots;
-                if (t == 0 || !a.share_w) { mbar_wait(sm.w_full(slot), (gc / kRingSlots) & 1); tc_fence_after(); }
-                const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
-                const uint32_t release = (t == 1 || !a.share_w) ? sm.w_empty(slot) : 0u;
-                if (a.x4) {
-                  umma_f16_x4<2, 2>(tmem + t * 256, desc_lo_sw128(sa, 16), desc_hi_sw128(1024), desc_lo_sw128(sb, 16),
-                                    desc_hi_sw128(1024), idesc, c > 0 ? 1u : 0u, release);
-                } else {
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) {
-                    const uint64_t ad = make_desc_sw128(sa + ks * 32, 16, 1024);
-                    const uint64_t bd = make_desc_sw128(sb + ks * 32, 16, 1024);
-                    umma_f16(tmem + t * 256, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-                  }
-                  if (release) umma_commit(release);
-                }
-              }
-              if (c1 == kNb) umma_commit(sm.acc_full(t));
+    // ---------------- MMA issuer (whole warp, converged)
+    uint32_t g = 0, par_a = 0u;
+    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+      for (int l = net.L - 1; l >= l_lo; --l) {
+        const uint32_t idesc = make_idesc_f16(128, layer_K(net, l), 0, 0);
+        const int cstep = a.share_w ? 2 : kNb;
+        for (int c0 = 0; c0 < kNb; c0 += cstep) {
+          const int c1 = min(c0 + cstep, kNb);
+          for (int t = 0; t < 2; ++t) {
+            if (c0 == 0) { mbar_wait_warp(sm.a_ready(t), par_a); tc_fence_after(); }
+            for (int c = c0; c < c1; ++c) {
+              const uint32_t gc = a.share_w ? g + c : g + t * kNb + c, slot = gc % kRingSlots;
+              if (t == 0 || !a.share_w) { mbar_wait_warp(sm.w_full(slot), (gc / kRingSlots) & 1); tc_fence_after(); }
+              const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
+              const uint32_t release = (t == 1 || !a.share_w) ? sm.w_empty(slot) : 0u;
+              umma_f16_x4_warp<2, 2>(tmem + t * 256, desc_lo_sw128(sa, 16), desc_hi_sw128(1024), desc_lo_sw128(sb, 16),
+                                     desc_hi_sw128(1024), idesc, c > 0 ? 1u : 0u, release);
             }
+            if (c1 == kNb) umma_commit_warp(sm.acc_full(t));
           }
-          g += a.share_w ? kNb : 2 * kNb;
-          par_a ^= 1u;
         }
+        g += a.share_w ? kNb : 2 * kNb;
+        par_a ^= 1u;
       }
     }
   } else {
@@ -647,13 +642,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
           const uint32_t bits = mw[t][it];
           const int col0 = h * kCols + it * 32;
           uint32_t hh[16];
-#pragma unroll
-          for (int p = 0; p < 16; ++p) {
-            const float2 w2 = *reinterpret_cast<const float2*>(sm.wout() + col0 + 2 * p);
-            const float g0 = ((bits >> p) & 1u) ? ds[t] * w2.x : 0.f;
-            const float g1 = ((bits >> (16 + p)) & 1u) ? ds[t] * w2.y : 0.f;
-            hh[p] = cvt_sat_h2(g0, g1);
-          }
+#define LONER_DZL(P)                                                                        \
+  {                                                                                         \
+    const float2 w2 = *reinterpret_cast<const float2*>(sm.wout() + col0 + 2 * P);           \
+    hh[P] = cvt_sat_h2(ds[t] * w2.x, ds[t] * w2.y) & half2_mask<P>(bits);                   \
+  }
+          LONER_DZL(0) LONER_DZL(1) LONER_DZL(2) LONER_DZL(3) LONER_DZL(4) LONER_DZL(5) LONER_DZL(6) LONER_DZL(7)
+          LONER_DZL(8) LONER_DZL(9) LONER_DZL(10) LONER_DZL(11) LONER_DZL(12) LONER_DZL(13) LONER_DZL(14) LONER_DZL(15)
+#undef LONER_DZL
           store32(srow, xs, col0, hh);
         }
         if (net.L >= 2) {
@@ -685,16 +681,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
           if (l >= 1) {
             // dZ_l = dA_l * relu'(Z_l)  -> fp16 image (next GEMM's A operand in smem, wgrad's B operand in HBM)
             const bool feeds_gemm = (l - 1 >= l_lo);
-            drain32<kCols>(acc_row + t * 256 + h * kCols, [&](int i, const uint32_t (&v)[32]) {
+            drain32<kCols>(acc_row + t * 256 + h * kCols, [&](int i, uint32_t (&v)[32]) {
               const uint32_t bits = mw[t][i];
-              uint32_t hh[16];
-#pragma unroll
-              for (int p = 0; p < 16; ++p) {
-                const float g0 = ((bits >> p) & 1u) ? __uint_as_float(v[2 * p]) : 0.f;
-                const float g1 = ((bits >> (16 + p)) & 1u) ? __uint_as_float(v[2 * p + 1]) : 0.f;
-                hh[p] = cvt_sat_h2(g0, g1);
-              }
-              store32(srow, xs, h * kCols + i * 32, hh);
+#define LONER_DZ(P) v[P] = cvt_sat_h2(__uint_as_float(v[2 * P]), __uint_as_float(v[2 * P + 1])) & half2_mask<P>(bits);
+              LONER_DZ(0) LONER_DZ(1) LONER_DZ(2) LONER_DZ(3) LONER_DZ(4) LONER_DZ(5) LONER_DZ(6) LONER_DZ(7)
+              LONER_DZ(8) LONER_DZ(9) LONER_DZ(10) LONER_DZ(11) LONER_DZ(12) LONER_DZ(13) LONER_DZ(14) LONER_DZ(15)
+#undef LONER_DZ
+              store32(srow, xs, h * kCols + i * 32, v);
             });
             tc_fence_before();
             // masks (and d_sigma) of this tile's next step: layer l-2 of this pair, or the first step of the next pair
@@ -718,25 +711,24 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
               float x[3];
               row_pos01(pos_mode, rin[t], x);
               float dx[3] = {0.f, 0.f, 0.f};
-              int dim = 0, f = 0;
-              float scale = 1.0f;
+              const uint2* tab = sm.enc_tab();
               for (int it = 0; it * 32 < net.Epad; ++it) {
                 uint32_t v[32];
                 tmem_ld32(acc_row + t * 256 + it * 32, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int pq = 0; pq < 16; ++pq) {
-                  if (dim < 3) {
-                    const float xv = dim == 0 ? x[0] : (dim == 1 ? x[1] : x[2]);
+                  const uint2 e = tab[it * 16 + pq];
+                  if (e.x < 3u) {
+                    const float xv = e.x == 0u ? x[0] : (e.x == 1u ? x[1] : x[2]);
+                    const float scale = __uint_as_float(e.y);
                     float sn, cs;
                     freq_pair(xv, scale, sn, cs);
                     // d/dx sin(pi 2^f x) = pi 2^f cos, d/dx cos = -pi 2^f sin
                     const float g = (__uint_as_float(v[2 * pq]) * cs - __uint_as_float(v[2 * pq + 1]) * sn) *
                                     (3.14159265358979323846f * scale);
-                    if (dim == 0) dx[0] += g; else if (dim == 1) dx[1] += g; else dx[2] += g;
+                    if (e.x == 0u) dx[0] += g; else if (e.x == 1u) dx[1] += g; else dx[2] += g;
                   }
-                  ++f; scale *= 2.0f;
-                  if (f == net.F) { f = 0; scale = 1.0f; ++dim; }
                 }
               }
               if (in) {
@@ -832,25 +824,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
   const int64_t dzY_off = (int64_t)l * net.nb * kBlk;
   const int64_t n_half = (t1 - t0) * 2;
 
-  if (tid == 0) {
-    // ---- producer: bulk loads, one column block (64 rows x 128 B = 8 KB) per copy
+  if (warp == 0) {
+    // ---- producer (whole warp, converged): bulk loads, one column block (64 rows x 128 B = 8 KB) per copy
     for (int64_t i = 0; i < n_half; ++i) {
       const int s = (int)(i % kWgStages);
       const uint32_t ph = (uint32_t)((i / kWgStages) & 1);
-      mbar_wait(empty_bar(s), ph ^ 1u);
+      mbar_wait_warp(empty_bar(s), ph ^ 1u);
       const int64_t tile = t0 + (i >> 1);
       const int hf = (int)(i & 1);
       const uint32_t dstA = smem_u32(base + s * kWgStageBytes), dstY = dstA + 32768;
-      mbar_expect_tx(full_bar(s), gen_y ? bytesA : bytesA + bytesY);
+      mbar_expect_tx_warp(full_bar(s), gen_y ? bytesA : bytesA + bytesY);
       const uint8_t* srcA = a.acts + tile * act_tile_bytes(net) + actA_off + hf * 8192;
       const uint8_t* srcY = a.dz + tile * dz_tile_bytes(net) + dzY_off + hf * 8192;
-      for (int cb = 0; cb < nbA; ++cb) bulk_g2s(dstA + cb * 8192, srcA + (int64_t)cb * kBlk, 8192, full_bar(s));
+      for (int cb = 0; cb < nbA; ++cb) bulk_g2s_warp(dstA + cb * 8192, srcA + (int64_t)cb * kBlk, 8192, full_bar(s));
       if (!gen_y)
-        for (int cb = 0; cb < nbY; ++cb) bulk_g2s(dstY + cb * 8192, srcY + (int64_t)cb * kBlk, 8192, full_bar(s));
+        for (int cb = 0; cb < nbY; ++cb) bulk_g2s_warp(dstY + cb * 8192, srcY + (int64_t)cb * kBlk, 8192, full_bar(s));
     }
-  } else if (tid == 32) {
-    // ---- MMA issuer.  Both operands MN-major: 64-element MN blocks 8 KB apart (LBO), 8-sample
-    // groups 1 KB apart (SBO), 16 samples per instruction = 2 KB per k-step.
+  } else if (warp == 1) {
+    // ---- MMA issuer (whole warp, converged).  Both operands MN-major: 64-element MN blocks 8 KB apart
+    // (LBO), 8-sample groups 1 KB apart (SBO), 16 samples per instruction = 2 KB per k-step.
     const bool swapped = (l == 0);   // layer 0: M = out-features (from dZ), N = Epad (from A_0)
     const int n_mblk = swapped ? net.W / 128 : K / 128;
     const int Ncols = swapped ? net.Epad : net.W;
@@ -858,21 +850,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
     for (int64_t i = 0; i < n_half; ++i) {
       const int s = (int)(i % kWgStages);
       const uint32_t ph = (uint32_t)((i / kWgStages) & 1);
-      mbar_wait(full_bar(s), ph);
+      mbar_wait_warp(full_bar(s), ph);
       tc_fence_after();
       const uint32_t sX = smem_u32(base + s * kWgStageBytes), sY = sX + 32768;
       for (int mb = 0; mb < n_mblk; ++mb) {
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t aaddr = (swapped ? sY : sX) + mb * 2 * 8192 + ks * 2048;
-          const uint32_t baddr = (swapped ? sX : sY) + ks * 2048;
-          const uint64_t ad = make_desc_sw128(aaddr, 8192, 1024);
-          const uint64_t bd = make_desc_sw128(baddr, 8192, 1024);
-          umma_f16(tmem + mb * 256, ad, bd, idesc, (i > 0 || ks > 0) ? 1u : 0u);
-        }
+        const uint32_t aaddr = (swapped ? sY : sX) + mb * 2 * 8192;
+        const uint32_t baddr = (swapped ? sX : sY);
+        umma_f16_x4_warp<128, 128>(tmem + mb * 256, desc_lo_sw128(aaddr, 8192), desc_hi_sw128(1024),
+                                   desc_lo_sw128(baddr, 8192), desc_hi_sw128(1024), idesc, i > 0 ? 1u : 0u,
+                                   mb == n_mblk - 1 ? empty_bar(s) : 0u);
       }
-      umma_commit(empty_bar(s));
     }
-    umma_commit(done_bar);
+    umma_commit_warp(done_bar);
   }
   __syncwarp();
   if (warp >= 2 && gen_y) {
@@ -1110,11 +1099,6 @@ static inline int share_weights() {
   static const int v = [] { const char* m = getenv("LONER_MMA_ORDER"); return (m && m[0] == 'p') ? 1 : 0; }();
   return v;
 }
-// LONER_MMA_X4=0 issues the MMAs one asm statement each (A/B: inference 1.77 vs 1.57 ms).
-static inline int mma_x4() {
-  static const int v = [] { const char* m = getenv("LONER_MMA_X4"); return (m && m[0] == '0') ? 0 : 1; }();
-  return v;
-}
 static inline bool wgrad_rebuilds_last() {
   static const int on = [] { const char* m = getenv("LONER_WGRAD_GEN"); return (m && m[0] == '1') ? 1 : 0; }();
   return on != 0;
@@ -1153,7 +1137,6 @@ extern "C" int loner_mlp_fwd(const loner_net_t* n, const void* packed, const flo
   a.tiles = n_tiles(P); a.sigma = sigma; a.acts = (uint8_t*)acts;
   a.masks = acts ? (uint8_t*)acts + a.tiles * act_tile_bytes(net) : nullptr;
   a.share_w = share_weights();
-  a.x4 = mma_x4();
   const int sms = device_sm_count();
   const int64_t pairs = (a.tiles + 1) / 2;
   const unsigned grid = (unsigned)(pairs < sms ? pairs : sms);
@@ -1190,13 +1173,13 @@ extern "C" int loner_mlp_dgrad(const loner_net_t* n, const void* packed, const f
   b.dz = (uint8_t*)scratch; b.gscale = grad_scale; b.d_pos = d_pos;
   b.stash_last = wgrad_rebuilds_last() ? 0 : 1;
   b.share_w = share_weights();
-  b.x4 = mma_x4();
   const int64_t pairs = (tiles + 1) / 2;
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem);
     kern<<<(unsigned)(pairs < sms ? pairs : sms), kPipeThreads, kPipeSmem, (cudaStream_t)stream>>>(b);
   };
-  if (net.W == 256) launch(mlp_dgrad_kernel<256>); else launch(mlp_dgrad_kernel<128>);
+  if (net.W == 256) { if (d_pos) launch(mlp_dgrad_kernel<256, true>); else launch(mlp_dgrad_kernel<256, false>); }
+  else              { if (d_pos) launch(mlp_dgrad_kernel<128, true>); else launch(mlp_dgrad_kernel<128, false>); }
   LONER_CHECK_LAUNCH();
   return LONER_OK;
 }

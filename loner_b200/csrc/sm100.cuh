@@ -115,49 +115,85 @@ __host__ __device__ constexpr uint32_t desc_hi_sw128(uint32_t sbo_bytes) {
   return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
 }
 
-// Four MMAs (one 64-deep K chunk) in ONE asm statement, then an optional commit to `commit_bar`
-// (0 = none).  The issuing thread is a single lane of a diverged warp, so every asm statement with
-// uniform-register operands costs a lane-election loop plus the descriptor arithmetic on the (slow)
-// uniform datapath: issuing MMA by MMA took ~270 clk per 128-clk MMA (ncu, profiles/), i.e. the
-// ISSUER bounded the kernels.  kAStep / kBStep = descriptor low-word step per 16-deep k-step.
+// arrive on `bar` when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ------------------------------------------------------------------ warp-convergent issue
+// The *_warp forms are executed by ALL 32 lanes of a converged warp with warp-uniform arguments; one
+// lane is elected inside the asm statement.  In converged code ptxas keeps the operands in uniform
+// registers and emits the UTCHMMA / UBLKCP / UTCBAR back to back; the same instruction issued from a
+// single lane of a diverged warp is wrapped in a lane-election loop (~10 extra instructions each),
+// which made the MMA issuer the bottleneck of the pipelined kernels (profiles/README.md).
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  mbar_wait(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void mbar_expect_tx_warp(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_warp(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16_warp(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint32_t bar) {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+               : "memory");
+}
+// Four MMAs (one 64-deep K chunk: descriptor low words stepped by kAStep / kBStep per 16-deep k-step),
+// then an optional commit to `commit_bar` (0 = none).
 template <int kAStep, int kBStep>
-__device__ __forceinline__ void umma_f16_x4(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
-                                            uint32_t b_hi, uint32_t idesc, uint32_t accumulate,
-                                            uint32_t commit_bar) {
+__device__ __forceinline__ void umma_f16_x4_warp(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                 uint32_t b_hi, uint32_t idesc, uint32_t accumulate,
+                                                 uint32_t commit_bar) {
   asm volatile(
       "{\n\t"
-      ".reg .pred p, q;\n\t"
+      ".reg .pred p, q, e;\n\t"
       ".reg .b64 da, db;\n\t"
       ".reg .b32 al, bl;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
       "setp.ne.b32 p, %6, 0;\n\t"
       "mov.b64 da, {%1, %2};\n\t"
       "mov.b64 db, {%3, %4};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
       "setp.ne.b32 p, %5, 0;\n\t"                       // idesc != 0: accumulate from here on
       "add.u32 al, %1, %8;\n\t"
       "add.u32 bl, %3, %9;\n\t"
       "mov.b64 da, {al, %2};\n\t"
       "mov.b64 db, {bl, %4};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
       "add.u32 al, al, %8;\n\t"
       "add.u32 bl, bl, %9;\n\t"
       "mov.b64 da, {al, %2};\n\t"
       "mov.b64 db, {bl, %4};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
       "add.u32 al, al, %8;\n\t"
       "add.u32 bl, bl, %9;\n\t"
       "mov.b64 da, {al, %2};\n\t"
       "mov.b64 db, {bl, %4};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
       "setp.ne.b32 q, %7, 0;\n\t"
+      "and.pred q, q, e;\n\t"
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
       "}" ::"r"(d_tmem),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(commit_bar), "n"(kAStep), "n"(kBStep)
       : "memory");
-}
-// arrive on `bar` when all previously issued MMAs of this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 // 32 consecutive fp32 columns of this thread's TMEM lane (lane = 32*(warp%4) + laneid)
