@@ -125,8 +125,10 @@ def ncu_traffic_bytes(kernel_substr):
     hdr, units = rows[0], rows[1]
     ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    # the training step runs the stash variant of the forward kernel: mlp_fwd_kernel<W, true>
+    need = [kernel_substr + "_kernel"] + ([", 1>"] if kernel_substr == "mlp_fwd" else [])
     for r in rows[2:]:
-        if kernel_substr in r[ki]:
+        if all(n in r[ki] for n in need):
             return float(r[ri]) * mult.get(units[ri], 1.0) + float(r[wi]) * mult.get(units[wi], 1.0)
     return None
 

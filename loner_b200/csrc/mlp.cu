@@ -100,12 +100,22 @@ __global__ void pack_kernel(Net net, const float* __restrict__ params, uint8_t* 
 // warp 1 = MMA issuer, warps 2-9 = epilogue (two warps per TMEM lane quarter, each owning half of the
 // columns).  Two tiles of 128 samples are in flight with one 256-column TMEM accumulator each; inside
 // a layer the MMAs of tile X (all K chunks) are followed by those of tile Y, and all eight epilogue
-// warps drain X, then Y.  X's epilogue therefore has the whole of Y's tensor time to finish (and vice
-// versa): the layer period is max(2 T_mma, T_mma + E) for an epilogue time E per tile.  The weight
-// chunks are fetched once per TILE (from L2; sharing them between the tiles would force the order
-// X[c0,c1] Y[c0,c1] X[c2,c3] Y[c2,c3] and the period max(2 T_mma, 2E + T_mma), measured 1.5x slower).
-// Ten warps leave 168 registers per thread: three 32-column TMEM buffers, i.e. 4-8 KB per warp in
-// flight (tests/gpu_probe.py: 8 warps reach 99 / 140 B/clk with one / two 4 KB loads in flight).
+// warps drain X, then Y, so X's epilogue has the whole of Y's tensor time to finish (and vice versa).
+// Design points, each measured on the GPU (profiles/README.md):
+//  * producer and issuer run as CONVERGED warps, one lane elected inside each asm statement: issued
+//    from a single lane of a diverged warp every UTCHMMA is wrapped in a lane-election loop and the
+//    issuer, not the tensor pipe, bounded the kernel;
+//  * ten warps leave 168 registers per thread: three 32-column TMEM buffers, 4-8 KB per warp in flight
+//    (tests/gpu_probe.py: 8 warps reach 99 / 140 B/clk with one / two 4 KB loads in flight);
+//  * no local memory at all (tables are address computations or live in shared memory): behind a
+//    saturated HBM a local load misses the 28 KB L1 and stalls its warp for microseconds;
+//  * the weight chunks are fetched once per TILE (LONER_MMA_ORDER=pair shares them between the tiles of
+//    a pair: X[c0,c1] Y[c0,c1] X[c2,c3] Y[c2,c3]; half the L2->SM traffic, but then a tile's epilogue
+//    overlaps only a quarter of the other tile's tensor work - slower in training, equal in inference);
+//  * what bounds the kernels now is the shared-memory data pipe: per tile and layer the tensor core
+//    reads 192 KB of operands (ncu: l1tex__data_pipe_tc_wavefronts), the epilogue stores 64 KB, the
+//    weight ring receives 128 KB and the stash copy reads 64 KB - 448 KB against 2048 tensor clocks.
+//    The next step is cta_group::2 (each SM holds half of B): -64 KB operands, -64 KB ring per tile-layer.
 constexpr int kPipeThreads = 320;
 constexpr int kGroupThreads = 256;
 constexpr int kRingSlots = 3;
@@ -347,6 +357,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pipe_init(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W, net);
   const uint32_t tmem = *sm.tmem_slot();
+  constexpr uint32_t nslots = kRingSlots;
   const int64_t pairs = (a.tiles + 1) / 2;
   constexpr int kNb = W / 64;
   constexpr uint32_t kChunkBytes = kNb * 8192;      // 64 K-rows x W out-features, fp16
@@ -361,7 +372,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
         const int reps = a.share_w ? 1 : 2;      // chunks fetched once per tile PAIR, or once per tile
         for (int t = 0; t < reps; ++t) {
           for (int c = 0; c < nch; ++c, ++g) {
-            const uint32_t slot = g % kRingSlots, use = g / kRingSlots;
+            const uint32_t slot = g % nslots, use = g / nslots;
             if (use > 0) mbar_wait_warp(sm.w_empty(slot), (use - 1) & 1);
             mbar_expect_tx_warp(sm.w_full(slot), kChunkBytes);
             bulk_g2s_warp(sm.ring(slot), fimg + fwd_off(net, l) + (int64_t)c * kChunkBytes, kChunkBytes, sm.w_full(slot));
@@ -384,8 +395,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
           for (int t = 0; t < 2; ++t) {
             if (c0 == 0) { mbar_wait_warp(sm.a_ready(t), par_a); tc_fence_after(); }
             for (int c = c0; c < c1; ++c) {
-              const uint32_t gc = a.share_w ? g + c : g + t * nch + c, slot = gc % kRingSlots;
-              if (t == 0 || !a.share_w) { mbar_wait_warp(sm.w_full(slot), (gc / kRingSlots) & 1); tc_fence_after(); }
+              const uint32_t gc = a.share_w ? g + c : g + t * nch + c, slot = gc % nslots;
+              if (t == 0 || !a.share_w) { mbar_wait_warp(sm.w_full(slot), (gc / nslots) & 1); tc_fence_after(); }
               const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
               const uint32_t release = (t == 1 || !a.share_w) ? sm.w_empty(slot) : 0u;
               if (ksteps0 == 4) {
@@ -547,6 +558,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pipe_init(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W, net);
   const uint32_t tmem = *sm.tmem_slot();
+  constexpr uint32_t nslots = kRingSlots;
   const int64_t pairs = (a.tiles + 1) / 2;
   constexpr bool want_dx = kDx;            // d_pos requested: one more GEMM (layer 0) and the encoding backward
   const int l_lo = want_dx ? 0 : 1;        // GEMMs run for l = L-1 .. l_lo : dA_l = dZ_{l+1} * W_l
@@ -561,7 +573,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
         const int reps = a.share_w ? 1 : 2;
         for (int t = 0; t < reps; ++t) {
           for (int c = 0; c < kNb; ++c, ++g) {
-            const uint32_t slot = g % kRingSlots, use = g / kRingSlots;
+            const uint32_t slot = g % nslots, use = g / nslots;
             if (use > 0) mbar_wait_warp(sm.w_empty(slot), (use - 1) & 1);
             mbar_expect_tx_warp(sm.w_full(slot), bytes);
             bulk_g2s_warp(sm.ring(slot), a.packed + packed_off(net, l) + (int64_t)c * bytes, bytes, sm.w_full(slot));
@@ -581,8 +593,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
           for (int t = 0; t < 2; ++t) {
             if (c0 == 0) { mbar_wait_warp(sm.a_ready(t), par_a); tc_fence_after(); }
             for (int c = c0; c < c1; ++c) {
-              const uint32_t gc = a.share_w ? g + c : g + t * kNb + c, slot = gc % kRingSlots;
-              if (t == 0 || !a.share_w) { mbar_wait_warp(sm.w_full(slot), (gc / kRingSlots) & 1); tc_fence_after(); }
+              const uint32_t gc = a.share_w ? g + c : g + t * kNb + c, slot = gc % nslots;
+              if (t == 0 || !a.share_w) { mbar_wait_warp(sm.w_full(slot), (gc / nslots) & 1); tc_fence_after(); }
               const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
               const uint32_t release = (t == 1 || !a.share_w) ? sm.w_empty(slot) : 0u;
               umma_f16_x4_warp<2, 2>(tmem + t * 256, desc_lo_sw128(sa, 16), desc_hi_sw128(1024), desc_lo_sw128(sb, 16),
@@ -993,7 +1005,7 @@ __global__ void __launch_bounds__(256) dwout_kernel(Net net, const uint8_t* __re
   const int64_t aL = (int64_t)kBlk + (int64_t)(net.L - 1) * net.nb * kBlk;
   for (int64_t tile = gw; tile < tiles; tile += nw) {
     const uint8_t* img = acts + tile * act_tile_bytes(net) + aL;
-#pragma unroll 4
+#pragma unroll 8
     for (int r0 = 0; r0 < kTile; r0 += 4) {
       const int r = r0 + rsub;
       const int64_t gs = tile * kTile + r;

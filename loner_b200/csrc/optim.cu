@@ -33,9 +33,12 @@ ogm_grad_kernel(const float* __restrict__ rays, const float* __restrict__ z_vals
                 int64_t n, int S, float scale, int V, float* __restrict__ d_grid) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * S) return;
-  const int64_t ray = i / S;
+  // consecutive threads = consecutive RAYS at the same sample index: the lanes of a warp then scatter
+  // into different voxels (neighbouring samples of one ray hit the same 8 cells and serialise in L2)
+  const int64_t ray = i % n;
+  const int64_t smp = i / n;
   const float* R = rays + ray * LONER_RAY_COLS;
-  const float z = z_vals[i];
+  const float z = z_vals[ray * S + smp];
   // get_logits_grad: x = s - gt in metres; +0.25 for x < -2, -2.5 for -2 < x < 2   (losses.py:54-62)
   const float x = __fmul_rn(z, scale) - __fmul_rn(depths[ray], scale);
   float g = 0.f;
