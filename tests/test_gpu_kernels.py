@@ -124,7 +124,7 @@ def test_mlp_forward_layers(W, L, P):
     assert torch.equal(sigma, sigma2)
 
 
-@pytest.mark.parametrize("W,L,P", [(256, 4, 1000), (128, 2, 640)])
+@pytest.mark.parametrize("W,L,P", [(256, 4, 1000), (128, 2, 640), (256, 1, 300), (128, 8, 260)])
 def test_mlp_backward_matches_autograd(W, L, P):
     spec = orc.NetSpec(n_frequencies=10, n_neurons=W, n_hidden_layers=L, precision="fp16")
     params = (tcnn_standin.xavier_uniform_flat(spec.shapes, 1337) * 1.5)
@@ -157,6 +157,12 @@ def test_mlp_backward_matches_autograd(W, L, P):
     e = norm_relerr(d_pos, pos_ref.grad)
     print(f"[mlp bwd W={W} L={L}] d_pos norm-rel err {e:.2e}")
     assert e < 1e-2
+    # the variant without d_pos (no layer-0 GEMM, different mask prefetch schedule) must give the same dW
+    d_params2 = torch.zeros(net.param_count, device=DEV)
+    assert ops.mlp_bwd(net, packed, P, d_sigma.to(DEV), acts, 2.0 ** 12, d_params2, pos=posd, want_dpos=False) is None
+    n_hidden = sum(no * ni for no, ni in spec.shapes[:-1])
+    assert torch.equal(d_params2[:n_hidden], d_params[:n_hidden])                  # deterministic reduction
+    assert norm_relerr(d_params2[n_hidden:], d_params[n_hidden:]) < 1e-5            # dW_out: atomics, order varies
 
 
 def _loss_cfg(scale):
