@@ -32,6 +32,9 @@ WORKLOADS = {
     "c5": dict(geom="canteen", K=16, rays_per_gpu=32768, S=512, W=256, L=4, poses=True,
                label="C5 weak scaling, 16-keyframe window, 32768 rays/GPU x 512 samples, joint pose+map"),
     "smoke": dict(geom="canteen", K=2, rays_per_gpu=512, S=128, W=128, L=2, poses=True, label="smoke"),
+    # the sigma head the reference SHIPS (cfg/nerf_config/default_nerf_hash.yaml) at the C2 size
+    "c2hash": dict(geom="canteen", K=1, rays_per_gpu=8192, S=512, W=64, L=1, poses=False, encoding="HashGrid",
+                   label="C2 geometry and size with the reference's shipped sigma head: HashGrid (16 levels x 2, 2^18) + 1x64 MLP"),
 }
 
 
@@ -139,7 +142,7 @@ def build_engine(wl, device, seed):
     wc = synth.world_cube(wl["geom"])
     cfg = eng.EngineConfig(scale=wc.scale_factor, shift=wc.shift, ray_range=synth.GEOMETRY[wl["geom"]]["ray_range"],
                            n_frequencies=10, n_neurons=wl["W"], n_hidden_layers=wl["L"], n_samples=wl["S"],
-                           sampler="OGM", seed=seed)
+                           sampler="OGM", seed=seed, encoding=wl.get("encoding", "Frequency"))
     e = eng.MappingEngine(cfg, device=device)
     scans, poses = synth.make_window(wl["geom"], wl["K"], seed=0)
     for k in range(wl["K"]):
@@ -177,8 +180,15 @@ def cpu_port_rays_per_sec(wl, n_rays, iters, warmup, tune=True):
     K = wl["K"]
     scans, poses = synth.make_window(wl["geom"], K, seed=0)
     poses6 = [synth.axis_angle_from_yaw_pose(poses[k]) for k in range(K)]
-    spec = orc.NetSpec(10, wl["W"], wl["L"], "fp32")
-    params = tcnn_standin.xavier_uniform_flat(spec.shapes, 1337).requires_grad_(True)
+    hash_spec = None
+    if wl.get("encoding") == "HashGrid":
+        from oracle import hashgrid_standin
+        hash_spec = hashgrid_standin.HashGridSpec()
+    spec = orc.NetSpec(10, wl["W"], wl["L"], "fp32", hash=hash_spec)
+    params = tcnn_standin.xavier_uniform_flat(spec.shapes, 1337)
+    if hash_spec is not None:
+        params = torch.cat([params, hashgrid_standin.init_table(hash_spec, 1338)])
+    params.requires_grad_(True)
     m, v = torch.zeros_like(params), torch.zeros_like(params)
     grid = synth.trained_occupancy_grid(wl["geom"])
     shift = torch.tensor(wc.shift)
@@ -338,6 +348,11 @@ def main():
         kern[k] = {"ms": round(t, 4)}
         if k in flops:
             kern[k]["tflops"] = round(flops[k] * per_chunk / (t * 1e-3) / 1e12, 1)
+    hashed = wl.get("encoding") == "HashGrid"
+    if hashed:          # E_pad = 32, no hidden-to-hidden layers; forward and the recomputing backward
+        f_fwd = 2 * (32 * 64 + 64)
+        f_train = 4 * f_fwd
+        flops = {"mlp_fwd": f_fwd, "mlp_dgrad": 3 * f_fwd}
     dom = max((k for k in sections if k in flops), key=lambda k: sections[k])
     achieved = flops[dom] * per_chunk / (sections[dom] * 1e-3) / 1e12
     traffic = ncu_traffic_bytes(dom) if args.workload == "c2" else None
@@ -352,6 +367,17 @@ def main():
                          "achieved_tflops": round(f_train * P / (ms_per_step * 1e-3) / 1e12, 1),
                          "frac_of_sustained_peak": round(f_train * P / (ms_per_step * 1e-3) / 1e12 / peaks["tflops_sustained"], 4)},
                 "kernels": kern}
+    if hashed:
+        # gather/scatter-bound: per sample the backward re-gathers 128 x 4 B and issues 128 x 8 B vector atomics
+        # (the forward gathers 128 x 4 B); the 14.8 MB fp16 table and its 29.7 MB fp32 gradient live in L2
+        nbytes = {"mlp_fwd": 512, "mlp_dgrad": 1536}[dom]
+        gbs = nbytes * per_chunk / (sections[dom] * 1e-3) / 1e9
+        roofline = {"kernel": "hash_bwd" if dom == "mlp_dgrad" else "hash_fwd", "bound": "hbm", "achieved": round(gbs, 1),
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 4), "traffic": None,
+                    "traffic_note": "algorithmic gather + atomic bytes per launch; they are served by L2 (table 14.8 MB, "
+                                    "gradient table 29.7 MB), reported against the measured HBM copy peak",
+                    "peak_source": peaks["source"], "algorithmic_bytes_per_sample": nbytes, "samples_per_launch": per_chunk,
+                    "kernels": kern}
     line = {"metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 (fp32 accumulate, fp32 master weights; render/loss fp32)",

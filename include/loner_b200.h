@@ -98,6 +98,37 @@ int loner_mlp_dgrad(const loner_net_t* net, const void* packed, const float* pos
 int loner_mlp_wgrad(const loner_net_t* net, const void* packed, int64_t P, const float* d_sigma,
                     const void* acts, float grad_scale, float* d_params, void* scratch, void* stream);
 
+/* ---- a12 (shipped configuration), SURVEY 8f rank 1: multiresolution hash encoding + one hidden layer
+ * of 64 neurons = the reference's default `pos_encoding_sigma` / `sigma_network`
+ * (cfg/nerf_config/default_nerf_hash.yaml; models/nerf_tcnn.py:35-38, :59-78).  tiny-cuda-nn semantics
+ * (grid type Hash, linear interpolation, fp16 table / weights / activations, fp32 accumulation).
+ * Flat fp32 params, tcnn order: W1 [64, E_pad] | W_out [16, 64] (row 0 used) | table [entries, 2]. */
+typedef struct {
+  int32_t n_levels;              /* <= 16 */
+  int32_t n_features_per_level;  /* 2 */
+  int32_t log2_hashmap_size;
+  int32_t base_resolution;
+  float per_level_scale;         /* <= 0: tcnn's default 2.0 */
+  int32_t n_neurons;             /* 64 */
+  int32_t n_hidden_layers;       /* 1 */
+  int32_t reserved;
+} loner_hashnet_t;
+
+int64_t loner_hash_param_count(const loner_hashnet_t* net);
+int64_t loner_hash_table_entries(const loner_hashnet_t* net);
+int64_t loner_hash_packed_bytes(const loner_hashnet_t* net);     /* fp16 weights + half2 table */
+int64_t loner_hash_bwd_scratch_bytes(const loner_hashnet_t* net, int64_t P);
+int loner_hash_pack(const loner_hashnet_t* net, const float* params, void* packed, void* stream);
+/* forward: pos [P,3] in [-1,1], or rays [n,13] + z_vals [n,S] with P = n*S.  Nothing is stashed:
+ * the backward recomputes the forward. */
+int loner_hash_fwd(const loner_hashnet_t* net, const void* packed, const float* pos, const float* rays,
+                   const float* z_vals, int32_t S, int64_t P, float* sigma, void* stream);
+/* backward: d_sigma [P] -> d_params (+=, caller zeroes; table gradients by 8-byte vector atomics, weight
+ * gradients through deterministic per-CTA partial sums) and, if d_pos != NULL, d_pos [P,3]. */
+int loner_hash_bwd(const loner_hashnet_t* net, const void* packed, const float* pos, const float* rays,
+                   const float* z_vals, int32_t S, int64_t P, const float* d_sigma, float grad_scale,
+                   float* d_params, float* d_pos, void* scratch, void* stream);
+
 /* ---- a13  raw2outputs (models/rendering_tcnn.py:93-145), sigma-only, far appended, variance.
  * noise: [n,S] standard normals or NULL (then Philox(seed) * raw_noise_std). */
 int loner_render_fwd(const float* sigma, const float* z_vals, const float* rays, int64_t n, int32_t S,

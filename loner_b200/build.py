@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libloner_b200.so")
-SOURCES = ["rays.cu", "sampler.cu", "render.cu", "mlp.cu", "optim.cu", "probe.cu"]
+SOURCES = ["rays.cu", "sampler.cu", "render.cu", "mlp.cu", "hashgrid.cu", "optim.cu", "probe.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

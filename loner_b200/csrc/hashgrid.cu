@@ -1,0 +1,476 @@
+// Sigma head of the reference's SHIPPED configuration: multiresolution hash encoding + one hidden
+// layer of 64 neurons (/root/reference/cfg/nerf_config/default_nerf_hash.yaml `pos_encoding_sigma`,
+// `sigma_network`; built at /root/reference/src/models/nerf_tcnn.py:35-38, evaluated at :59-78).
+// SURVEY.md 8f rank 1.  Semantics: oracle/hashgrid_standin.py (tiny-cuda-nn GridEncoding, grid type
+// Hash, linear interpolation) + oracle/tcnn_standin.py (bias-free ReLU MLP, fp16 weights and
+// activations, fp32 accumulation, fp32 output).
+//
+// This path is gather-bound, not tensor-bound: 16 levels x 8 corners x 4 B per sample out of a 14 MB fp16
+// table that lives in L2, against 4.2 KFLOP of MLP.  Design:
+//  * one sample per thread, the 32 encoded features and the 64 hidden activations stay in registers,
+//    weights are broadcast from shared memory; nothing but sigma is written by the forward;
+//  * the backward RECOMPUTES the forward (re-gathering from L2 is cheaper than a 200 B/sample stash),
+//    scatters table gradients with 8-byte vector atomics (red.global.add.v2.f32) into an fp32 gradient
+//    table, and accumulates dW1 / dW_out per CTA from a shared-memory stash of (dh, enc, h) tiles -
+//    persistent CTAs, per-CTA partial sums, deterministic reduction, no atomics on the weights.
+#include <cmath>
+#include <cstdlib>
+#include "common.cuh"
+
+namespace loner {
+namespace hashgrid {
+
+constexpr int kMaxLevels = 16;
+constexpr int kW = 64;             // hidden width
+constexpr int kThreads = 256;
+
+struct HashNet {
+  int n_levels, E, Epad;           // E = 2 * n_levels encoded features, padded to 16 with 1.0
+  float scale[kMaxLevels];
+  uint32_t res[kMaxLevels];
+  uint32_t entries[kMaxLevels];    // "hashmap size" of the level
+  uint32_t offset[kMaxLevels + 1]; // first entry of the level in the table
+  uint32_t dense[kMaxLevels];      // 1: index = x + y res + z res^2, 0: spatial hash
+};
+
+__host__ inline bool net_from(const loner_hashnet_t* n, HashNet& o) {
+  if (!n) return false;
+  if (n->n_levels < 1 || n->n_levels > kMaxLevels || n->n_features_per_level != 2) return false;
+  if (n->log2_hashmap_size < 4 || n->log2_hashmap_size > 24 || n->base_resolution < 1) return false;
+  if (n->n_neurons != kW || n->n_hidden_layers != 1) return false;
+  const float pls = n->per_level_scale > 0.f ? n->per_level_scale : 2.0f;
+  o.n_levels = n->n_levels;
+  o.E = 2 * n->n_levels;
+  o.Epad = (o.E + 15) / 16 * 16;
+  uint32_t off = 0;
+  const float log2_pls = log2f(pls);
+  for (int l = 0; l < o.n_levels; ++l) {
+    const float scale = exp2f((float)l * log2_pls) * (float)n->base_resolution - 1.0f;   // grid_scale()
+    const uint32_t res = (uint32_t)ceilf(scale) + 1u;                                     // grid_resolution()
+    const double cube = (double)res * res * res;
+    uint64_t cnt = cube > 2147483647.0 ? 2147483647ull : (uint64_t)cube;
+    cnt = (cnt + 7) / 8 * 8;
+    const uint64_t cap = 1ull << n->log2_hashmap_size;
+    if (cnt > cap) cnt = cap;
+    // grid_index(): walk the strides while stride <= hashmap size; hashed iff the walk was cut short
+    uint64_t stride = 1;
+    for (int d = 0; d < 3 && stride <= cnt; ++d) stride *= res;
+    o.scale[l] = scale; o.res[l] = res; o.entries[l] = (uint32_t)cnt; o.offset[l] = off;
+    o.dense[l] = (cnt < stride) ? 0u : 1u;
+    off += (uint32_t)cnt;
+  }
+  for (int l = o.n_levels; l <= kMaxLevels; ++l) o.offset[l] = off;
+  for (int l = o.n_levels; l < kMaxLevels; ++l) { o.scale[l] = 0.f; o.res[l] = 1; o.entries[l] = 1; o.dense[l] = 1; }
+  return true;
+}
+__host__ __device__ inline int64_t n_entries(const HashNet& n) { return n.offset[kMaxLevels]; }
+__host__ __device__ inline int64_t w1_floats(const HashNet& n) { return (int64_t)kW * n.Epad; }
+__host__ __device__ inline int64_t net_floats(const HashNet& n) { return w1_floats(n) + 16 * kW; }   // + padded [16, W] output matrix
+// packed image: W1 fp16 [64][Epad] | w_out fp32 [64] (values of the fp16-rounded row 0) | table half2 [entries]
+__host__ __device__ inline int64_t packed_wout_off(const HashNet& n) { return w1_floats(n) * 2; }
+__host__ __device__ inline int64_t packed_table_off(const HashNet& n) { return packed_wout_off(n) + kW * 4; }
+__host__ __device__ inline int64_t packed_total(const HashNet& n) { return packed_table_off(n) + n_entries(n) * 4; }
+
+__global__ void __launch_bounds__(256) pack_kernel(HashNet net, const float* __restrict__ params, uint8_t* __restrict__ packed) {
+  const int64_t nw1 = w1_floats(net), nt = n_entries(net);
+  __half* w1 = reinterpret_cast<__half*>(packed);
+  float* wo = reinterpret_cast<float*>(packed + packed_wout_off(net));
+  __half2* tb = reinterpret_cast<__half2*>(packed + packed_table_off(net));
+  const float* tsrc = params + net_floats(net);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw1 + kW + nt; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < nw1) w1[i] = __float2half_rn(params[i]);
+    else if (i < nw1 + kW) wo[i - nw1] = __half2float(__float2half_rn(params[nw1 + (i - nw1)]));   // row 0 of [16, W]
+    else { const int64_t e = i - nw1 - kW; tb[e] = __floats2half2_rn(tsrc[2 * e], tsrc[2 * e + 1]); }
+  }
+}
+
+struct Args {
+  HashNet net;
+  const uint8_t* packed;
+  const float* pos;      // [P,3] in [-1,1] or null
+  const float* rays;     // [n,13]
+  const float* z;        // [n,S]
+  int S;
+  int64_t P;
+  float* sigma;          // forward output
+  const float* d_sigma;  // backward input
+  float gscale;          // loss scale of the fp16 (dh) stash
+  float* d_table;        // [entries][2] fp32, += with vector atomics
+  float* d_pos;          // [P,3] or null
+  float* partials;       // [gridDim.x][64*Epad + 64]
+};
+
+// sample position in [0,1]^3:  (o + d z + 1) / 2     rendering_tcnn.py:241, nerf_tcnn.py:63
+__device__ __forceinline__ void position01(const Args& a, int64_t s, float (&x)[3]) {
+  if (a.pos) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x[d] = __fmul_rn(__fadd_rn(__ldg(a.pos + s * 3 + d), 1.0f), 0.5f);
+  } else {
+    const int64_t ray = s / a.S;
+    const float* R = a.rays + ray * LONER_RAY_COLS;
+    const float z = __ldg(a.z + s);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float p = __fadd_rn(__ldg(R + d), __fmul_rn(__ldg(R + 3 + d), z));
+      x[d] = __fmul_rn(__fadd_rn(p, 1.0f), 0.5f);
+    }
+  }
+}
+
+struct Cell {
+  uint32_t c[3];
+  float f[3];
+};
+__device__ __forceinline__ Cell locate(float scale, const float (&x)[3]) {
+  Cell r;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float pos = fmaf(scale, x[d], 0.5f);
+    const float fl = floorf(pos);
+    r.c[d] = (uint32_t)(int)fl;
+    r.f[d] = pos - fl;
+  }
+  return r;
+}
+__device__ __forceinline__ uint32_t entry_index(uint32_t px, uint32_t py, uint32_t pz, uint32_t res, uint32_t entries, bool dense) {
+  uint32_t idx = dense ? px + py * res + pz * res * res : (px * 1u) ^ (py * 2654435761u) ^ (pz * 805459861u);
+  return ((entries & (entries - 1u)) == 0u) ? (idx & (entries - 1u)) : (idx % entries);
+}
+__device__ __forceinline__ float corner_weight(const Cell& q, int c) {
+  return ((c & 1) ? q.f[0] : 1.0f - q.f[0]) * ((c & 2) ? q.f[1] : 1.0f - q.f[1]) * ((c & 4) ? q.f[2] : 1.0f - q.f[2]);
+}
+
+// encoded features of one sample, as fp32 values of the fp16-rounded encoding (tcnn writes __half)
+__device__ __forceinline__ void encode(const HashNet& net, const __half2* __restrict__ table, const float (&x)[3],
+                                       float (&enc)[2 * kMaxLevels]) {
+#pragma unroll
+  for (int l = 0; l < kMaxLevels; ++l) {
+    if (l < net.n_levels) {
+      const Cell q = locate(net.scale[l], x);
+      const __half2* t = table + net.offset[l];
+      const uint32_t res = net.res[l], ent = net.entries[l];
+      const bool dense = net.dense[l] != 0u;
+      float ax = 0.f, ay = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t idx = entry_index(q.c[0] + (c & 1), q.c[1] + ((c >> 1) & 1), q.c[2] + (c >> 2), res, ent, dense);
+        const float2 v = __half22float2(__ldg(t + idx));
+        const float w = corner_weight(q, c);
+        ax = fmaf(w, v.x, ax);
+        ay = fmaf(w, v.y, ay);
+      }
+      const float2 r = __half22float2(__floats2half2_rn(ax, ay));
+      enc[2 * l] = r.x; enc[2 * l + 1] = r.y;
+    } else {
+      const float pad = (2 * l < net.Epad) ? 1.0f : 0.0f;     // encoded width padded to 16 with ones
+      enc[2 * l] = pad; enc[2 * l + 1] = pad;
+    }
+  }
+}
+
+// hidden pre-activation j:  sum_i W1[j][i] enc[i]   (fp16 weights broadcast from shared memory, fp32 accumulate)
+__device__ __forceinline__ float hidden_dot(const __half2* __restrict__ sW1row, const float (&enc)[2 * kMaxLevels], int pairs) {
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxLevels; ++i) {
+    if (i < pairs) {
+      const float2 w = __half22float2(sW1row[i]);
+      a0 = fmaf(w.x, enc[2 * i], a0);
+      a1 = fmaf(w.y, enc[2 * i + 1], a1);
+    }
+  }
+  return a0 + a1;
+}
+__device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
+
+__device__ __forceinline__ void load_weights(const Args& a, __half2 (*sW1)[kMaxLevels], float* sWout, int tid) {
+  const __half2* w1 = reinterpret_cast<const __half2*>(a.packed);
+  const int pairs = a.net.Epad / 2;
+  for (int i = tid; i < kW * kMaxLevels; i += kThreads) {
+    const int j = i / kMaxLevels, k = i % kMaxLevels;
+    sW1[j][k] = k < pairs ? w1[j * pairs + k] : __floats2half2_rn(0.f, 0.f);
+  }
+  const float* wo = reinterpret_cast<const float*>(a.packed + packed_wout_off(a.net));
+  for (int j = tid; j < kW; j += kThreads) sWout[j] = wo[j];
+}
+
+__global__ void __launch_bounds__(kThreads) hash_fwd_kernel(const Args a) {
+  __shared__ __half2 sW1[kW][kMaxLevels];
+  __shared__ float sWout[kW];
+  load_weights(a, sW1, sWout, threadIdx.x);
+  __syncthreads();
+  const __half2* table = reinterpret_cast<const __half2*>(a.packed + packed_table_off(a.net));
+  const int pairs = a.net.Epad / 2;
+  for (int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x; s < a.P; s += (int64_t)gridDim.x * kThreads) {
+    float x[3], enc[2 * kMaxLevels];
+    position01(a, s, x);
+    encode(a.net, table, x, enc);
+    float sig0 = 0.f, sig1 = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < kW; j += 2) {
+      const float h0 = round_h(fmaxf(hidden_dot(sW1[j], enc, pairs), 0.f));
+      const float h1 = round_h(fmaxf(hidden_dot(sW1[j + 1], enc, pairs), 0.f));
+      sig0 = fmaf(h0, sWout[j], sig0);
+      sig1 = fmaf(h1, sWout[j + 1], sig1);
+    }
+    a.sigma[s] = sig0 + sig1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: recompute, d_sigma -> table gradients (vector atomics), per-CTA dW1 / dW_out partials, d_pos
+// Stash rows are written by their owning thread with 16-byte stores; the row strides (144 B and 80 B)
+// put the eight lanes of a quarter warp on disjoint bank groups.
+constexpr int kStashH = kW + 8;            // halves per row of the dh and h stashes (144 B)
+constexpr int kStashE = 2 * kMaxLevels + 8;   // halves per row of the encoding stash (80 B)
+struct BwdSmem {
+  __half2 sW1[kW][kMaxLevels];             // 4 KB
+  float sWout[kW];
+  float s_ds[kThreads];
+  __align__(16) __half s_dh[kThreads][kStashH];    // 36 KB  loss-scaled dh, fp16
+  __align__(16) __half s_h[kThreads][kStashH];     // 36 KB  hidden activations (already fp16 values)
+  __align__(16) __half s_enc[kThreads][kStashE];   // 20 KB  encoded inputs (already fp16 values)
+};
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <bool kDx>
+__global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const Args a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  load_weights(a, sm.sW1, sm.sWout, tid);
+  __syncthreads();
+  const HashNet& net = a.net;
+  const __half2* table = reinterpret_cast<const __half2*>(a.packed + packed_table_off(net));
+  const int pairs = net.Epad / 2;
+  // this thread's slice of dW1: row j = tid / 4, columns [i0, i0 + per)
+  const int per = net.Epad / 4;            // 4 or 8
+  const int gj = tid >> 2, i0 = (tid & 3) * per;
+  float accW[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) accW[k] = 0.f;
+  float accWout = 0.f;                     // threads 0..63: dW_out[tid]
+  const int64_t n_tiles = (a.P + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t s = tile * kThreads + tid;
+    const bool in = s < a.P;
+    float x[3] = {0.f, 0.f, 0.f}, enc[2 * kMaxLevels];
+    if (in) position01(a, s, x);
+    encode(net, table, x, enc);
+    const float ds = in ? __ldg(a.d_sigma + s) : 0.f;
+    // forward through the hidden layer, backward into d_enc
+    float d_enc[2 * kMaxLevels];
+#pragma unroll
+    for (int i = 0; i < 2 * kMaxLevels; ++i) d_enc[i] = 0.f;
+    for (int j0 = 0; j0 < kW; j0 += 8) {
+      float hv[8], dv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = j0 + u;
+        const float hj = round_h(fmaxf(hidden_dot(sm.sW1[j], enc, pairs), 0.f));
+        const float dh = hj > 0.f ? ds * sm.sWout[j] : 0.f;
+        hv[u] = hj;
+        dv[u] = fminf(fmaxf(dh * a.gscale, -65504.f), 65504.f);
+#pragma unroll
+        for (int i = 0; i < kMaxLevels; ++i) {
+          if (i < pairs) {
+            const float2 w = __half22float2(sm.sW1[j][i]);
+            d_enc[2 * i] = fmaf(dh, w.x, d_enc[2 * i]);
+            d_enc[2 * i + 1] = fmaf(dh, w.y, d_enc[2 * i + 1]);
+          }
+        }
+      }
+      *reinterpret_cast<uint4*>(&sm.s_h[tid][j0]) =
+          make_uint4(pack_h2(hv[0], hv[1]), pack_h2(hv[2], hv[3]), pack_h2(hv[4], hv[5]), pack_h2(hv[6], hv[7]));
+      *reinterpret_cast<uint4*>(&sm.s_dh[tid][j0]) =
+          make_uint4(pack_h2(dv[0], dv[1]), pack_h2(dv[2], dv[3]), pack_h2(dv[4], dv[5]), pack_h2(dv[6], dv[7]));
+    }
+    sm.s_ds[tid] = ds;
+#pragma unroll
+    for (int i = 0; i < 2 * kMaxLevels; i += 8)
+      *reinterpret_cast<uint4*>(&sm.s_enc[tid][i]) =
+          make_uint4(pack_h2(enc[i], enc[i + 1]), pack_h2(enc[i + 2], enc[i + 3]), pack_h2(enc[i + 4], enc[i + 5]),
+                     pack_h2(enc[i + 6], enc[i + 7]));
+    // scatter into the gradient table, and d_pos through the interpolation weights
+    float dx[3] = {0.f, 0.f, 0.f};
+    if (in && ds != 0.f) {
+#pragma unroll
+      for (int l = 0; l < kMaxLevels; ++l) {
+        if (l < net.n_levels) {
+          const Cell q = locate(net.scale[l], x);
+          const uint32_t res = net.res[l], ent = net.entries[l];
+          const bool dense = net.dense[l] != 0u;
+          float2* gt = reinterpret_cast<float2*>(a.d_table) + net.offset[l];
+          const float gx = d_enc[2 * l], gy = d_enc[2 * l + 1];
+          float lx[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t idx = entry_index(q.c[0] + (c & 1), q.c[1] + ((c >> 1) & 1), q.c[2] + (c >> 2), res, ent, dense);
+            const float w = corner_weight(q, c);
+            atomicAdd(gt + idx, make_float2(w * gx, w * gy));
+            if (kDx) {
+              const float2 v = __half22float2(__ldg(table + net.offset[l] + idx));
+              const float dot = v.x * gx + v.y * gy;
+              const float w0 = (c & 1) ? q.f[0] : 1.0f - q.f[0], w1 = (c & 2) ? q.f[1] : 1.0f - q.f[1],
+                          w2 = (c & 4) ? q.f[2] : 1.0f - q.f[2];
+              lx[0] += ((c & 1) ? 1.0f : -1.0f) * w1 * w2 * dot;
+              lx[1] += ((c & 2) ? 1.0f : -1.0f) * w0 * w2 * dot;
+              lx[2] += ((c & 4) ? 1.0f : -1.0f) * w0 * w1 * dot;
+            }
+          }
+          if (kDx) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) dx[d] = fmaf(net.scale[l], lx[d], dx[d]);
+          }
+        }
+      }
+    }
+    if (kDx && in) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) a.d_pos[s * 3 + d] = 0.5f * dx[d];     // x = (pos + 1) / 2
+    }
+    __syncthreads();
+    // dW1[j][i] += sum_s dh[s][j] enc[s][i];  dW_out[j] += sum_s d_sigma[s] h[s][j]
+    for (int t = 0; t < kThreads; ++t) {
+      const float dh = __half2float(sm.s_dh[t][gj]);
+      if (per == 8) {
+        const uint4 e4 = *reinterpret_cast<const uint4*>(&sm.s_enc[t][i0]);
+        const uint32_t ew[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&ew[k]));
+          accW[2 * k] = fmaf(dh, e.x, accW[2 * k]);
+          accW[2 * k + 1] = fmaf(dh, e.y, accW[2 * k + 1]);
+        }
+      } else {
+        const uint2 e2 = *reinterpret_cast<const uint2*>(&sm.s_enc[t][i0]);
+        const uint32_t ew[2] = {e2.x, e2.y};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&ew[k]));
+          accW[2 * k] = fmaf(dh, e.x, accW[2 * k]);
+          accW[2 * k + 1] = fmaf(dh, e.y, accW[2 * k + 1]);
+        }
+      }
+      if (tid < kW) accWout = fmaf(sm.s_ds[t], __half2float(sm.s_h[t][tid]), accWout);
+    }
+    __syncthreads();
+  }
+  float* part = a.partials + (int64_t)blockIdx.x * (w1_floats(net) + kW);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (k < per) part[gj * net.Epad + i0 + k] = accW[k];
+  if (tid < kW) part[w1_floats(net) + tid] = accWout;
+}
+
+// d_params[W1] += sum_b partials[b][W1] / gscale;  d_params[W_out row 0] += sum_b partials[b][W_out]
+__global__ void __launch_bounds__(256) hash_reduce_kernel(HashNet net, const float* __restrict__ partials, int n_blocks,
+                                                         float inv_gscale, float* __restrict__ d_params) {
+  const int64_t nw1 = w1_floats(net), per = nw1 + kW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < n_blocks; ++b) s += partials[(int64_t)b * per + i];
+    if (i < nw1) d_params[i] += s * inv_gscale;
+    else d_params[nw1 + (i - nw1)] += s;
+  }
+}
+
+inline int sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      sms <= 0) {
+    cudaGetLastError();
+    sms = 148;
+  }
+  return sms;
+}
+inline int bwd_blocks() { return sm_count() * 2; }      // 85 KB of shared memory per CTA: two per SM
+
+}  // namespace hashgrid
+}  // namespace loner
+
+using namespace loner::hashgrid;
+
+extern "C" int64_t loner_hash_param_count(const loner_hashnet_t* n) {
+  HashNet net;
+  if (!net_from(n, net)) return -1;
+  return net_floats(net) + n_entries(net) * 2;
+}
+extern "C" int64_t loner_hash_table_entries(const loner_hashnet_t* n) {
+  HashNet net;
+  if (!net_from(n, net)) return -1;
+  return n_entries(net);
+}
+extern "C" int64_t loner_hash_packed_bytes(const loner_hashnet_t* n) {
+  HashNet net;
+  if (!net_from(n, net)) return -1;
+  return packed_total(net);
+}
+extern "C" int64_t loner_hash_bwd_scratch_bytes(const loner_hashnet_t* n, int64_t P) {
+  HashNet net;
+  if (!net_from(n, net) || P < 0) return -1;
+  return (int64_t)bwd_blocks() * (w1_floats(net) + kW) * 4;
+}
+
+extern "C" int loner_hash_pack(const loner_hashnet_t* n, const float* params, void* packed, void* stream) {
+  HashNet net;
+  if (!net_from(n, net)) return LONER_E_UNSUPPORTED;
+  if (!params || !packed) return LONER_E_BAD_ARG;
+  pack_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(net, params, (uint8_t*)packed);
+  LONER_CHECK_LAUNCH();
+  return LONER_OK;
+}
+
+static int fill_args(const loner_hashnet_t* n, Args& a, const void* packed, const float* pos, const float* rays,
+                     const float* z_vals, int32_t S, int64_t P) {
+  if (!net_from(n, a.net)) return LONER_E_UNSUPPORTED;
+  if (!packed || P < 0 || (!pos && (!rays || !z_vals || S <= 0))) return LONER_E_BAD_ARG;
+  a.packed = (const uint8_t*)packed; a.pos = pos; a.rays = rays; a.z = z_vals; a.S = S > 0 ? S : 1; a.P = P;
+  a.sigma = nullptr; a.d_sigma = nullptr; a.gscale = 1.f; a.d_table = nullptr; a.d_pos = nullptr; a.partials = nullptr;
+  return LONER_OK;
+}
+
+extern "C" int loner_hash_fwd(const loner_hashnet_t* n, const void* packed, const float* pos, const float* rays,
+                              const float* z_vals, int32_t S, int64_t P, float* sigma, void* stream) {
+  if (P == 0) { HashNet t; return net_from(n, t) ? LONER_OK : LONER_E_UNSUPPORTED; }
+  Args a;
+  const int rc = fill_args(n, a, packed, pos, rays, z_vals, S, P);
+  if (rc) return rc;
+  if (!sigma) return LONER_E_BAD_ARG;
+  a.sigma = sigma;
+  const int64_t want = (P + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  hash_fwd_kernel<<<(unsigned)(want < cap ? want : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+  LONER_CHECK_LAUNCH();
+  return LONER_OK;
+}
+
+extern "C" int loner_hash_bwd(const loner_hashnet_t* n, const void* packed, const float* pos, const float* rays,
+                              const float* z_vals, int32_t S, int64_t P, const float* d_sigma, float grad_scale,
+                              float* d_params, float* d_pos, void* scratch, void* stream) {
+  if (P == 0) { HashNet t; return net_from(n, t) ? LONER_OK : LONER_E_UNSUPPORTED; }
+  Args a;
+  const int rc = fill_args(n, a, packed, pos, rays, z_vals, S, P);
+  if (rc) return rc;
+  if (!d_sigma || !d_params || !scratch || !(grad_scale > 0.f)) return LONER_E_BAD_ARG;
+  a.d_sigma = d_sigma; a.gscale = grad_scale; a.d_pos = d_pos; a.partials = (float*)scratch;
+  a.d_table = d_params + net_floats(a.net);
+  const int64_t tiles = (P + kThreads - 1) / kThreads;
+  const int blocks = (int)(tiles < bwd_blocks() ? tiles : bwd_blocks());
+  cudaStream_t st = (cudaStream_t)stream;
+  const int smem = (int)sizeof(BwdSmem);
+  if (d_pos) {
+    cudaFuncSetAttribute(hash_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    hash_bwd_kernel<true><<<blocks, kThreads, smem, st>>>(a);
+  } else {
+    cudaFuncSetAttribute(hash_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    hash_bwd_kernel<false><<<blocks, kThreads, smem, st>>>(a);
+  }
+  LONER_CHECK_LAUNCH();
+  hash_reduce_kernel<<<16, 256, 0, st>>>(a.net, a.partials, blocks, 1.0f / grad_scale, d_params);
+  LONER_CHECK_LAUNCH();
+  return LONER_OK;
+}

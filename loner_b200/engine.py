@@ -54,9 +54,15 @@ class EngineConfig:
     shift: tuple
     ray_range: tuple
     # network (nerf_config: pos_encoding_sigma / sigma_network keys)
+    encoding: str = "Frequency"         # pos_encoding_sigma.otype: Frequency | HashGrid (the shipped default)
     n_frequencies: int = 10
     n_neurons: int = 256
     n_hidden_layers: int = 4
+    # HashGrid keys of cfg/nerf_config/default_nerf_hash.yaml (with encoding="HashGrid": n_neurons 64, 1 hidden layer)
+    n_levels: int = 16
+    log2_hashmap_size: int = 18
+    base_resolution: int = 16
+    per_level_scale: float = 2.0
     # render (default_model_config.yaml:11-20)
     n_samples: int = 512
     perturb: float = 1.0
@@ -104,13 +110,23 @@ class MappingEngine:
     def __init__(self, cfg: EngineConfig, device="cuda", params: torch.Tensor = None):
         self.cfg = cfg
         self.dev = torch.device(device)
-        self.net = ops.Net(cfg.n_frequencies, cfg.n_neurons, cfg.n_hidden_layers)
+        if cfg.encoding not in ("Frequency", "HashGrid"):
+            raise ValueError(f"unknown pos_encoding_sigma.otype {cfg.encoding}")
+        self.hash = cfg.encoding == "HashGrid"
+        if self.hash:
+            self.net = ops.HashNet(cfg.n_levels, 2, cfg.log2_hashmap_size, cfg.base_resolution, cfg.per_level_scale,
+                                   cfg.n_neurons, cfg.n_hidden_layers)
+        else:
+            self.net = ops.Net(cfg.n_frequencies, cfg.n_neurons, cfg.n_hidden_layers)
         if params is None:
             params = xavier_uniform_flat(self.net.layer_shapes(), 1337)
+            if self.hash:           # tcnn: table ~ U(-1e-4, 1e-4), after the network matrices
+                g = torch.Generator().manual_seed(1338)
+                params = torch.cat([params, (torch.rand(2 * self.net.table_entries, generator=g) * 2 - 1) * 1e-4])
         assert params.numel() == self.net.param_count
         self.params = params.detach().to(self.dev, torch.float32).contiguous().clone()
         self.packed = torch.empty(self.net.packed_bytes, device=self.dev, dtype=torch.uint8)
-        ops.mlp_pack(self.net, self.params, self.packed)
+        self._pack()
         self.exp_avg = torch.zeros_like(self.params)
         self.exp_avg_sq = torch.zeros_like(self.params)
         self.adam_t = 0
@@ -142,6 +158,19 @@ class MappingEngine:
         self._last_d_poses12 = None
         self._counters = torch.zeros(2, device=self.dev, dtype=torch.int32)
         self._loss_acc = torch.zeros(4, device=self.dev, dtype=torch.float32)
+
+    def _pack(self):
+        """fp32 master parameters -> the fp16 image the kernels read (after construction and every Adam step)."""
+        if self.hash:
+            ops.hash_pack(self.net, self.params, self.packed)
+        else:
+            ops.mlp_pack(self.net, self.params, self.packed)
+
+    def _sigma(self, P, rays, z):
+        """Inference forward (no stash)."""
+        if self.hash:
+            return ops.hash_fwd(self.net, self.packed, P, rays=rays, z=z)
+        return ops.mlp_fwd(self.net, self.packed, P, rays=rays, z=z, stash=False)[0]
 
     # ---------------------------------------------------------------- keyframes
     def add_keyframe(self, ray_directions, distances, pose6, mask=None):
@@ -315,20 +344,29 @@ class MappingEngine:
                     z = ops.sample_ogm(r, self.grid, S, cfg.perturb, u1, u2, seed=seed + c0)
                 else:
                     z = ops.sample_uniform(r, S, cfg.perturb, u1, seed=seed + c0)
-            acts = self._buf("acts", self.net.act_bytes(P))
+            acts = None if self.hash else self._buf("acts", self.net.act_bytes(P))
             with self._sec("mlp_fwd"):
-                sigma, _ = ops.mlp_fwd(self.net, self.packed, P, rays=r, z=z, stash=True, acts=acts)
+                if self.hash:       # nothing is stashed: the hash-grid backward recomputes the forward
+                    sigma = ops.hash_fwd(self.net, self.packed, P, rays=r, z=z)
+                else:
+                    sigma, _ = ops.mlp_fwd(self.net, self.packed, P, rays=r, z=z, stash=True, acts=acts)
             with self._sec("render_loss"):
                 res = ops.render_loss(sigma, z, r, dpt, fl, counters, cfg.loss_cfg(self.phase_iteration), noise=noise,
                                       raw_noise_std=cfg.raw_noise_std, seed=seed + c0 + 1, loss_acc=loss_acc,
                                       want_outputs=want_outputs, d_rays=d_rays[c0:c1] if optimize_poses else None)
-            scratch = self._buf("scratch", self.net.bwd_scratch_bytes(P))
-            with self._sec("mlp_dgrad"):
-                d_pos = ops.mlp_dgrad(self.net, self.packed, P, res["d_sigma"], acts, gscale, scratch, rays=r, z=z,
-                                      want_dpos=optimize_poses)
-            with self._sec("mlp_wgrad"):
-                ops.mlp_wgrad(self.net, self.packed, P, res["d_sigma"], acts, gscale, self.d_params, scratch)
-            self.launches += 3 + 4
+            scratch = self._buf("scratch", max(self.net.bwd_scratch_bytes(P), 16))
+            if self.hash:
+                with self._sec("mlp_dgrad"):
+                    d_pos = ops.hash_bwd(self.net, self.packed, P, res["d_sigma"], gscale, self.d_params, rays=r, z=z,
+                                         want_dpos=optimize_poses, scratch=scratch)
+                self.launches += 3 + 2      # sampler, forward, render/loss; backward, partial reduce
+            else:
+                with self._sec("mlp_dgrad"):
+                    d_pos = ops.mlp_dgrad(self.net, self.packed, P, res["d_sigma"], acts, gscale, scratch, rays=r, z=z,
+                                          want_dpos=optimize_poses)
+                with self._sec("mlp_wgrad"):
+                    ops.mlp_wgrad(self.net, self.packed, P, res["d_sigma"], acts, gscale, self.d_params, scratch)
+                self.launches += 3 + 4
             if optimize_poses:
                 ops.points_bwd(d_pos, z, d_rays[c0:c1])
                 self.launches += 1
@@ -360,7 +398,7 @@ class MappingEngine:
             with self._sec("adam_pack"):
                 ops.adam_step(self.params, self.d_params, self.exp_avg, self.exp_avg_sq, self.adam_t,
                               cfg.lrate_sigma_mlp)
-                ops.mlp_pack(self.net, self.params, self.packed)
+                self._pack()
             self.launches += 2
         cnt = counters.to(torch.float32)
         loss = (cfg.depthloss_lambda * loss_acc[0] / cnt[1] + cfg.los_lambda * loss_acc[1] / (cnt[0] * cfg.n_samples)
@@ -396,7 +434,7 @@ class MappingEngine:
             z = ops.sample_ogm(rays, self.grid, S, 0.0, None, None, seed=seed)
         else:
             z = ops.sample_uniform(rays, S, 0.0, None, seed=seed)
-        sigma, _ = ops.mlp_fwd(self.net, self.packed, rays.shape[0] * S, rays=rays, z=z, stash=False)
+        sigma = self._sigma(rays.shape[0] * S, rays, z)
         w, d, o, v = ops.render_fwd(sigma, z, rays, noise=None, raw_noise_std=cfg.raw_noise_std, seed=seed + 1,
                                     want_weights=False)
         self.launches += 3

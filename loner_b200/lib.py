@@ -18,6 +18,12 @@ class NetT(_c.Structure):
     _fields_ = [("n_frequencies", _i32), ("n_neurons", _i32), ("n_hidden_layers", _i32), ("reserved", _i32)]
 
 
+class HashNetT(_c.Structure):
+    _fields_ = [("n_levels", _i32), ("n_features_per_level", _i32), ("log2_hashmap_size", _i32),
+                ("base_resolution", _i32), ("per_level_scale", _f32), ("n_neurons", _i32),
+                ("n_hidden_layers", _i32), ("reserved", _i32)]
+
+
 _SIGS = {
     "loner_version": (_c.c_int, []),
     "loner_sm_arch": (_c.c_int, []),
@@ -35,6 +41,13 @@ _SIGS = {
     "loner_mlp_bwd": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
     "loner_mlp_dgrad": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _f32, _vp, _vp, _vp]),
     "loner_mlp_wgrad": (_c.c_int, [_vp, _vp, _i64, _vp, _vp, _f32, _vp, _vp, _vp]),
+    "loner_hash_param_count": (_i64, [_vp]),
+    "loner_hash_table_entries": (_i64, [_vp]),
+    "loner_hash_packed_bytes": (_i64, [_vp]),
+    "loner_hash_bwd_scratch_bytes": (_i64, [_vp, _i64]),
+    "loner_hash_pack": (_c.c_int, [_vp, _vp, _vp, _vp]),
+    "loner_hash_fwd": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp]),
+    "loner_hash_bwd": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _f32, _vp, _vp, _vp, _vp]),
     "loner_render_fwd": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _f32, _u64, _vp, _vp, _vp, _vp, _vp]),
     "loner_render_bwd": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _f32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "loner_render_loss": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _f32, _u64, _vp, _vp, _vp,

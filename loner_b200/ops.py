@@ -47,6 +47,66 @@ class Net:
         return s
 
 
+class HashNet:
+    """The reference's shipped sigma head: multiresolution hash encoding + 1 x 64 MLP
+    (cfg/nerf_config/default_nerf_hash.yaml `pos_encoding_sigma` / `sigma_network`, models/nerf_tcnn.py:35-38).
+    Flat fp32 params in tcnn's order: W1 [64, e_pad] | W_out [16, 64] | table [entries, 2]."""
+
+    def __init__(self, n_levels=16, n_features_per_level=2, log2_hashmap_size=18, base_resolution=16,
+                 per_level_scale=2.0, n_neurons=64, n_hidden_layers=1):
+        self.c = L.HashNetT(int(n_levels), int(n_features_per_level), int(log2_hashmap_size), int(base_resolution),
+                            float(per_level_scale), int(n_neurons), int(n_hidden_layers), 0)
+        lib = L.load()
+        self.param_count = lib.loner_hash_param_count(ctypes.byref(self.c))
+        if self.param_count < 0:
+            raise RuntimeError(f"unsupported hash-grid sigma network {n_levels=} {n_features_per_level=} "
+                               f"{log2_hashmap_size=} {n_neurons=} {n_hidden_layers=} (kernels implement <=16 levels "
+                               "x 2 features, one hidden layer of 64 neurons)")
+        self.n_levels, self.n_neurons, self.n_hidden_layers = int(n_levels), int(n_neurons), int(n_hidden_layers)
+        self.e_pad = (2 * self.n_levels + 15) // 16 * 16
+        self.table_entries = lib.loner_hash_table_entries(ctypes.byref(self.c))
+        self.packed_bytes = lib.loner_hash_packed_bytes(ctypes.byref(self.c))
+        self.n_network_params = self.n_neurons * self.e_pad + 16 * self.n_neurons
+
+    def ref(self):
+        return ctypes.byref(self.c)
+
+    def bwd_scratch_bytes(self, P):
+        return L.load().loner_hash_bwd_scratch_bytes(self.ref(), P)
+
+    def layer_shapes(self):
+        return [(self.n_neurons, self.e_pad), (16, self.n_neurons)]
+
+
+def hash_pack(net: HashNet, params, packed=None):
+    if packed is None:
+        packed = torch.empty(net.packed_bytes, device=params.device, dtype=torch.uint8)
+    L.check(L.load().loner_hash_pack(net.ref(), L.ptr(_f32(params)), L.ptr(packed), L.stream_ptr()), "loner_hash_pack")
+    return packed
+
+
+def hash_fwd(net: HashNet, packed, P, pos=None, rays=None, z=None, sigma=None):
+    if sigma is None:
+        sigma = torch.empty(P, device=packed.device, dtype=torch.float32)
+    S = z.shape[1] if z is not None else 1
+    L.check(L.load().loner_hash_fwd(net.ref(), L.ptr(packed), L.ptr(pos), L.ptr(rays), L.ptr(z), S, P, L.ptr(sigma),
+                                    L.stream_ptr()), "loner_hash_fwd")
+    return sigma
+
+
+def hash_bwd(net: HashNet, packed, P, d_sigma, grad_scale, d_params, pos=None, rays=None, z=None, want_dpos=False,
+             scratch=None):
+    dev = packed.device
+    if scratch is None:
+        scratch = torch.empty(max(net.bwd_scratch_bytes(P), 16), device=dev, dtype=torch.uint8)
+    d_pos = torch.empty(P, 3, device=dev, dtype=torch.float32) if want_dpos else None
+    S = z.shape[1] if z is not None else 1
+    L.check(L.load().loner_hash_bwd(net.ref(), L.ptr(packed), L.ptr(pos), L.ptr(rays), L.ptr(z), S, P,
+                                    L.ptr(_f32(d_sigma)), float(grad_scale), L.ptr(d_params), L.ptr(d_pos),
+                                    L.ptr(scratch), L.stream_ptr()), "loner_hash_bwd")
+    return d_pos
+
+
 def pack_points(ray_directions, distances):
     """[3,M] + [M] -> [M,4] float4 rows (dx,dy,dz,dist): one 16-byte load per picked ray."""
     return torch.cat([ray_directions.t(), distances[:, None]], dim=1).contiguous().float()

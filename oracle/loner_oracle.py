@@ -17,7 +17,7 @@ from dataclasses import dataclass, field
 import torch
 import torch.nn.functional as F
 
-from . import p3d_standin, tcnn_standin
+from . import hashgrid_standin, p3d_standin, tcnn_standin
 
 
 # ----------------------------------------------------------------------------- poses / rays
@@ -116,27 +116,41 @@ def ogm_samples(rays, grid, S, perturb, u1, u2):
 # ----------------------------------------------------------------------------- network
 @dataclass
 class NetSpec:
-    """Sigma head: Frequency encoding + bias-free ReLU MLP (models/nerf_tcnn.py:35-38)."""
+    """Sigma head (models/nerf_tcnn.py:35-38): Frequency encoding + bias-free ReLU MLP, or - `hash` given -
+    the shipped configuration, multiresolution hash encoding + MLP (cfg/nerf_config/default_nerf_hash.yaml).
+    Flat params in tcnn's order: network matrices, then the hash table."""
     n_frequencies: int = 10
     n_neurons: int = 256
     n_hidden_layers: int = 4
     precision: str = "fp16"
+    hash: object = None            # oracle.hashgrid_standin.HashGridSpec or None
     shapes: list = field(init=False)
 
     def __post_init__(self):
-        e_pad = (3 * 2 * self.n_frequencies + 15) // 16 * 16
+        width = self.hash.n_output_dims if self.hash is not None else 3 * 2 * self.n_frequencies
+        e_pad = (width + 15) // 16 * 16
+        self.e_pad = e_pad
         self.shapes = tcnn_standin.mlp_layer_shapes(e_pad, self.n_neurons, self.n_hidden_layers, 16)
 
     @property
-    def n_params(self):
+    def n_network_params(self):
         return sum(a * b for a, b in self.shapes)
+
+    @property
+    def n_params(self):
+        return self.n_network_params + (self.hash.n_params if self.hash is not None else 0)
 
 
 def sigma_net(pos, params, spec: NetSpec):
     """models/nerf_tcnn.py:59-78 with sigma_only=True: pos in [-1,1] -> sigma [P]."""
     x = (pos + 1) / 2
-    enc = tcnn_standin.frequency_encode(x, spec.n_frequencies, pad_to=16)
-    out = tcnn_standin.mlp_forward(enc, params, spec.shapes, spec.precision)
+    if spec.hash is not None:
+        enc = hashgrid_standin.hashgrid_encode(x, params[spec.n_network_params:], spec.hash, spec.precision)
+        if enc.shape[1] < spec.e_pad:
+            enc = torch.cat([enc, torch.ones(enc.shape[0], spec.e_pad - enc.shape[1])], dim=1)
+    else:
+        enc = tcnn_standin.frequency_encode(x, spec.n_frequencies, pad_to=16)
+    out = tcnn_standin.mlp_forward(enc, params[:spec.n_network_params], spec.shapes, spec.precision)
     sigma = out[:, 0]
     finfo = torch.finfo(torch.float16)
     if not torch.isfinite(sigma).all():

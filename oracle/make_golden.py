@@ -24,7 +24,7 @@ sys.path.insert(0, REPO)
 
 from loner_b200 import synth  # noqa: E402
 from oracle import ref_harness as rh  # noqa: E402
-from oracle import tcnn_standin  # noqa: E402
+from oracle import hashgrid_standin, tcnn_standin  # noqa: E402
 
 GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
 
@@ -39,7 +39,12 @@ CASES = {
     "kf2_2x128_l2js": dict(geom="garden", K=2, n=128, S=128, L=2, W=128, grid="trained", prec="fp16", poses=True, rows=64, loss="L2_JS"),
     "kf2_2x128_l1los": dict(geom="garden", K=2, n=128, S=128, L=2, W=128, grid="trained", prec="fp16", poses=True, rows=64, loss="L1_LOS"),
     "quad_4x256_fp16": dict(geom="quad", K=2, n=128, S=512, L=4, W=256, grid="trained", prec="fp16", poses=True, rows=32),
+    # the reference's SHIPPED sigma head (cfg/nerf_config/default_nerf_hash.yaml): HashGrid + 1 x 64, with a
+    # smaller table (2^14 entries per level) to keep the fixture's regeneration and the oracle run cheap
+    "hash_1x64_fp16": dict(geom="canteen", K=2, n=128, S=128, L=1, W=64, grid="trained", prec="fp16", poses=True, rows=64,
+                           hash=dict(n_levels=16, n_features_per_level=2, log2_hashmap_size=14, base_resolution=16)),
 }
+TABLE_SEED, TABLE_SCALE = 4242, 0.5
 N_BEAMS, N_AZ = 16, 256   # 4,096-point scans keep the fixtures' regeneration cheap
 
 
@@ -54,7 +59,7 @@ def case_randoms(seed, n_per_kf, K, M, n_rays, S):
     return idx, u1, u2, noise
 
 
-def build_reference_optimizer(ns, geom, S, L, W, tmpdir, loss="L1_JS"):
+def build_reference_optimizer(ns, geom, S, L, W, tmpdir, loss="L1_JS", hash_cfg=None):
     s = rh.load_settings()
     g = synth.GEOMETRY[geom]
     opt_s = s["mapper"]["optimizer"]
@@ -65,6 +70,8 @@ def build_reference_optimizer(ns, geom, S, L, W, tmpdir, loss="L1_JS"):
     mc["loss"]["loss_selection"] = loss
     nc = mc["model"]["nerf_config"]
     nc["pos_encoding_sigma"] = {"otype": "Frequency", "n_frequencies": 10}
+    if hash_cfg is not None:
+        nc["pos_encoding_sigma"] = dict(otype="HashGrid", **hash_cfg)
     nc["sigma_network"] = {"otype": "CutlassMLP" if W > 128 else "FullyFusedMLP", "activation": "ReLU",
                            "output_activation": "None", "n_neurons": W, "n_hidden_layers": L}
     opt_s["debug"] = s["debug"]["flags"]
@@ -80,7 +87,12 @@ def run_case(name, c, seed=1234):
     tcnn_standin.PRECISION["mode"] = c["prec"]
     torch.manual_seed(0)
     with tempfile.TemporaryDirectory() as tmp:
-        opt, wc, settings = build_reference_optimizer(ns, c["geom"], c["S"], c["L"], c["W"], tmp, c.get("loss", "L1_JS"))
+        opt, wc, settings = build_reference_optimizer(ns, c["geom"], c["S"], c["L"], c["W"], tmp, c.get("loss", "L1_JS"),
+                                                      c.get("hash"))
+        if c.get("hash"):
+            sig = opt._model.nerf_model._model_sigma
+            with torch.no_grad():
+                sig.params[sig.n_network_params:] = hashgrid_standin.init_table(sig.encoding.hash_spec, TABLE_SEED, TABLE_SCALE)
         g = synth.GEOMETRY[c["geom"]]
         scans, poses = synth.make_window(c["geom"], c["K"], seed=7, n_beams=N_BEAMS, n_azimuth=N_AZ)
         M = scans[0].distances.shape[0]
@@ -135,6 +147,9 @@ def run_case(name, c, seed=1234):
             geom=np.array(c["geom"]), grid=np.array(c["grid"]), prec=np.array(c["prec"]),
             scale=np.float32(float(wc.scale_factor)), shift=wc.shift.numpy().astype(np.float32),
             params_seed=np.int64(1337), loss_selection=np.array(c.get("loss", "L1_JS")),
+            hash_cfg=np.array([c["hash"][k] for k in ("n_levels", "n_features_per_level", "log2_hashmap_size",
+                                                       "base_resolution")] if c.get("hash") else [], dtype=np.int64),
+            table_seed=np.int64(TABLE_SEED), table_scale=np.float32(TABLE_SCALE),
             rays=rays.detach().numpy(), depths=depths.numpy(),
             z_vals=res["samples_fine"][:rows].detach().numpy(),
             weights=res["weights_fine"][:rows].detach().numpy(),

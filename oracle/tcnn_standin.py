@@ -26,6 +26,11 @@ import math
 import torch
 import torch.nn as nn
 
+try:                                   # imported as oracle.tcnn_standin or, by the reference harness, top-level
+    from . import hashgrid_standin
+except ImportError:                    # pragma: no cover
+    import hashgrid_standin
+
 PRECISION = {"mode": "fp32"}   # module-level switch used by the reference harness
 
 
@@ -71,7 +76,8 @@ class Encoding(nn.Module):
             self.n_frequencies = int(self.cfg.get("n_frequencies", 10))
             self.n_output_dims = n_input_dims * 2 * self.n_frequencies
         elif ot == "HashGrid":
-            self.n_output_dims = int(self.cfg["n_levels"]) * int(self.cfg["n_features_per_level"])
+            self.hash_spec = hashgrid_standin.HashGridSpec.from_config(self.cfg)
+            self.n_output_dims = self.hash_spec.n_output_dims
         elif ot == "SphericalHarmonics":
             self.n_output_dims = int(self.cfg["degree"]) ** 2
         else:
@@ -83,6 +89,8 @@ class Encoding(nn.Module):
     def forward(self, x):
         if self.otype == "Frequency":
             return frequency_encode(x.float(), self.n_frequencies, pad_to=1)
+        # stand-alone HashGrid / SphericalHarmonics encodings only feed the frozen intensity head, whose
+        # output the LiDAR-only path discards (nerf_tcnn.py:64): zeros of the right width
         return torch.zeros(x.shape[0], self.n_output_dims, dtype=torch.float32, device=x.device)
 
 
@@ -146,9 +154,8 @@ class NetworkWithInputEncoding(nn.Module):
     def __init__(self, n_input_dims, n_output_dims, encoding_config, network_config, seed=1337):
         super().__init__()
         self.encoding = Encoding(n_input_dims, encoding_config)
-        if self.encoding.otype != "Frequency":
-            raise NotImplementedError(
-                "tcnn stand-in: sigma-head encoding must be Frequency (HashGrid is a 'next' row, SURVEY 8f)")
+        if self.encoding.otype not in ("Frequency", "HashGrid"):
+            raise NotImplementedError("tcnn stand-in: sigma-head encoding must be Frequency or HashGrid")
         cfg = dict(network_config)
         self.n_input_dims = n_input_dims
         self.n_output_dims = n_output_dims
@@ -157,10 +164,20 @@ class NetworkWithInputEncoding(nn.Module):
         self.in_padded = _pad16(self.encoding.n_output_dims)
         self.out_padded = _pad16(n_output_dims)
         self.shapes = mlp_layer_shapes(self.in_padded, self.n_neurons, self.n_hidden_layers, self.out_padded)
-        self.params = nn.Parameter(xavier_uniform_flat(self.shapes, seed))
+        flat = xavier_uniform_flat(self.shapes, seed)
+        self.n_network_params = flat.numel()
+        if self.encoding.otype == "HashGrid":       # tcnn order: network parameters, then the encoding's table
+            flat = torch.cat([flat, hashgrid_standin.init_table(self.encoding.hash_spec, seed + 1)])
+        self.params = nn.Parameter(flat)
         self.dtype = torch.float16
 
     def forward(self, x):
-        enc = frequency_encode(x.float(), self.encoding.n_frequencies, pad_to=16)
-        out = mlp_forward(enc, self.params, self.shapes, PRECISION["mode"])
+        if self.encoding.otype == "HashGrid":
+            enc = hashgrid_standin.hashgrid_encode(x.float(), self.params[self.n_network_params:],
+                                                   self.encoding.hash_spec, PRECISION["mode"])
+            if enc.shape[1] < self.in_padded:
+                enc = torch.cat([enc, torch.ones(enc.shape[0], self.in_padded - enc.shape[1])], dim=1)
+        else:
+            enc = frequency_encode(x.float(), self.encoding.n_frequencies, pad_to=16)
+        out = mlp_forward(enc, self.params[:self.n_network_params], self.shapes, PRECISION["mode"])
         return out[:, :self.n_output_dims]

@@ -12,6 +12,7 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 from loner_b200 import synth  # noqa: E402
+from oracle import hashgrid_standin  # noqa: E402
 from oracle import loner_oracle as orc  # noqa: E402
 from oracle import tcnn_standin  # noqa: E402
 
@@ -48,8 +49,16 @@ class Case:
         self.poses6 = [synth.axis_angle_from_yaw_pose(poses[k]) for k in range(K)]
         self.M = self.scans[0].distances.shape[0]
         self.idx, self.u1, self.u2, self.noise = case_randoms(seed, n, K, self.M, n_rays, S)
-        self.spec = orc.NetSpec(n_frequencies=10, n_neurons=W, n_hidden_layers=L, precision=self.prec)
+        self.hash_spec = None
+        if "hash_cfg" in self.g.files and self.g["hash_cfg"].size:      # the reference's shipped HashGrid sigma head
+            nl, nf, lt, br = [int(v) for v in self.g["hash_cfg"]]
+            self.hash_spec = hashgrid_standin.HashGridSpec(n_levels=nl, n_features_per_level=nf, log2_hashmap_size=lt,
+                                                           base_resolution=br)
+        self.spec = orc.NetSpec(n_frequencies=10, n_neurons=W, n_hidden_layers=L, precision=self.prec, hash=self.hash_spec)
         self.params = tcnn_standin.xavier_uniform_flat(self.spec.shapes, int(self.g["params_seed"]))
+        if self.hash_spec is not None:
+            self.params = torch.cat([self.params, hashgrid_standin.init_table(self.hash_spec, int(self.g["table_seed"]),
+                                                                              float(self.g["table_scale"]))])
         if str(self.g["grid"]) == "trained":
             self.grid = synth.trained_occupancy_grid(self.geom)
         else:
