@@ -79,8 +79,8 @@ class FusedOptimizer:
         m = mc.model
         nc = m.nerf_config
         enc, net = nc["pos_encoding_sigma"], nc["sigma_network"]
-        if enc["otype"] != "Frequency":
-            raise NotImplementedError("sigma-head encoding %r: only Frequency is implemented" % enc["otype"])
+        if enc["otype"] not in ("Frequency", "HashGrid"):
+            raise NotImplementedError("sigma-head encoding %r: Frequency and HashGrid are implemented" % enc["otype"])
         if mc.loss.loss_selection not in ("L1_JS", "L2_JS", "L1_LOS", "L2_LOS"):
             raise ValueError(f"Can't use unknown Loss {mc.loss.loss_selection}")
         if mc.loss.decay_los_lambda:
@@ -93,6 +93,9 @@ class FusedOptimizer:
         cfg = eng.EngineConfig(
             scale=float(world_cube.scale_factor), shift=tuple(float(x) for x in world_cube.shift),
             ray_range=tuple(float(x) for x in m.ray_range),
+            encoding=enc["otype"], n_levels=int(enc.get("n_levels", 16)),
+            log2_hashmap_size=int(enc.get("log2_hashmap_size", 18)), base_resolution=int(enc.get("base_resolution", 16)),
+            per_level_scale=float(enc.get("per_level_scale", 2.0)),
             n_frequencies=int(enc.get("n_frequencies", 10)), n_neurons=int(net["n_neurons"]),
             n_hidden_layers=int(net["n_hidden_layers"]), n_samples=int(m.render.N_samples_train),
             perturb=float(m.render.perturb), raw_noise_std=float(m.render.raw_noise_std), sampler=sampler,

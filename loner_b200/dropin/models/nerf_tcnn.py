@@ -1,6 +1,7 @@
 """models.nerf_tcnn of the reference (/root/reference/src/models/nerf_tcnn.py): DecoupledNeRF with the
-sigma head on the hand-written sm_100a kernels (loner_mlp_fwd / loner_mlp_bwd).  Driven by the same
-`nerf_config` keys (nerf_tcnn.py:29-33).  The intensity head exists only as frozen empty modules:
+sigma head on the hand-written sm_100a kernels: Frequency + MLP on the tensor cores (loner_mlp_fwd /
+loner_mlp_bwd) or the shipped HashGrid + 1 x 64 configuration (loner_hash_fwd / loner_hash_bwd).  Driven by
+the same `nerf_config` keys (nerf_tcnn.py:29-33).  The intensity head exists only as frozen empty modules:
 the reference never enables the camera (mapping/optimizer.py:433-434)."""
 import torch
 import torch.nn as nn
@@ -18,7 +19,7 @@ class _SigmaFn(torch.autograd.Function):
         packed = module.packed()
         need = params.requires_grad or pos.requires_grad
         posc = pos.detach().contiguous().float()
-        sigma, acts = ops.mlp_fwd(module.net, packed, P, pos=posc, stash=need)
+        sigma, acts = module.fwd(P, need, pos=posc)
         ctx.module, ctx.P, ctx.acts, ctx.pos = module, P, acts, posc
         ctx.want_dpos = pos.requires_grad
         return sigma.view(P, 1)
@@ -31,8 +32,7 @@ class _SigmaFn(torch.autograd.Function):
         scale = float(2.0 ** 12)
         gmax = g.abs().max()                      # loss scale: bring the largest gradient to ~2^4
         scale = float(torch.clamp(16.0 / (gmax + 1e-30), 1.0, 2.0 ** 24).log2().floor().exp2())
-        d_pos = ops.mlp_bwd(m.net, m.packed(), ctx.P, g, ctx.acts, scale, d_params, pos=ctx.pos,
-                            want_dpos=ctx.want_dpos)
+        d_pos = m.bwd(ctx.P, g, ctx.acts, scale, d_params, ctx.want_dpos, pos=ctx.pos)
         return d_pos, d_params, None
 
 
@@ -42,12 +42,22 @@ class SigmaNet(nn.Module):
     def __init__(self, encoding_config, network_config, seed=1337):
         super().__init__()
         enc = dict(encoding_config)
-        if enc.get("otype", "Frequency") != "Frequency":
-            raise NotImplementedError("sigma-head encoding otype=%r: only Frequency is implemented "
-                                      "(HashGrid is SURVEY.md 8f rank 1)" % enc.get("otype"))
         nw = dict(network_config)
-        self.net = ops.Net(int(enc.get("n_frequencies", 10)), int(nw["n_neurons"]), int(nw["n_hidden_layers"]))
-        self.params = nn.Parameter(_engine.xavier_uniform_flat(self.net.layer_shapes(), seed))
+        otype = enc.get("otype", "Frequency")
+        if otype not in ("Frequency", "HashGrid"):
+            raise NotImplementedError("sigma-head encoding otype=%r: Frequency and HashGrid are implemented" % otype)
+        self.hash = otype == "HashGrid"
+        if self.hash:
+            self.net = ops.HashNet(int(enc["n_levels"]), int(enc["n_features_per_level"]), int(enc["log2_hashmap_size"]),
+                                   int(enc["base_resolution"]), float(enc.get("per_level_scale", 2.0)),
+                                   int(nw["n_neurons"]), int(nw["n_hidden_layers"]))
+            flat = _engine.xavier_uniform_flat(self.net.layer_shapes(), seed)
+            g = torch.Generator().manual_seed(seed + 1)      # tcnn: table ~ U(-1e-4, 1e-4), after the network matrices
+            flat = torch.cat([flat, (torch.rand(2 * self.net.table_entries, generator=g) * 2 - 1) * 1e-4])
+        else:
+            self.net = ops.Net(int(enc.get("n_frequencies", 10)), int(nw["n_neurons"]), int(nw["n_hidden_layers"]))
+            flat = _engine.xavier_uniform_flat(self.net.layer_shapes(), seed)
+        self.params = nn.Parameter(flat)
         self.n_output_dims = 1
         self.dtype = torch.float16
         self._packed = None
@@ -55,9 +65,23 @@ class SigmaNet(nn.Module):
 
     def packed(self):
         if self._packed is None or self._packed_version != self.params._version or self._packed.device != self.params.device:
-            self._packed = ops.mlp_pack(self.net, self.params.detach())
+            pack = ops.hash_pack if self.hash else ops.mlp_pack
+            self._packed = pack(self.net, self.params.detach())
             self._packed_version = self.params._version
         return self._packed
+
+    def fwd(self, P, stash, pos=None, rays=None, z=None):
+        """-> (sigma [P], activation stash or None).  The hash-grid path never stashes: its backward recomputes."""
+        if self.hash:
+            return ops.hash_fwd(self.net, self.packed(), P, pos=pos, rays=rays, z=z), None
+        return ops.mlp_fwd(self.net, self.packed(), P, pos=pos, rays=rays, z=z, stash=stash)
+
+    def bwd(self, P, d_sigma, acts, scale, d_params, want_dpos, pos=None, rays=None, z=None):
+        if self.hash:
+            return ops.hash_bwd(self.net, self.packed(), P, d_sigma, scale, d_params, pos=pos, rays=rays, z=z,
+                                want_dpos=want_dpos)
+        return ops.mlp_bwd(self.net, self.packed(), P, d_sigma, acts, scale, d_params, pos=pos, rays=rays, z=z,
+                           want_dpos=want_dpos)
 
     def forward(self, pos01):
         """pos01 in [0,1] as tcnn receives it (nerf_tcnn.py:63); the kernel takes [-1,1]."""

@@ -41,7 +41,7 @@ class _RenderFn(torch.autograd.Function):
         n, S = z.shape
         r = rays.detach().contiguous().float()
         need = params.requires_grad or rays.requires_grad
-        sigma, acts = ops.mlp_fwd(sigma_module.net, sigma_module.packed(), n * S, rays=r, z=z, stash=need)
+        sigma, acts = sigma_module.fwd(n * S, need, rays=r, z=z)
         w, d, o, v = ops.render_fwd(sigma, z, r, noise=None, raw_noise_std=raw_noise_std, seed=seed)
         ctx.save_for_backward(r, z, sigma)
         ctx.m, ctx.acts, ctx.std, ctx.seed = sigma_module, acts, raw_noise_std, seed
@@ -58,8 +58,7 @@ class _RenderFn(torch.autograd.Function):
         d_params = torch.zeros_like(m.params)
         gmax = d_sigma.abs().max()
         scale = float(torch.clamp(16.0 / (gmax + 1e-30), 1.0, 2.0 ** 24).log2().floor().exp2())
-        d_pos = ops.mlp_bwd(m.net, m.packed(), n * S, d_sigma.view(-1), ctx.acts, scale, d_params, rays=r, z=z,
-                            want_dpos=ctx.want_rays)
+        d_pos = m.bwd(n * S, d_sigma.view(-1), ctx.acts, scale, d_params, ctx.want_rays, rays=r, z=z)
         if ctx.want_rays:
             ops.points_bwd(d_pos, z, d_rays)
         return (d_rays if ctx.want_rays else None), d_params, None, None, None, None

@@ -146,3 +146,36 @@ def test_hash_step_matches_reference_fixture():
     assert ep < 5e-2
     p_ref, _, _ = orc.adam_update(params0.cpu(), gp, torch.zeros_like(gp), torch.zeros_like(gp), 1, 0.01)
     assert relerr(e.params, p_ref) < 1e-6
+
+
+def test_dropin_decoupled_nerf_with_the_shipped_config():
+    """models.nerf_tcnn.DecoupledNeRF built from the reference's default nerf_config keys (HashGrid + 1 x 64):
+    forward and autograd backward through loner_hash_fwd / loner_hash_bwd against the oracle."""
+    from loner_b200.dropin.models import nerf_tcnn
+    cfg = dict(enable_view_dependence=True,
+               pos_encoding_sigma=dict(otype="HashGrid", n_levels=16, n_features_per_level=2, log2_hashmap_size=14,
+                                       base_resolution=16),
+               sigma_network=dict(otype="FullyFusedMLP", activation="ReLU", output_activation="None", n_neurons=64,
+                                  n_hidden_layers=1))
+    model = nerf_tcnn.DecoupledNeRF(cfg).cuda()
+    sm = model._model_sigma
+    hs = H.HashGridSpec(n_levels=16, log2_hashmap_size=14)
+    spec = orc.NetSpec(n_neurons=64, n_hidden_layers=1, precision="fp16", hash=hs)
+    assert sm.params.numel() == spec.n_params
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():                       # O(1) table values instead of tcnn's 1e-4 initialisation
+        sm.params[spec.n_network_params:] = (torch.rand(hs.n_params, generator=g) - 0.5).cuda()
+    pos = torch.rand(1500, 3, generator=g) * 1.8 - 0.9
+    up = torch.randn(1500, 1, generator=g) * 1e-3
+    p_ref = sm.params.detach().cpu().clone().requires_grad_(True)
+    pos_ref = pos.clone().requires_grad_(True)
+    ref = orc.sigma_net(pos_ref, p_ref, spec)
+    (ref[:, None] * up).sum().backward()
+    posd = pos.cuda().requires_grad_(True)
+    out = model(posd, None, sigma_only=True)
+    assert out.shape == (1500, 1)
+    (out * up.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert norm_relerr(out[:, 0], ref) < 2e-3
+    assert norm_relerr(sm.params.grad, p_ref.grad) < 1e-2
+    assert norm_relerr(posd.grad, pos_ref.grad) < 2e-2
