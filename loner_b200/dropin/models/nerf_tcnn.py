@@ -11,12 +11,11 @@ from loner_b200 import ops
 
 
 class _SigmaFn(torch.autograd.Function):
-    """sigma = MLP(Frequency((pos + 1) / 2)) with a hand-rolled backward (params and positions)."""
+    """sigma = MLP(encoding((pos + 1) / 2)) with a hand-rolled backward (params and positions)."""
 
     @staticmethod
     def forward(ctx, pos, params, module):
         P = pos.shape[0]
-        packed = module.packed()
         need = params.requires_grad or pos.requires_grad
         posc = pos.detach().contiguous().float()
         sigma, acts = module.fwd(P, need, pos=posc)

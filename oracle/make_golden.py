@@ -44,23 +44,31 @@ CASES = {
     "hash_1x64_fp16": dict(geom="canteen", K=2, n=128, S=128, L=1, W=64, grid="trained", prec="fp16", poses=True, rows=64,
                            hash=dict(n_levels=16, n_features_per_level=2, log2_hashmap_size=14, base_resolution=16)),
 }
+CASES["kf2_2x128_uni_l2los"] = dict(geom="garden", K=2, n=128, S=128, L=2, W=128, grid="zeros", prec="fp16", poses=True,
+                                     rows=64, loss="L2_LOS", sampler="UNIFORM")   # the two branches no other case takes
 TABLE_SEED, TABLE_SCALE = 4242, 0.5
 N_BEAMS, N_AZ = 16, 256   # 4,096-point scans keep the fixtures' regeneration cheap
 
 
-def case_randoms(seed, n_per_kf, K, M, n_rays, S):
-    """The replayed random numbers, regenerable from `seed` alone (CPU torch generators)."""
+def case_randoms(seed, n_per_kf, K, M, n_rays, S, sampler="OGM"):
+    """The replayed random numbers, regenerable from `seed` alone (CPU torch generators).  The OGM sampler
+    draws two [n, S/2] uniforms (ray_sampling.py:71-72, rendering_tcnn.py:48), the uniform sampler one [n, S]
+    (ray_sampling.py:39)."""
     g = torch.Generator().manual_seed(seed)
     idx = [torch.randint(0, M, (n_per_kf,), generator=g) for _ in range(K)]
     g2 = torch.Generator().manual_seed(seed + 1)
+    if sampler == "UNIFORM":
+        u1 = torch.rand(n_rays, S, generator=g2)
+        return idx, u1, None, torch.randn(n_rays, S, generator=g2)
     u1 = torch.rand(n_rays, S // 2, generator=g2)
     u2 = torch.rand(n_rays, S // 2, generator=g2)
     noise = torch.randn(n_rays, S, generator=g2)
     return idx, u1, u2, noise
 
 
-def build_reference_optimizer(ns, geom, S, L, W, tmpdir, loss="L1_JS", hash_cfg=None):
+def build_reference_optimizer(ns, geom, S, L, W, tmpdir, loss="L1_JS", hash_cfg=None, sampler="OGM"):
     s = rh.load_settings()
+    s["mapper"]["optimizer"]["samples_selection"]["strategy"] = sampler
     g = synth.GEOMETRY[geom]
     opt_s = s["mapper"]["optimizer"]
     mc = opt_s["model_config"]
@@ -88,7 +96,7 @@ def run_case(name, c, seed=1234):
     torch.manual_seed(0)
     with tempfile.TemporaryDirectory() as tmp:
         opt, wc, settings = build_reference_optimizer(ns, c["geom"], c["S"], c["L"], c["W"], tmp, c.get("loss", "L1_JS"),
-                                                      c.get("hash"))
+                                                      c.get("hash"), c.get("sampler", "OGM"))
         if c.get("hash"):
             sig = opt._model.nerf_model._model_sigma
             with torch.no_grad():
@@ -115,7 +123,7 @@ def run_case(name, c, seed=1234):
             kfs.append(ns.keyframe.KeyFrame(fr, "cpu"))
         ray_range = torch.Tensor(list(g["ray_range"]))
         # pass 1 (no randomness needed): ray build, to learn the post-filter ray count
-        idx, _, _, _ = case_randoms(seed, c["n"], c["K"], M, 1, c["S"])
+        idx, _, _, _ = case_randoms(seed, c["n"], c["K"], M, 1, c["S"], c.get("sampler", "OGM"))
         rays_l, dep_l = [], []
         for kf, ix in zip(kfs, idx):
             r, d = kf.build_lidar_rays(ix, ray_range, wc, False)
@@ -124,9 +132,9 @@ def run_case(name, c, seed=1234):
         rays = torch.vstack(rays_l).float()
         depths = torch.cat(dep_l).float()
         n_rays = rays.shape[0]
-        idx, u1, u2, noise = case_randoms(seed, c["n"], c["K"], M, n_rays, c["S"])
+        idx, u1, u2, noise = case_randoms(seed, c["n"], c["K"], M, n_rays, c["S"], c.get("sampler", "OGM"))
         replay = rh.Replay()
-        replay.rand = [u1, u2]
+        replay.rand = [u1, u2] if u2 is not None else [u1]
         replay.randn = [noise]
         opt._optimization_settings.freeze_poses = not c["poses"]
         with rh.injected_randomness(replay):
@@ -135,10 +143,13 @@ def run_case(name, c, seed=1234):
         params = opt._model.nerf_model._model_sigma.params
         loss.backward()
         res = opt._results_lidar
-        grid_before = opt._occupancy_grid.detach().clone()
-        opt._step_occupancy_grid()
-        grid_after = opt._occupancy_grid.detach().clone()
-        dgrid = grid_after - grid_before
+        if c.get("sampler", "OGM") == "OGM":
+            grid_before = opt._occupancy_grid.detach().clone()
+            opt._step_occupancy_grid()
+            grid_after = opt._occupancy_grid.detach().clone()
+            dgrid = grid_after - grid_before
+        else:                       # no occupancy grid with the uniform sampler (optimizer.py:102-118, :382-384)
+            dgrid = torch.zeros(1, 1, 100, 100, 100)
         nz = dgrid.flatten().nonzero()[:, 0]
 
         rows = min(c["rows"], n_rays)
@@ -150,6 +161,7 @@ def run_case(name, c, seed=1234):
             hash_cfg=np.array([c["hash"][k] for k in ("n_levels", "n_features_per_level", "log2_hashmap_size",
                                                        "base_resolution")] if c.get("hash") else [], dtype=np.int64),
             table_seed=np.int64(TABLE_SEED), table_scale=np.float32(TABLE_SCALE),
+            sampler=np.array(c.get("sampler", "OGM")),
             rays=rays.detach().numpy(), depths=depths.numpy(),
             z_vals=res["samples_fine"][:rows].detach().numpy(),
             weights=res["weights_fine"][:rows].detach().numpy(),

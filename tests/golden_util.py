@@ -23,11 +23,14 @@ def golden_names():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
 
 
-def case_randoms(seed, n_per_kf, K, M, n_rays, S):
+def case_randoms(seed, n_per_kf, K, M, n_rays, S, sampler="OGM"):
     """Same generator protocol as oracle/make_golden.py::case_randoms."""
     g = torch.Generator().manual_seed(seed)
     idx = [torch.randint(0, M, (n_per_kf,), generator=g) for _ in range(K)]
     g2 = torch.Generator().manual_seed(seed + 1)
+    if sampler == "UNIFORM":
+        u1 = torch.rand(n_rays, S, generator=g2)
+        return idx, u1, None, torch.randn(n_rays, S, generator=g2)
     u1 = torch.rand(n_rays, S // 2, generator=g2)
     u2 = torch.rand(n_rays, S // 2, generator=g2)
     noise = torch.randn(n_rays, S, generator=g2)
@@ -48,7 +51,8 @@ class Case:
         self.scans, poses = synth.make_window(self.geom, K, seed=7, n_beams=nb, n_azimuth=naz)
         self.poses6 = [synth.axis_angle_from_yaw_pose(poses[k]) for k in range(K)]
         self.M = self.scans[0].distances.shape[0]
-        self.idx, self.u1, self.u2, self.noise = case_randoms(seed, n, K, self.M, n_rays, S)
+        self.sampler = str(self.g["sampler"]) if "sampler" in self.g.files else "OGM"
+        self.idx, self.u1, self.u2, self.noise = case_randoms(seed, n, K, self.M, n_rays, S, self.sampler)
         self.hash_spec = None
         if "hash_cfg" in self.g.files and self.g["hash_cfg"].size:      # the reference's shipped HashGrid sigma head
             nl, nf, lt, br = [int(v) for v in self.g["hash_cfg"]]
@@ -73,10 +77,11 @@ class Case:
         poses6 = [p.clone().requires_grad_(self.pose_grads and k > 0) for k, p in enumerate(self.poses6)]
         rays, depths, res, out = orc.mapping_iteration(
             self.scans, poses6, self.idx, params, self.spec, self.grid, self.S, self.scale, self.shift,
-            self.ray_range, 1.0, self.u1, self.u2, self.noise, self.loss_cfg)
+            self.ray_range, 1.0, self.u1, self.u2, self.noise, self.loss_cfg, sampler=self.sampler)
         out["loss"].backward()
         s = res["samples_fine"].detach() * self.scale
         G = depths.reshape(-1, 1) * self.scale
-        grid_after = orc.occupancy_step(self.grid, res["points_fine"], s, G, 1e-4)
+        # the occupancy grid only exists (and is only stepped) with the OGM sampler   optimizer.py:102-118,382-384
+        grid_after = orc.occupancy_step(self.grid, res["points_fine"], s, G, 1e-4) if self.sampler == "OGM" else self.grid
         return dict(rays=rays, depths=depths, res=res, out=out, params=params, poses6=poses6,
                     grid_after=grid_after)

@@ -40,4 +40,5 @@ def test_oracle_matches_reference_fixture(name):
     d = (r["grid_after"] - c.grid).flatten()
     assert abs(float(d.double().sum()) - float(g["ogm_delta_sum"])) <= 1e-5 * float(g["ogm_delta_abs"]) + 1e-9
     idx = torch.from_numpy(g["ogm_delta_idx"])
-    assert rel(d[idx], g["ogm_delta_val"]) < 1e-4
+    if idx.numel():                      # empty with the uniform sampler: no occupancy grid is kept or stepped
+        assert rel(d[idx], g["ogm_delta_val"]) < 1e-4
