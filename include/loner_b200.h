@@ -29,10 +29,32 @@ enum {
 #define LONER_RAY_COLS 13
 #define LONER_FLAG_VALID 1u   /* far > near + 1/scale           (ray_utils.py:321) */
 #define LONER_FLAG_OPAQUE 2u  /* depth > 0 and not depth > far  (optimizer.py:460-463) */
+/* ray_kf[i] = keyframe row of `poses`, optionally OR-ed with LONER_KF_DETACHED: the ray is built from the
+ * detached pose (sky rays, mapping/keyframe.py:93-95) and loner_ray_build_bwd skips it. */
+#define LONER_KF_DETACHED 0x40000000
+#define LONER_KF_MASK 0x3FFFFFFF
 
 int loner_version(void);
 int loner_sm_arch(void); /* compute capability of the current device *10 + minor, e.g. 100 */
 const char* loner_error_string(int code);
+
+/* ---- a2  ray pick of the optimisation loop (mapping/optimizer.py:286-305): per keyframe
+ * `torch.randint(len(scan), (n,))` (RANDOM), picks among `scan.mask.nonzero()` (MASK), `arange(n)`
+ * (FIXED), and `num_samples.sky` picks among the keyframe's sky directions.  The output rays are
+ * a concatenation of segments; segment s fills rays [out_begin, next segment's out_begin). */
+enum { LONER_PICK_RANDOM = 0, LONER_PICK_FIXED = 1, LONER_PICK_MASK = 2 };
+typedef struct {
+  int32_t kf;        /* value written to ray_kf (keyframe row, | LONER_KF_DETACHED for sky segments) */
+  int32_t mode;      /* LONER_PICK_*                                                               */
+  int64_t base;      /* index in `points` of the segment's first candidate                         */
+  int64_t size;      /* number of candidates (points of the scan / sky set, or mask entries)       */
+  int64_t map_off;   /* MASK: offset of the scan's mask index list inside `index_map`              */
+  int64_t out_begin; /* first output ray of the segment                                            */
+} loner_pick_seg_t;
+/* segs: DEVICE array [n_segs] sorted by out_begin; index_map: device int64 (may be NULL without MASK);
+ * draws are Philox(seed, ray index).  Writes ray_kf [n] and ray_point [n] for loner_ray_build. */
+int loner_ray_pick(const loner_pick_seg_t* segs, int32_t n_segs, const int64_t* index_map, uint64_t seed,
+                   int64_t n, int32_t* ray_kf, int64_t* ray_point, void* stream);
 
 /* ---- a3/a4  LidarRayDirections.build_lidar_rays + get_far_val (common/ray_utils.py:269-322,
  * :31-60).  points: keyframe store, one float4 (dx,dy,dz,dist[m]) per LiDAR return, all
@@ -169,13 +191,12 @@ int loner_adam_step(float* params, const float* grads, float* exp_avg, float* ex
 
 /* ---- a19  Optimizer._step_occupancy_grid + get_logits_grad (mapping/optimizer.py:598-609,
  * models/losses.py:54-62): scatter the pseudo-gradient trilinearly into d_grid [V,V,V]
- * (caller zeroes), then loner_sgd_step applies grid -= lr * d_grid. */
-int loner_ogm_grad(const float* rays, const float* z_vals, const float* depths, int64_t n, int32_t S,
-                   float scale, int32_t V, float* d_grid, void* stream);
+ * (caller zeroes), then loner_sgd_step applies grid -= lr * d_grid.  flags (may be NULL): rows whose
+ * LONER_FLAG_VALID bit is clear were dropped by build_lidar_rays (ray_utils.py:321-322) and never reach
+ * `points_fine`; they are skipped. */
+int loner_ogm_grad(const float* rays, const float* z_vals, const float* depths, const uint8_t* flags,
+                   int64_t n, int32_t S, float scale, int32_t V, float* d_grid, void* stream);
 int loner_sgd_step(float* x, const float* g, int64_t count, float lr, void* stream);
-
-/* hardware probe (not on the product path): TMEM -> register bandwidth of tcgen05.ld */
-int loner_probe_tmem(int warps, int iters, int mode, long long* cycles, unsigned* sink, void* stream);
 
 #ifdef __cplusplus
 }

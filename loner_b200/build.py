@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libloner_b200.so")
-SOURCES = ["rays.cu", "sampler.cu", "render.cu", "mlp.cu", "hashgrid.cu", "optim.cu", "probe.cu"]
+SOURCES = ["rays.cu", "sampler.cu", "render.cu", "mlp.cu", "hashgrid.cu", "optim.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -49,6 +49,15 @@ def build(force=False, verbose=False):
     if verbose:
         print("\n".join(log))
     return LIB
+
+
+def build_probe():
+    """Hardware probes used while sizing the kernels (tests/gpu_probe.py); NOT part of the product library."""
+    src = os.path.join(HERE, "..", "tests", "probes", "probe_tmem.cu")
+    out = os.path.join(HERE, "..", "tests", "probes", "libloner_probe.so")
+    if not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out):
+        subprocess.check_call([NVCC] + FLAGS + ["-I", CSRC, "-shared", src, "-o", out, "-lcudart"])
+    return out
 
 
 if __name__ == "__main__":

@@ -26,26 +26,32 @@ using namespace sm100;
 constexpr int kTile = 128;            // samples per tile = UMMA M
 constexpr int kBlk = 16384;           // bytes of one [128 x 64] fp16 column block
 
+// W = width the kernels run at (128 or 256); Wr = the network's real width.  A 64-wide network
+// (tcnn FullyFusedMLP widths, BASELINE config 1) runs EXACTLY on the 128-wide kernels with its
+// matrices zero-padded: padded neurons output relu(0) = 0, their mask bits are 0, and every padded
+// weight gradient is a product with one of those zeros; only pack / reduce know the real layout.
 struct Net {
-  int F, E, Epad, W, L, nb;
+  int F, E, Epad, W, L, nb, Wr;
 };
 
 __host__ inline bool net_from(const loner_net_t* n, Net& o) {
   if (!n) return false;
-  o.F = n->n_frequencies; o.W = n->n_neurons; o.L = n->n_hidden_layers;
+  o.F = n->n_frequencies; o.Wr = n->n_neurons; o.L = n->n_hidden_layers;
   if (o.F < 1 || o.F > 10) return false;
-  if (!(o.W == 128 || o.W == 256)) return false;
+  if (!(o.Wr == 64 || o.Wr == 128 || o.Wr == 256)) return false;
   if (o.L < 1 || o.L > 8) return false;
+  o.W = o.Wr == 64 ? 128 : o.Wr;
   o.E = 6 * o.F; o.Epad = (o.E + 15) / 16 * 16; o.nb = o.W / 64;
   return true;
 }
 __host__ __device__ inline int layer_K(const Net& n, int l) { return l == 0 ? n.Epad : n.W; }
+__host__ __device__ inline int layer_Kr(const Net& n, int l) { return l == 0 ? n.Epad : n.Wr; }   // real in-features
 __host__ __device__ inline int64_t packed_off(const Net& n, int l) {      // byte offset of layer l's image
   return l == 0 ? 0 : (int64_t)n.Epad * n.W * 2 + (int64_t)(l - 1) * n.W * n.W * 2;
 }
 __host__ __device__ inline int64_t packed_wout_off(const Net& n) { return packed_off(n, n.L); }
-__host__ __device__ inline int64_t param_off(const Net& n, int l) {       // float offset in flat params
-  return l == 0 ? 0 : (int64_t)n.Epad * n.W + (int64_t)(l - 1) * n.W * n.W;
+__host__ __device__ inline int64_t param_off(const Net& n, int l) {       // float offset in flat params (real layout)
+  return l == 0 ? 0 : (int64_t)n.Epad * n.Wr + (int64_t)(l - 1) * n.Wr * n.Wr;
 }
 __host__ __device__ inline int64_t act_tile_bytes(const Net& n) { return (int64_t)kBlk * (1 + n.L * n.nb); }
 __host__ __device__ inline int64_t mask_tile_bytes(const Net& n) { return (int64_t)n.L * kTile * (n.W / 32) * 4; }
@@ -71,11 +77,13 @@ __global__ void pack_kernel(Net net, const float* __restrict__ params, uint8_t* 
     float* wo = (float*)(packed + packed_wout_off(net));
     const float* src = params + param_off(net, net.L);
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < net.W; j += gridDim.x * blockDim.x)
-      wo[j] = __half2float(__float2half_rn(src[j]));
+      wo[j] = j < net.Wr ? __half2float(__float2half_rn(src[j])) : 0.f;
     return;
   }
   const int K = layer_K(net, l), N = net.W;
+  const int Kr = layer_Kr(net, l), Nr = net.Wr;
   const float* Wm = params + param_off(net, l);
+  auto wv = [&](int n, int k) { return (n < Nr && k < Kr) ? Wm[(int64_t)n * Kr + k] : 0.f; };
   uint8_t* img_b = packed + packed_off(net, l);
   uint8_t* img_f = packed + packed_fwd_base(net) + fwd_off(net, l);
   const int chunks = K * (N / 8);
@@ -84,7 +92,7 @@ __global__ void pack_kernel(Net net, const float* __restrict__ params, uint8_t* 
     __half2 h[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      h[i] = __floats2half2_rn(Wm[(int64_t)(n0 + 2 * i) * K + k], Wm[(int64_t)(n0 + 2 * i + 1) * K + k]);
+      h[i] = __floats2half2_rn(wv(n0 + 2 * i, k), wv(n0 + 2 * i + 1, k));
     const int cb = n0 / 64, j = (n0 % 64) / 8;
     const int sw = (j ^ (k & 7)) * 16;
     *reinterpret_cast<uint4*>(img_b + (int64_t)cb * K * 128 + (int64_t)k * 128 + sw) = *reinterpret_cast<uint4*>(h);
@@ -976,14 +984,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
 __global__ void wgrad_reduce_kernel(Net net, const float* __restrict__ partials, WgradArgs w, float inv_gscale,
                                     float* __restrict__ d_params) {
   const int l = blockIdx.y;
-  const int K = layer_K(net, l);
+  const int K = layer_K(net, l), Kr = layer_Kr(net, l);
   const int64_t sz = (int64_t)K * net.W;
   const int n_items = w.item_begin[l + 1] - w.item_begin[l];
   const float* p = partials + w.part_off[l];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sz; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / K), k = (int)(i % K);         // partials are [out n][in k] at the kernel width
+    if (n >= net.Wr || k >= Kr) continue;                 // zero-padded part of a 64-wide network
     float s = 0.f;
     for (int g = 0; g < n_items; ++g) s += p[(int64_t)g * sz + i];
-    d_params[param_off(net, l) + i] += s * inv_gscale;
+    d_params[param_off(net, l) + (int64_t)n * Kr + k] += s * inv_gscale;
   }
 }
 
@@ -1038,7 +1048,7 @@ __global__ void __launch_bounds__(256) dwout_kernel(Net net, const uint8_t* __re
       if (rsub == 0 && cb < net.nb) atomicAdd(&red[cb * 64 + j * 8 + i], v);
     }
   __syncthreads();
-  for (int c = threadIdx.x; c < net.W; c += blockDim.x)
+  for (int c = threadIdx.x; c < net.Wr; c += blockDim.x)
     if (red[c] != 0.f) atomicAdd(d_params + param_off(net, net.L) + c, red[c]);
 }
 
@@ -1092,7 +1102,7 @@ using namespace loner::mlp;
 extern "C" int64_t loner_mlp_param_count(const loner_net_t* n) {
   Net net;
   if (!net_from(n, net)) return -1;
-  return param_off(net, net.L) + 16 * (int64_t)net.W;
+  return param_off(net, net.L) + 16 * (int64_t)net.Wr;
 }
 extern "C" int64_t loner_mlp_packed_bytes(const loner_net_t* n) {
   Net net;

@@ -19,7 +19,7 @@ ray_build_kernel(const float4* __restrict__ points, const int32_t* __restrict__ 
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int valid = 0, opaque = 0;
   if (i < n) {
-    const int kf = ray_kf[i];
+    const int kf = ray_kf[i] & LONER_KF_MASK;
     const float4 p = __ldg(points + ray_point[i]);
     const float* P = poses + (int64_t)kf * 12;
     // origin = (t + shift) / scale                         ray_utils.py:282-284
@@ -68,6 +68,31 @@ ray_build_kernel(const float4* __restrict__ points, const int32_t* __restrict__ 
   }
 }
 
+// Ray pick (optimizer.py:286-305): every output ray belongs to one segment = (keyframe, lidar | sky);
+// RANDOM draws torch.randint(size) with Philox, MASK draws among the scan mask's index list, FIXED is
+// arange.  One launch for the whole window instead of ~25 ATen micro-kernels.
+__global__ void __launch_bounds__(256)
+ray_pick_kernel(const loner_pick_seg_t* __restrict__ segs, int n_segs, const int64_t* __restrict__ index_map,
+                uint64_t seed, int64_t n, int32_t* __restrict__ ray_kf, int64_t* __restrict__ ray_point) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int s = 0;
+  while (s + 1 < n_segs && i >= segs[s + 1].out_begin) ++s;
+  const loner_pick_seg_t sg = segs[s];
+  const int64_t j = i - sg.out_begin;
+  int64_t pick;
+  if (sg.mode == LONER_PICK_FIXED) {
+    pick = j;
+  } else {
+    const uint4 q = Philox(seed)((uint64_t)i, 4u);
+    const uint64_t r = ((uint64_t)q.x << 32) | q.y;
+    pick = (int64_t)__umul64hi(r, (uint64_t)sg.size);                 // uniform over [0, size)
+  }
+  if (sg.mode == LONER_PICK_MASK) pick = index_map[sg.map_off + pick];
+  ray_kf[i] = sg.kf;
+  ray_point[i] = sg.base + pick;
+}
+
 // Backward w.r.t. the pose (R,t): do -> dt / scale; dd -> through the normalisation -> dR.
 // One block reduces its rays per keyframe in shared memory, then one atomic per (kf, entry).
 __global__ void __launch_bounds__(256)
@@ -79,8 +104,9 @@ ray_build_bwd_kernel(const float4* __restrict__ points, const int32_t* __restric
   for (int j = threadIdx.x; j < K * 12; j += blockDim.x) acc[j] = 0.f;
   __syncthreads();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const int kf = ray_kf[i];
+  // sky rays are built from the DETACHED pose (keyframe.py:93-95): no pose gradient through them
+  if (i < n && !(ray_kf[i] & LONER_KF_DETACHED)) {
+    const int kf = ray_kf[i] & LONER_KF_MASK;
     const float4 p = __ldg(points + ray_point[i]);
     const float* P = poses + (int64_t)kf * 12;
     const float* g = d_rays + i * LONER_RAY_COLS;
@@ -166,6 +192,16 @@ extern "C" int loner_ray_build(const void* points, const int32_t* ray_kf, const 
   loner::ray_build_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
       (const float4*)points, ray_kf, ray_point, n, poses, shift3_host[0], shift3_host[1], shift3_host[2], scale,
       r0, r1, rays, depths, flags, counters);
+  LONER_CHECK_LAUNCH();
+  return LONER_OK;
+}
+
+extern "C" int loner_ray_pick(const loner_pick_seg_t* segs, int32_t n_segs, const int64_t* index_map, uint64_t seed,
+                              int64_t n, int32_t* ray_kf, int64_t* ray_point, void* stream) {
+  if (n == 0) return LONER_OK;
+  if (!segs || n_segs <= 0 || !ray_kf || !ray_point || n < 0) return LONER_E_BAD_ARG;
+  loner::ray_pick_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(segs, n_segs, index_map, seed, n,
+                                                                                    ray_kf, ray_point);
   LONER_CHECK_LAUNCH();
   return LONER_OK;
 }

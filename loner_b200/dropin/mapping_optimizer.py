@@ -40,26 +40,62 @@ class OptimizationSettings:
 
 
 class _ParamView(nn.Module):
-    """Checkpoint surface: `state_dict()` with the reference's key names."""
+    """Checkpoint surface: `state_dict()` with the reference's key names AND shapes, so that
+    `Model(...).load_state_dict(ckpt['network_state_dict'])` / `OccupancyGridModel(...).load_state_dict(
+    ckpt['occ_model_state_dict'])` of the analysis scripts (analysis/renderer_lidar.py:172-180,
+    compute_l1_depth.py:146-153) accept what Mapper.build_ckpt (mapping/mapper.py:161-175) saved."""
 
-    def __init__(self, key, tensor):
+    def __init__(self, key, tensor, shape=None):
         super().__init__()
         self._key, self._t = key, tensor
+        self._shape = tuple(shape) if shape is not None else tuple(tensor.shape)
 
     def state_dict(self, *a, **kw):
-        return {self._key: self._t.detach().clone()}
+        return {self._key: self._t.detach().clone().reshape(self._shape)}
 
     def load_state_dict(self, sd, strict=True):
-        self._t.copy_(sd[self._key].reshape(self._t.shape))
+        if strict and set(sd) != {self._key}:
+            raise RuntimeError(f"unexpected / missing keys in state_dict: {sorted(set(sd) ^ {self._key})}")
+        src = sd[self._key]
+        if src.numel() != self._t.numel():
+            raise RuntimeError(f"size mismatch for {self._key}: {tuple(src.shape)} vs {self._shape}")
+        self._t.copy_(src.reshape(self._t.shape))
 
 
-class _OptState:
+class _AdamState:
+    """`Optimizer._optimizer.state_dict()` in torch.optim.Adam's format (mapper.py:167): one param group for the
+    sigma network (state index 0), and the pose group of the current phase when poses are optimised."""
+
     def __init__(self, engine):
         self._e = engine
 
     def state_dict(self):
         e = self._e
-        return {"exp_avg": e.exp_avg.detach().clone(), "exp_avg_sq": e.exp_avg_sq.detach().clone(), "step": e.adam_t}
+        base = dict(betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, maximize=False, foreach=None,
+                    capturable=False, differentiable=False, fused=None)
+        state = {0: {"step": torch.tensor(float(e.adam_t)), "exp_avg": e.exp_avg.detach().clone(),
+                     "exp_avg_sq": e.exp_avg_sq.detach().clone()}}
+        groups = [dict(base, lr=e.cfg.lrate_sigma_mlp, params=[0])]
+        if e.pose_opt is not None:
+            sd = e.pose_opt.state_dict()
+            ids = sd["param_groups"][0]["params"]
+            for i in ids:
+                if i in sd["state"]:
+                    state[1 + i] = sd["state"][i]
+            groups.append(dict(base, lr=e.cfg.lrate_pose, params=[1 + i for i in ids]))
+        return {"state": state, "param_groups": groups}
+
+
+class _SgdState:
+    """`_occupancy_grid_optimizer.state_dict()`: torch.optim.SGD without momentum is stateless (optimizer.py:108-109)."""
+
+    def __init__(self, lr):
+        self._lr = lr
+
+    def state_dict(self):
+        return {"state": {}, "param_groups": [dict(lr=self._lr, momentum=0, dampening=0, weight_decay=0, nesterov=False,
+                                                   maximize=False, foreach=None, differentiable=False, fused=None,
+                                                   params=[0])]}
 
 
 class FusedOptimizer:
@@ -83,8 +119,6 @@ class FusedOptimizer:
             raise NotImplementedError("sigma-head encoding %r: Frequency and HashGrid are implemented" % enc["otype"])
         if mc.loss.loss_selection not in ("L1_JS", "L2_JS", "L1_LOS", "L2_LOS"):
             raise ValueError(f"Can't use unknown Loss {mc.loss.loss_selection}")
-        if mc.loss.decay_los_lambda:
-            raise NotImplementedError("decay_los_lambda (off in the reference defaults) is not fused")
         sampler = settings.samples_selection.strategy
         if sampler not in ("OGM", "UNIFORM"):
             raise RuntimeError(f"Can't find samples_selection strategy: {sampler}")
@@ -103,18 +137,26 @@ class FusedOptimizer:
             min_depth_eps=float(mc.loss.min_depth_eps), min_js=float(mc.loss.JS_loss.min_js_score),
             max_js=float(mc.loss.JS_loss.max_js_score), js_alpha=float(mc.loss.JS_loss.alpha),
             los_lambda=float(mc.loss.los_lambda), depthloss_lambda=float(mc.loss.depthloss_lambda),
+            decay_los_lambda=bool(mc.loss.get("decay_los_lambda", False)),
+            los_lambda_decay_rate=float(mc.loss.get("los_lambda_decay_rate", 0.999)),
+            los_lambda_decay_steps=float(mc.loss.get("los_lambda_decay_steps", 1)),
+            min_los_lambda=float(mc.loss.get("min_los_lambda", 100.0)),
             loss_selection=mc.loss.loss_selection, depth_eps=float(mc.loss.get("depth_eps", 3.0)),
             decay_depth_eps=bool(mc.loss.get("decay_depth_eps", True)),
             depth_eps_decay_rate=float(mc.loss.get("depth_eps_decay_rate", 0.95)),
             depth_eps_decay_steps=float(mc.loss.get("depth_eps_decay_steps", 1)),
             rays_selection=settings.rays_selection.strategy,
             lrate_sigma_mlp=float(mc.train.lrate_sigma_mlp), lrate_pose=float(mc.train.lrate_pose),
-            chunk_rays=min(int(m.render.chunk), 8192))
+            lrate_gamma=float(mc.train.get("lrate_gamma", 1.0)),
+            n_sky=int(settings.num_samples.get("sky", 0)) if enable_sky_segmentation else 0,
+            chunk_rays=int(m.render.chunk))
+        self._enable_sky_segmentation = enable_sky_segmentation
         self._engine = eng.MappingEngine(cfg, device=self._device)
+        V = cfg.voxel_size
         self._model = _ParamView("nerf_model._model_sigma.params", self._engine.params)
-        self._occupancy_grid_model = _ParamView("occupancy_grid", self._engine.grid)
-        self._optimizer = _OptState(self._engine)
-        self._occupancy_grid_optimizer = _OptState(self._engine)
+        self._occupancy_grid_model = _ParamView("occupancy_grid", self._engine.grid, shape=(1, 1, V, V, V))
+        self._optimizer = _AdamState(self._engine)
+        self._occupancy_grid_optimizer = _SgdState(cfg.occ_lr)
         self._keyframe_count = 0
         self._global_step = 0
         self._keyframe_schedule = settings["keyframe_schedule"]
@@ -135,15 +177,25 @@ class FusedOptimizer:
         self._keyframe_count += 1
         return result
 
+    def _pose_of(self, kf):
+        """KeyFrame.build_lidar_rays builds from the ground-truth pose when use_gt_poses is set (keyframe.py:82-85)."""
+        if self._use_gt_poses:
+            return kf._frame._gt_lidar_pose.get_pose_tensor()
+        return kf.get_lidar_pose().get_pose_tensor()
+
     def _register(self, kf):
-        k = self._kf_ids.get(id(kf))
-        if k is None:
+        # keyed by id(kf) with a strong reference held next to the slot, so an id cannot be recycled for another
+        # keyframe; like the reference's KeyFrameManager (keyframe_manager.py) keyframes are never dropped
+        entry = self._kf_ids.get(id(kf))
+        if entry is None:
             scan = kf.get_lidar_scan()
-            k = self._engine.add_keyframe(scan.ray_directions, scan.distances, kf.get_lidar_pose().get_pose_tensor(),
-                                          mask=getattr(scan, "mask", None))
-            self._kf_ids[id(kf)] = k
+            k = self._engine.add_keyframe(scan.ray_directions, scan.distances, self._pose_of(kf),
+                                          mask=getattr(scan, "mask", None),
+                                          sky_rays=getattr(scan, "sky_rays", None) if self._enable_sky_segmentation else None)
+            self._kf_ids[id(kf)] = (k, kf)
         else:   # the tracker / previous phases may have moved the pose
-            self._engine.poses6[k].data.copy_(kf.get_lidar_pose().get_pose_tensor().detach().to(self._device))
+            k = entry[0]
+            self._engine.poses6[k].data.copy_(self._pose_of(kf).detach().to(self._device))
             self._engine._pose_cache = None
         return k
 

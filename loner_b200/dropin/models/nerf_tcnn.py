@@ -10,6 +10,13 @@ from loner_b200 import engine as _engine
 from loner_b200 import ops
 
 
+def device_grad_scale(g):
+    """Power-of-two loss scale that brings the largest upstream gradient to ~2^4, as a DEVICE scalar: the
+    backward stays free of host synchronisation (the kernels take grad_scale = 1 and the pre-scaled gradient)."""
+    gmax = g.abs().max()
+    return torch.clamp(16.0 / (gmax + 1e-30), 1.0, 2.0 ** 24).log2().floor().exp2()
+
+
 class _SigmaFn(torch.autograd.Function):
     """sigma = MLP(encoding((pos + 1) / 2)) with a hand-rolled backward (params and positions)."""
 
@@ -28,10 +35,11 @@ class _SigmaFn(torch.autograd.Function):
         m = ctx.module
         d_params = torch.zeros_like(m.params)
         g = g.contiguous().view(-1).float()
-        scale = float(2.0 ** 12)
-        gmax = g.abs().max()                      # loss scale: bring the largest gradient to ~2^4
-        scale = float(torch.clamp(16.0 / (gmax + 1e-30), 1.0, 2.0 ** 24).log2().floor().exp2())
-        d_pos = m.bwd(ctx.P, g, ctx.acts, scale, d_params, ctx.want_dpos, pos=ctx.pos)
+        c = device_grad_scale(g)
+        d_pos = m.bwd(ctx.P, g * c, ctx.acts, 1.0, d_params, ctx.want_dpos, pos=ctx.pos)
+        d_params.div_(c)
+        if d_pos is not None:
+            d_pos.div_(c)
         return d_pos, d_params, None
 
 

@@ -5,6 +5,7 @@ loner_render_fwd, with loner_render_bwd -> loner_mlp_bwd -> loner_points_bwd as 
 import torch
 
 from loner_b200 import ops
+from models.nerf_tcnn import device_grad_scale
 
 
 def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5):
@@ -37,14 +38,14 @@ def inference(model, xyz_, dir_, sigma_only=False, netchunk=32768, detach_sigma=
 
 class _RenderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rays, params, z, sigma_module, raw_noise_std, seed):
+    def forward(ctx, rays, params, z, sigma_module, raw_noise_std, seed, noise):
         n, S = z.shape
         r = rays.detach().contiguous().float()
         need = params.requires_grad or rays.requires_grad
         sigma, acts = sigma_module.fwd(n * S, need, rays=r, z=z)
-        w, d, o, v = ops.render_fwd(sigma, z, r, noise=None, raw_noise_std=raw_noise_std, seed=seed)
+        w, d, o, v = ops.render_fwd(sigma, z, r, noise=noise, raw_noise_std=raw_noise_std, seed=seed)
         ctx.save_for_backward(r, z, sigma)
-        ctx.m, ctx.acts, ctx.std, ctx.seed = sigma_module, acts, raw_noise_std, seed
+        ctx.m, ctx.acts, ctx.std, ctx.seed, ctx.noise = sigma_module, acts, raw_noise_std, seed, noise
         ctx.want_rays = rays.requires_grad
         return d, w, o, v
 
@@ -53,15 +54,15 @@ class _RenderFn(torch.autograd.Function):
         r, z, sigma = ctx.saved_tensors
         n, S = z.shape
         c = lambda t: None if t is None else t.contiguous().float()
-        d_sigma, d_rays = ops.render_bwd(sigma, z, r, None, ctx.std, ctx.seed, c(gw), c(gd), c(go), c(gv))
+        d_sigma, d_rays = ops.render_bwd(sigma, z, r, ctx.noise, ctx.std, ctx.seed, c(gw), c(gd), c(go), c(gv))
         m = ctx.m
         d_params = torch.zeros_like(m.params)
-        gmax = d_sigma.abs().max()
-        scale = float(torch.clamp(16.0 / (gmax + 1e-30), 1.0, 2.0 ** 24).log2().floor().exp2())
-        d_pos = m.bwd(n * S, d_sigma.view(-1), ctx.acts, scale, d_params, ctx.want_rays, rays=r, z=z)
+        cs = device_grad_scale(d_sigma)            # device scalar: no host sync in the backward
+        d_pos = m.bwd(n * S, (d_sigma * cs).view(-1), ctx.acts, 1.0, d_params, ctx.want_rays, rays=r, z=z)
+        d_params.div_(cs)
         if ctx.want_rays:
-            ops.points_bwd(d_pos, z, d_rays)
-        return (d_rays if ctx.want_rays else None), d_params, None, None, None, None
+            ops.points_bwd(d_pos.div_(cs), z, d_rays)
+        return (d_rays if ctx.want_rays else None), d_params, None, None, None, None, None
 
 
 _render_calls = [0]
@@ -76,8 +77,12 @@ def render_rays(rays, ray_sampler, nerf_model, ray_range, scale_factor, N_sample
     z_vals = ray_sampler.get_samples(rays, N_samples, perturb)
     _render_calls[0] += 1
     sm = nerf_model._model_sigma
+    # parity hook: tests may attach `injected = dict(u1=, u2=, noise=)` to the sampler to replay the reference's draws
+    inj = getattr(ray_sampler, "injected", None) or {}
+    noise = inj.get("noise")
     depth, weights, opacity, variance = _RenderFn.apply(rays, sm.params, z_vals, sm, float(raw_noise_std),
-                                                        12345 + _render_calls[0])
+                                                        12345 + _render_calls[0],
+                                                        None if noise is None else noise.to(z_vals.device).contiguous())
     result = {'rgb_fine': torch.tensor([-1.]), 'depth_fine': depth, 'weights_fine': weights,
               'opacity_fine': opacity}
     if return_variance:

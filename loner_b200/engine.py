@@ -79,6 +79,10 @@ class EngineConfig:
     js_alpha: float = 1.0
     los_lambda: float = 1000.0
     depthloss_lambda: float = 0.005
+    decay_los_lambda: bool = False      # optimizer.py:448-452 (default_model_config.yaml:44-48)
+    los_lambda_decay_rate: float = 0.999
+    los_lambda_decay_steps: float = 1.0
+    min_los_lambda: float = 100.0
     loss_selection: str = "L1_JS"       # L1_JS | L2_JS | L1_LOS | L2_LOS   (optimizer.py:497-532,568-574)
     depth_eps: float = 3.0              # *_LOS: fixed / decaying margin (optimizer.py:516-521)
     decay_depth_eps: bool = True
@@ -87,12 +91,21 @@ class EngineConfig:
     # train (default_model_config.yaml:27-31)
     lrate_sigma_mlp: float = 0.01
     lrate_pose: float = 0.001
+    lrate_gamma: float = 1.0            # ExponentialLR stepped every iteration (optimizer.py:269,378)
     # engine
     rays_selection: str = "RANDOM"      # RANDOM | FIXED | MASK   (optimizer.py:286-296)
-    chunk_rays: int = 8192
+    n_sky: int = 0                      # num_samples.sky picks per keyframe among its sky directions (optimizer.py:299-303)
+    chunk_rays: int = 16384             # render.chunk (default_model_config.yaml:19); the stash is ~4.3 KB per sample
     seed: int = 0
 
-    def loss_cfg(self, iteration_idx=0):
+    def los_lambda_at(self, global_step):
+        """optimizer.py:448-452: the LOS weight, optionally decayed with the optimiser's global step."""
+        if not self.decay_los_lambda:
+            return self.los_lambda
+        return max(self.los_lambda * self.los_lambda_decay_rate ** ((global_step + 1) / self.los_lambda_decay_steps),
+                   self.min_los_lambda)
+
+    def loss_cfg(self, iteration_idx=0, global_step=0):
         """The 9 floats loner_render_loss takes; *_LOS margins follow optimizer.py:516-521."""
         if self.loss_selection not in ("L1_JS", "L2_JS", "L1_LOS", "L2_LOS"):
             raise ValueError(f"Can't use unknown Loss {self.loss_selection}")
@@ -102,7 +115,7 @@ class EngineConfig:
             if self.decay_depth_eps:
                 fixed = max(self.depth_eps * self.depth_eps_decay_rate ** (iteration_idx / self.depth_eps_decay_steps),
                             self.min_depth_eps)
-        return [self.scale, self.min_depth_eps, self.min_js, self.max_js, self.js_alpha, self.los_lambda,
+        return [self.scale, self.min_depth_eps, self.min_js, self.max_js, self.js_alpha, self.los_lambda_at(global_step),
                 self.depthloss_lambda, 1.0 if self.loss_selection.startswith("L2") else 0.0, fixed]
 
 
@@ -130,21 +143,24 @@ class MappingEngine:
         self.exp_avg = torch.zeros_like(self.params)
         self.exp_avg_sq = torch.zeros_like(self.params)
         self.adam_t = 0
-        self.d_params = torch.zeros_like(self.params)
         V = cfg.voxel_size
         self.grid = torch.zeros(V, V, V, device=self.dev, dtype=torch.float32)
         self.d_grid = torch.zeros_like(self.grid)
         self.global_step = 0
-        # keyframe store
-        self.points = None
+        # keyframe store: one float4 per return, lidar returns of a keyframe followed by its sky directions
+        self.points = torch.empty(0, 4, device=self.dev, dtype=torch.float32)
+        self.n_points = 0
         self.kf_offsets = []
         self.kf_sizes = []
+        self.kf_sky_offsets = []
+        self.kf_sky_sizes = []
         self.kf_masks = []
         self.poses6 = []            # list of [6] leaf tensors on device
         self.pose_opt = None
-        self.gen = torch.Generator(device=self.dev)
-        self.gen.manual_seed(cfg.seed)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        # every rank draws its own rays and noise: the streams are keyed by (cfg.seed, rank)
+        self._seed_base = (int(cfg.seed) * 1000003 + self.rank * 7368787) & 0xFFFFFFFFFFFF
         self._bufs = {}
         self.launches = 0           # kernels of OURS launched (bench reports it)
         self.last = {}
@@ -153,11 +169,25 @@ class MappingEngine:
         self._pose_cache = None
         self.phase_iteration = 0
         self.train_map = True       # False = "tracking" phase: poses only, MLP frozen (freeze_sigma_mlp)
-        self._exchange = None
+        self._flat = None           # [MLP grads | pose grads | 4 loss sums]: ONE buffer, all-reduced in place
+        self._flat_K = -1
+        self._views(1)
         self._z_all = None
         self._last_d_poses12 = None
         self._counters = torch.zeros(2, device=self.dev, dtype=torch.int32)
-        self._loss_acc = torch.zeros(4, device=self.dev, dtype=torch.float32)
+        self._side = None           # side stream of the loss-normaliser all-reduce (multi-GPU)
+
+    def _views(self, K):
+        """The flat exchange buffer for a K-keyframe window and its three views.  The kernels write the
+        gradients and loss sums straight into it, so the multi-GPU all-reduce needs no staging copies."""
+        if self._flat_K != K:
+            n = self.net.param_count
+            self._flat = torch.zeros(n + 12 * K + 4, device=self.dev, dtype=torch.float32)
+            self.d_params = self._flat[:n]
+            self._d_poses12 = self._flat[n:n + 12 * K].view(K, 12)
+            self._loss_acc = self._flat[n + 12 * K:]
+            self._flat_K = K
+        return self._flat
 
     def _pack(self):
         """fp32 master parameters -> the fp16 image the kernels read (after construction and every Adam step)."""
@@ -173,23 +203,41 @@ class MappingEngine:
         return ops.mlp_fwd(self.net, self.packed, P, rays=rays, z=z, stash=False)[0]
 
     # ---------------------------------------------------------------- keyframes
-    def add_keyframe(self, ray_directions, distances, pose6, mask=None):
-        """mask: optional bool [M] (LidarScan.mask) used by rays_selection = MASK."""
+    def add_keyframe(self, ray_directions, distances, pose6, mask=None, sky_rays=None):
+        """LidarScan buffers of one keyframe (common/sensors.py:57-82) -> the device store.
+        mask: optional bool [M] (LidarScan.mask) used by rays_selection = MASK;
+        sky_rays: optional [3,Ks] unit directions (LidarScan.sky_rays); stored as returns at distance
+        ray_range[1] + 1 like LidarScan.get_sky_scan (sensors.py:162-167, keyframe.py:92)."""
         self.kf_masks.append(None if mask is None else mask.nonzero(as_tuple=True)[0].to(self.dev))
-        pts = ops.pack_points(ray_directions, distances).to(self.dev)
-        off = 0 if self.points is None else self.points.shape[0]
-        self.points = pts if self.points is None else torch.cat([self.points, pts])
-        self.kf_offsets.append(off)
-        self.kf_sizes.append(pts.shape[0])
+        pts = ops.pack_points(ray_directions, distances)
+        n_l = pts.shape[0]
+        n_s = 0
+        if sky_rays is not None and sky_rays.numel() > 0:
+            sky = ops.pack_points(sky_rays, torch.full_like(sky_rays[0], float(self.cfg.ray_range[1]) + 1.0))
+            n_s = sky.shape[0]
+            pts = torch.cat([pts, sky.to(pts.device)])
+        need = self.n_points + pts.shape[0]
+        if need > self.points.shape[0]:            # capacity doubling: adding a keyframe does not re-copy the whole store
+            cap = max(need, 2 * self.points.shape[0])
+            grown = torch.empty(cap, 4, device=self.dev, dtype=torch.float32)
+            grown[:self.n_points] = self.points[:self.n_points]
+            self.points = grown
+        self.points[self.n_points:need] = pts.to(self.dev)
+        self.kf_offsets.append(self.n_points)
+        self.kf_sizes.append(n_l)
+        self.kf_sky_offsets.append(self.n_points + n_l)
+        self.kf_sky_sizes.append(n_s)
+        self.n_points = need
         self.poses6.append(pose6.detach().to(self.dev, torch.float32).clone())
         self._pose_cache = None
+        self._wcache = {}
         return len(self.poses6) - 1
 
     def new_phase(self, optimize_poses: bool, train_map: bool = True, pose_ids=None):
         """A new Adam per optimisation phase, as the reference does (optimizer.py:257-267).
         pose_ids: keyframes whose pose is optimised (default: all but the anchored keyframe 0)."""
         self.train_map = bool(train_map)
-        self.phase_iteration = 0            # `iteration_idx` of optimizer.py:276 (drives the *_LOS decay)
+        self.phase_iteration = 0            # `iteration_idx` of optimizer.py:276 (drives the *_LOS decay and the LR schedule)
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
         self.adam_t = 0
@@ -219,44 +267,83 @@ class MappingEngine:
     def _buf(self, name, nbytes):
         b = self._bufs.get(name)
         if b is None or b.numel() < nbytes:
+            self._bufs[name] = None
             b = torch.empty(nbytes, device=self.dev, dtype=torch.uint8)
             self._bufs[name] = b
         return b
 
+    def rays_per_keyframe(self, k, n_per_kf):
+        """Rays a keyframe contributes per iteration: n lidar picks + num_samples.sky picks if it has sky directions."""
+        return n_per_kf + (self.cfg.n_sky if self.cfg.n_sky > 0 and self.kf_sky_sizes[k] > 0 else 0)
+
     def _window_consts(self, window, n_per_kf):
-        """Per-window constants live on the device; built once (no per-step host->device traffic)."""
+        """Per-window pick segments (device array of loner_pick_seg_t), built once per window."""
         key = (tuple(window), n_per_kf)
         c = self._wcache.get(key)
         if c is None:
-            K = len(window)
-            c = dict(
-                sizes=torch.tensor([self.kf_sizes[k] for k in window], device=self.dev, dtype=torch.float32)[:, None],
-                maxi=torch.tensor([self.kf_sizes[k] - 1 for k in window], device=self.dev, dtype=torch.int64)[:, None],
-                offs=torch.tensor([self.kf_offsets[k] for k in window], device=self.dev, dtype=torch.int64)[:, None],
-                ray_kf=torch.arange(K, device=self.dev, dtype=torch.int32).repeat_interleave(n_per_kf).contiguous())
+            strategy = self.cfg.rays_selection
+            if strategy not in ("RANDOM", "FIXED", "MASK"):
+                raise RuntimeError(f"Can't find rays_selection strategy: {strategy}")
+            segs, maps, out, map_off = [], [], 0, 0
+            for row, k in enumerate(window):
+                if strategy == "RANDOM":                    # torch.randint(len(scan), (n,))       optimizer.py:288
+                    segs.append((row, ops.PICK_RANDOM, self.kf_offsets[k], self.kf_sizes[k], 0, out))
+                elif strategy == "FIXED":                   # torch.arange(n)                       optimizer.py:293-294
+                    if n_per_kf > self.kf_sizes[k]:
+                        raise IndexError(f"rays_selection FIXED asks for {n_per_kf} rays but keyframe {k} has "
+                                         f"{self.kf_sizes[k]} returns")
+                    segs.append((row, ops.PICK_FIXED, self.kf_offsets[k], self.kf_sizes[k], 0, out))
+                else:                                       # picks among scan.mask.nonzero()       optimizer.py:289-292
+                    m = self.kf_masks[k]
+                    if m is None or m.numel() == 0:
+                        raise RuntimeError("rays_selection MASK needs add_keyframe(..., mask=...) with a non-empty mask")
+                    segs.append((row, ops.PICK_MASK, self.kf_offsets[k], m.numel(), map_off, out))
+                    maps.append(m)
+                    map_off += m.numel()
+                out += n_per_kf
+                if self.cfg.n_sky > 0 and self.kf_sky_sizes[k] > 0:     # optimizer.py:299-303, pose detached keyframe.py:93-95
+                    segs.append((row | ops.KF_DETACHED, ops.PICK_RANDOM, self.kf_sky_offsets[k], self.kf_sky_sizes[k], 0, out))
+                    out += self.cfg.n_sky
+            c = dict(segs=ops.pick_segments(segs, self.dev), n_segs=len(segs), n_rays=out,
+                     index_map=torch.cat(maps).contiguous() if maps else None,
+                     ray_kf=torch.empty(out, device=self.dev, dtype=torch.int32),
+                     ray_point=torch.empty(out, device=self.dev, dtype=torch.int64))
             self._wcache = {key: c}
         return c
 
     def _pick_rays(self, window, n_per_kf):
+        """ray pick of optimizer.py:286-305 as ONE kernel (loner_ray_pick)."""
         c = self._window_consts(window, n_per_kf)
-        strategy = self.cfg.rays_selection
-        if strategy == "RANDOM":                      # torch.randint(len(scan), (n,))          optimizer.py:288
-            u = torch.rand(len(window), n_per_kf, device=self.dev, generator=self.gen)
-            idx = torch.minimum((u * c["sizes"]).long(), c["maxi"])
-        elif strategy == "FIXED":                     # torch.arange(n)                          optimizer.py:293-294
-            idx = torch.arange(n_per_kf, device=self.dev)[None, :].expand(len(window), n_per_kf)
-        elif strategy == "MASK":                      # random picks among scan.mask.nonzero()   optimizer.py:289-292
-            rows = []
-            for k in window:
-                m = self.kf_masks[k]
-                if m is None:
-                    raise RuntimeError("rays_selection MASK needs add_keyframe(..., mask=...)")
-                u = torch.rand(n_per_kf, device=self.dev, generator=self.gen)
-                rows.append(m[torch.clamp((u * m.numel()).long(), max=m.numel() - 1)])
-            idx = torch.stack(rows)
-        else:
-            raise RuntimeError(f"Can't find rays_selection strategy: {strategy}")
-        return c["ray_kf"], (idx + c["offs"]).reshape(-1)
+        seed = (self._seed_base + self.global_step * 104729 + 5) & 0x7FFFFFFFFFFF
+        ops.ray_pick(c["segs"], c["n_segs"], c["index_map"], seed, c["n_rays"], c["ray_kf"], c["ray_point"])
+        self.launches += 1
+        return c["ray_kf"], c["ray_point"]
+
+    def _injected_rays(self, window, n_per_kf, ray_point, ray_kf=None):
+        """Parity tests inject the picked indices: validated like the reference's indexing would (IndexError).
+        ray_kf (optional, int32, LONER_KF_DETACHED allowed) is needed when sky rays are injected too."""
+        ray_point = ray_point.to(self.dev)
+        if ray_point.dtype != torch.int64:
+            raise TypeError("injected ray_point must be int64")
+        K = len(window)
+        if ray_kf is not None:
+            ray_kf = ray_kf.to(self.dev, torch.int32).contiguous()
+            rows = (ray_kf & ops.KF_MASK).long()
+            if ray_kf.numel() != ray_point.numel() or bool((rows >= K).any()):
+                raise IndexError("injected ray_kf does not match the window")
+            lo = torch.tensor([self.kf_offsets[k] for k in window], device=self.dev)[rows]
+            hi = torch.tensor([self.kf_sky_offsets[k] + self.kf_sky_sizes[k] for k in window], device=self.dev)[rows]
+            if bool(((ray_point < lo) | (ray_point >= hi)).any()):
+                raise IndexError("injected ray_point outside its keyframe's scan")
+            return ray_kf, ray_point.contiguous()
+        if ray_point.numel() != K * n_per_kf:
+            raise IndexError(f"injected ray_point has {ray_point.numel()} entries, expected {K} x {n_per_kf}")
+        lo = torch.tensor([self.kf_offsets[k] for k in window], device=self.dev).repeat_interleave(n_per_kf)
+        hi = torch.tensor([self.kf_sky_offsets[k] + self.kf_sky_sizes[k] for k in window], device=self.dev).repeat_interleave(n_per_kf)
+        if bool(((ray_point < lo) | (ray_point >= hi)).any()):
+            raise IndexError("injected ray_point outside its keyframe's scan")
+        ray_kf = torch.arange(K, device=self.dev, dtype=torch.int32).repeat_interleave(n_per_kf).contiguous()
+        return ray_kf, ray_point.contiguous()
 
     def _poses12(self, window, optimize_poses):
         """[K,12] pose matrices; recomputed through autograd only while poses are being optimised."""
@@ -267,30 +354,52 @@ class MappingEngine:
         self._pose_cache = None if optimize_poses else (key, p12.detach().contiguous())
         return p12
 
+    def _lr(self, base):
+        """ExponentialLR(gamma) stepped after every iteration of the phase (optimizer.py:269,378)."""
+        g = self.cfg.lrate_gamma
+        return base if g == 1.0 else base * g ** self.phase_iteration
+
+    def _reduce_counts_async(self, counters):
+        """Global loss normalisers (#valid, #opaque): all-reduced on a side stream right after ray_build,
+        hidden behind the sampler and the forward kernel; returns the event the loss kernel waits for."""
+        if self.world == 1:
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        cur = torch.cuda.current_stream(self.dev)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            parallel.allreduce_counts(counters)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        return ev
+
     # ---------------------------------------------------------------- the step
     def step(self, window, n_per_kf, optimize_poses=False, injected=None, want_outputs=False):
-        """One mapping iteration over `window` (keyframe ids), n_per_kf rays per keyframe on THIS rank.
-        injected: optional dict(ray_point, u1, u2, noise) for parity tests.  Returns the loss (0-dim
-        device tensor, no host sync)."""
+        """One mapping iteration over `window` (keyframe ids), n_per_kf lidar rays (+ cfg.n_sky sky rays) per
+        keyframe on THIS rank.  injected: optional dict(ray_point, u1, u2, noise) for parity tests.
+        Returns the loss (0-dim device tensor, no host sync)."""
         cfg = self.cfg
+        K = len(window)
+        self._views(K)
         if injected is not None and "ray_point" in injected:
-            ray_point = injected["ray_point"].to(self.dev)
-            ray_kf = self._window_consts(window, n_per_kf)["ray_kf"]
+            ray_kf, ray_point = self._injected_rays(window, n_per_kf, injected["ray_point"], injected.get("ray_kf"))
         else:
             ray_kf, ray_point = self._pick_rays(window, n_per_kf)
         poses12 = self._poses12(window, optimize_poses)
         p12 = poses12.detach().contiguous()
+        self._flat.zero_()                 # d_params, d_poses12, loss sums: one memset
         counters = self._counters.zero_()
         rays, depths, flags = ops.ray_build(self.points, ray_kf, ray_point, p12, cfg.shift, cfg.scale,
                                             cfg.ray_range, counters)
         self.launches += 1
-        parallel.allreduce_counts(counters)
+        counts_ready = self._reduce_counts_async(counters)
         loss_acc, d_rays = self._forward_backward(rays, depths, flags, counters, optimize_poses, injected,
-                                                  want_outputs)
+                                                  want_outputs, counts_ready)
         d_poses12 = None
         if optimize_poses:
             d_poses12 = ops.ray_build_bwd(self.points, ray_kf, ray_point, p12, cfg.shift, cfg.scale, cfg.ray_range,
-                                          d_rays)
+                                          d_rays, out=self._d_poses12)
             self.launches += 1
         loss = self._exchange_and_update(loss_acc, counters, d_poses12)
         if d_poses12 is not None:
@@ -298,8 +407,10 @@ class MappingEngine:
                 p.grad = None
             poses12.backward(self._last_d_poses12)
             if self.pose_opt is not None:
+                for g in self.pose_opt.param_groups:
+                    g["lr"] = self._lr(cfg.lrate_pose)
                 self.pose_opt.step()
-        self._occupancy_update(rays, depths)
+        self._occupancy_update(rays, depths, flags)
         return loss
 
     def step_from_host(self, rays_host, depths_host):
@@ -307,6 +418,8 @@ class MappingEngine:
         fed with HOST rays [N,13] and depths [N] (pinned), as the reference's data_prep_on_cpu path
         does: H2D copy -> step -> loss read back."""
         cfg = self.cfg
+        self._views(1)
+        self._flat.zero_()
         rays = rays_host.to(self.dev, non_blocking=True)
         depths = depths_host.to(self.dev, non_blocking=True)
         far, near = rays[:, 12], rays[:, 11]
@@ -314,30 +427,31 @@ class MappingEngine:
         opaque = valid & (depths > 0) & ~(depths > far)
         flags = (valid.to(torch.uint8) + 2 * opaque.to(torch.uint8)).contiguous()
         counters = torch.stack([valid.sum(), opaque.sum()]).to(torch.int32)
-        parallel.allreduce_counts(counters)
-        loss_acc, _ = self._forward_backward(rays, depths, flags, counters, False, None, False)
+        counts_ready = self._reduce_counts_async(counters)
+        loss_acc, _ = self._forward_backward(rays, depths, flags, counters, False, None, False, counts_ready)
         loss = self._exchange_and_update(loss_acc, counters, None)
-        self._occupancy_update(rays, depths)
+        self._occupancy_update(rays, depths, flags)
         return float(loss.item())
 
-    def _forward_backward(self, rays, depths, flags, counters, optimize_poses, injected, want_outputs):
+    def _forward_backward(self, rays, depths, flags, counters, optimize_poses, injected, want_outputs, counts_ready=None):
         cfg = self.cfg
         N, S = rays.shape[0], cfg.n_samples
-        gscale = ops.default_grad_scale(N * self.world, S, cfg.los_lambda)
-        loss_acc = self._loss_acc.zero_()
-        self.d_params.zero_()
+        los_lambda = cfg.los_lambda_at(self.global_step)
+        gscale = ops.default_grad_scale(N * self.world, S, los_lambda)
+        loss_acc = self._loss_acc
         d_rays = torch.zeros(N, ops.RAY_COLS, device=self.dev, dtype=torch.float32) if optimize_poses else None
         outs = []
-        seed = (cfg.seed * 1000003 + self.global_step * 7919 + 13) & 0x7FFFFFFFFFFF
+        seed = (self._seed_base + self.global_step * 7919 + 13) & 0x7FFFFFFFFFFF
         keep_z = self.global_step % cfg.occ_every == 0 and cfg.sampler == "OGM"
         self._z_all = [] if keep_z else None
+        loss_cfg = cfg.loss_cfg(self.phase_iteration, self.global_step)
         for c0 in range(0, N, cfg.chunk_rays):
             c1 = min(N, c0 + cfg.chunk_rays)
             r, dpt, fl = rays[c0:c1], depths[c0:c1], flags[c0:c1]
             P = (c1 - c0) * S
             inj = injected or {}
             u1 = inj["u1"][c0:c1].contiguous().to(self.dev) if "u1" in inj else None
-            u2 = inj["u2"][c0:c1].contiguous().to(self.dev) if "u2" in inj else None
+            u2 = inj["u2"][c0:c1].contiguous().to(self.dev) if inj.get("u2") is not None else None
             noise = inj["noise"][c0:c1].contiguous().to(self.dev) if "noise" in inj else None
             with self._sec("sample"):
                 if cfg.sampler == "OGM":
@@ -350,8 +464,11 @@ class MappingEngine:
                     sigma = ops.hash_fwd(self.net, self.packed, P, rays=r, z=z)
                 else:
                     sigma, _ = ops.mlp_fwd(self.net, self.packed, P, rays=r, z=z, stash=True, acts=acts)
+            if counts_ready is not None:
+                torch.cuda.current_stream(self.dev).wait_event(counts_ready)
+                counts_ready = None
             with self._sec("render_loss"):
-                res = ops.render_loss(sigma, z, r, dpt, fl, counters, cfg.loss_cfg(self.phase_iteration), noise=noise,
+                res = ops.render_loss(sigma, z, r, dpt, fl, counters, loss_cfg, noise=noise,
                                       raw_noise_std=cfg.raw_noise_std, seed=seed + c0 + 1, loss_acc=loss_acc,
                                       want_outputs=want_outputs, d_rays=d_rays[c0:c1] if optimize_poses else None)
             scratch = self._buf("scratch", max(self.net.bwd_scratch_bytes(P), 16))
@@ -366,7 +483,7 @@ class MappingEngine:
                                           want_dpos=optimize_poses)
                 with self._sec("mlp_wgrad"):
                     ops.mlp_wgrad(self.net, self.packed, P, res["d_sigma"], acts, gscale, self.d_params, scratch)
-                self.launches += 3 + 4
+                self.launches += 3 + ops.MLP_BWD_LAUNCHES
             if optimize_poses:
                 ops.points_bwd(d_pos, z, d_rays[c0:c1])
                 self.launches += 1
@@ -380,44 +497,39 @@ class MappingEngine:
         return loss_acc, d_rays
 
     def _exchange_and_update(self, loss_acc, counters, d_poses12):
-        """ONE all-reduce of [MLP grads | pose grads | 4 loss sums], then Adam + fp16 repack."""
+        """ONE in-place all-reduce of [MLP grads | pose grads | 4 loss sums], then Adam + fp16 repack."""
         cfg = self.cfg
         if self.world > 1:
-            shapes = [tuple(self.d_params.shape), tuple(d_poses12.shape) if d_poses12 is not None else (0,), (4,)]
-            if self._exchange is None or self._exchange.shapes != shapes:
-                self._exchange = parallel.FlatExchange(shapes, self.dev)
-            g, gp, acc = self._exchange.reduce([self.d_params,
-                                                d_poses12 if d_poses12 is not None else self.d_params[:0], loss_acc])
-            self.d_params.copy_(g)
-            loss_acc = acc.clone()
-            if d_poses12 is not None:
-                d_poses12 = gp.clone()
+            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
         self._last_d_poses12 = d_poses12
         if self.train_map:
             self.adam_t += 1
             with self._sec("adam_pack"):
                 ops.adam_step(self.params, self.d_params, self.exp_avg, self.exp_avg_sq, self.adam_t,
-                              cfg.lrate_sigma_mlp)
+                              self._lr(cfg.lrate_sigma_mlp))
                 self._pack()
             self.launches += 2
         cnt = counters.to(torch.float32)
-        loss = (cfg.depthloss_lambda * loss_acc[0] / cnt[1] + cfg.los_lambda * loss_acc[1] / (cnt[0] * cfg.n_samples)
+        los_lambda = cfg.los_lambda_at(self.global_step)
+        loss = (cfg.depthloss_lambda * loss_acc[0] / cnt[1] + los_lambda * loss_acc[1] / (cnt[0] * cfg.n_samples)
                 + loss_acc[2] / cnt[1])
-        self.last.update(loss_acc=loss_acc, counters=counters, depth_eps=loss_acc[3] / cnt[0])
+        self.last.update(loss_acc=loss_acc.clone(), counters=counters, depth_eps=loss_acc[3] / cnt[0])
         return loss
 
-    def _occupancy_update(self, rays, depths):
+    def _occupancy_update(self, rays, depths, flags=None):
         """Every occ_every global steps (optimizer.py:382-384): scatter the pseudo-gradient, SGD step."""
         cfg = self.cfg
         if self._z_all is not None:
             self.d_grid.zero_()
-            for ci, c0 in enumerate(range(0, rays.shape[0], cfg.chunk_rays)):
-                c1 = min(rays.shape[0], c0 + cfg.chunk_rays)
-                ops.ogm_grad(rays[c0:c1], self._z_all[ci], depths[c0:c1], cfg.scale, cfg.voxel_size, self.d_grid)
-                self.launches += 1
-            if self.world > 1:
-                dist.all_reduce(self.d_grid, op=dist.ReduceOp.SUM)
-            ops.sgd_step(self.grid, self.d_grid, cfg.occ_lr)
+            with self._sec("ogm_update"):
+                for ci, c0 in enumerate(range(0, rays.shape[0], cfg.chunk_rays)):
+                    c1 = min(rays.shape[0], c0 + cfg.chunk_rays)
+                    ops.ogm_grad(rays[c0:c1], self._z_all[ci], depths[c0:c1], cfg.scale, cfg.voxel_size, self.d_grid,
+                                 flags=None if flags is None else flags[c0:c1])
+                    self.launches += 1
+                if self.world > 1:
+                    dist.all_reduce(self.d_grid, op=dist.ReduceOp.SUM)
+                ops.sgd_step(self.grid, self.d_grid, cfg.occ_lr)
             self.launches += 1
             self._z_all = None
         self.global_step += 1
@@ -425,20 +537,36 @@ class MappingEngine:
 
     # ---------------------------------------------------------------- inference (test mode)
     @torch.no_grad()
-    def render(self, rays, n_samples=None, seed=0):
-        """Model.forward(testing=True) (models/model_tcnn.py:70-105): perturb = 0; like the reference the
-        importance draws and raw_noise_std stay active."""
+    def render(self, rays, n_samples=None, seed=0, injected=None, want_weights=False):
+        """Model.forward(testing=True) (models/model_tcnn.py:70-105): N_samples_test samples, perturb = 0; like
+        the reference the importance draws and raw_noise_std stay active, so parity
+        tests inject u2 / noise.  Processed in chunks of cfg.chunk_rays rays like the reference's chunk loop
+        (model_tcnn.py:82)."""
         cfg = self.cfg
         S = n_samples or cfg.n_samples
-        if cfg.sampler == "OGM":
-            z = ops.sample_ogm(rays, self.grid, S, 0.0, None, None, seed=seed)
-        else:
-            z = ops.sample_uniform(rays, S, 0.0, None, seed=seed)
-        sigma = self._sigma(rays.shape[0] * S, rays, z)
-        w, d, o, v = ops.render_fwd(sigma, z, rays, noise=None, raw_noise_std=cfg.raw_noise_std, seed=seed + 1,
-                                    want_weights=False)
-        self.launches += 3
-        return dict(depth_fine=d, opacity_fine=o, variance=v, samples_fine=z)
+        inj = injected or {}
+        N = rays.shape[0]
+        step = max(1, min(cfg.chunk_rays, (cfg.chunk_rays * cfg.n_samples) // S))     # same samples per chunk as training
+        parts = []
+        for c0 in range(0, N, step):
+            c1 = min(N, c0 + step)
+            r = rays[c0:c1].contiguous()
+            u2 = inj["u2"][c0:c1].contiguous().to(self.dev) if inj.get("u2") is not None else None
+            noise = inj["noise"][c0:c1].contiguous().to(self.dev) if inj.get("noise") is not None else None
+            if cfg.sampler == "OGM":
+                z = ops.sample_ogm(r, self.grid, S, 0.0, None, u2, seed=seed + c0)
+            else:
+                z = ops.sample_uniform(r, S, 0.0, None, seed=seed + c0)
+            sigma = self._sigma(r.shape[0] * S, r, z)
+            w, d, o, v = ops.render_fwd(sigma, z, r, noise=noise, raw_noise_std=cfg.raw_noise_std, seed=seed + c0 + 1,
+                                        want_weights=want_weights)
+            self.launches += 3
+            parts.append((d, o, v, z, w))
+        cat = (lambda i: parts[0][i] if len(parts) == 1 else torch.cat([p[i] for p in parts]))
+        out = dict(depth_fine=cat(0), opacity_fine=cat(1), variance=cat(2), samples_fine=cat(3))
+        if want_weights:
+            out["weights_fine"] = cat(4)
+        return out
 
 
 def xavier_uniform_flat(layer_shapes, seed):

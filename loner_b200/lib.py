@@ -18,6 +18,10 @@ class NetT(_c.Structure):
     _fields_ = [("n_frequencies", _i32), ("n_neurons", _i32), ("n_hidden_layers", _i32), ("reserved", _i32)]
 
 
+class PickSegT(_c.Structure):
+    _fields_ = [("kf", _i32), ("mode", _i32), ("base", _i64), ("size", _i64), ("map_off", _i64), ("out_begin", _i64)]
+
+
 class HashNetT(_c.Structure):
     _fields_ = [("n_levels", _i32), ("n_features_per_level", _i32), ("log2_hashmap_size", _i32),
                 ("base_resolution", _i32), ("per_level_scale", _f32), ("n_neurons", _i32),
@@ -28,6 +32,7 @@ _SIGS = {
     "loner_version": (_c.c_int, []),
     "loner_sm_arch": (_c.c_int, []),
     "loner_error_string": (_c.c_char_p, [_c.c_int]),
+    "loner_ray_pick": (_c.c_int, [_vp, _i32, _vp, _u64, _i64, _vp, _vp, _vp]),
     "loner_ray_build": (_c.c_int, [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "loner_ray_build_bwd": (_c.c_int, [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _f32, _f32, _vp, _vp, _vp]),
     "loner_sample_uniform": (_c.c_int, [_vp, _i64, _i32, _f32, _vp, _u64, _vp, _vp]),
@@ -54,9 +59,8 @@ _SIGS = {
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "loner_points_bwd": (_c.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "loner_adam_step": (_c.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _vp]),
-    "loner_ogm_grad": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp]),
+    "loner_ogm_grad": (_c.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp]),
     "loner_sgd_step": (_c.c_int, [_vp, _vp, _i64, _f32, _vp]),
-    "loner_probe_tmem": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _vp, _vp, _vp]),
 }
 
 _lib = None

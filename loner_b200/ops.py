@@ -112,6 +112,30 @@ def pack_points(ray_directions, distances):
     return torch.cat([ray_directions.t(), distances[:, None]], dim=1).contiguous().float()
 
 
+KF_DETACHED = 0x40000000
+KF_MASK = 0x3FFFFFFF
+MLP_BWD_LAUNCHES = 4          # dgrad, wgrad, wgrad partial reduce, dW_out
+PICK_RANDOM, PICK_FIXED, PICK_MASK = 0, 1, 2
+
+
+def pick_segments(segs, device):
+    """[(kf, mode, base, size, map_off, out_begin)] -> device array of loner_pick_seg_t (uint8 tensor)."""
+    arr = (L.PickSegT * len(segs))(*[L.PickSegT(*[int(v) for v in s]) for s in segs])
+    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+    return raw.to(device)
+
+
+def ray_pick(segs_dev, n_segs, index_map, seed, n, ray_kf=None, ray_point=None):
+    dev = segs_dev.device
+    if ray_kf is None:
+        ray_kf = torch.empty(n, device=dev, dtype=torch.int32)
+    if ray_point is None:
+        ray_point = torch.empty(n, device=dev, dtype=torch.int64)
+    L.check(L.load().loner_ray_pick(L.ptr(segs_dev), n_segs, L.ptr(index_map), seed, n, L.ptr(ray_kf), L.ptr(ray_point),
+                                    L.stream_ptr()), "loner_ray_pick")
+    return ray_kf, ray_point
+
+
 def ray_build(points, ray_kf, ray_point, poses12, shift, scale, ray_range, counters=None):
     n = ray_point.shape[0]
     dev = points.device
@@ -126,8 +150,9 @@ def ray_build(points, ray_kf, ray_point, poses12, shift, scale, ray_range, count
     return rays, depths, flags
 
 
-def ray_build_bwd(points, ray_kf, ray_point, poses12, shift, scale, ray_range, d_rays):
-    d_poses = torch.zeros_like(poses12)
+def ray_build_bwd(points, ray_kf, ray_point, poses12, shift, scale, ray_range, d_rays, out=None):
+    """out: optional zeroed [K,12] buffer the gradient is accumulated into."""
+    d_poses = torch.zeros_like(poses12) if out is None else out
     sh = L.host_floats(shift)
     L.check(L.load().loner_ray_build_bwd(L.ptr(points), L.ptr(ray_kf), L.ptr(ray_point), ray_point.shape[0],
                                          L.ptr(_f32(poses12)), poses12.shape[0], sh, float(scale),
@@ -264,12 +289,12 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.9
                                      float(grad_unscale), L.stream_ptr()), "loner_adam_step")
 
 
-def ogm_grad(rays, z, depths, scale, V, d_grid=None):
+def ogm_grad(rays, z, depths, scale, V, d_grid=None, flags=None):
     n, S = z.shape
     if d_grid is None:
         d_grid = torch.zeros(V, V, V, device=z.device, dtype=torch.float32)
-    L.check(L.load().loner_ogm_grad(L.ptr(_f32(rays)), L.ptr(_f32(z)), L.ptr(_f32(depths)), n, S, float(scale), V,
-                                    L.ptr(d_grid), L.stream_ptr()), "loner_ogm_grad")
+    L.check(L.load().loner_ogm_grad(L.ptr(_f32(rays)), L.ptr(_f32(z)), L.ptr(_f32(depths)), L.ptr(flags), n, S,
+                                    float(scale), V, L.ptr(d_grid), L.stream_ptr()), "loner_ogm_grad")
     return d_grid
 
 

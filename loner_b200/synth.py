@@ -137,6 +137,15 @@ def make_scan(geom: str, pose: torch.Tensor, seed: int, t0: float = 0.0,
     return Scan(dirs, dist.float(), ts)
 
 
+def sky_directions(n: int, seed: int) -> torch.Tensor:
+    """[3, n] unit directions above the horizon (elevation 25..85 degrees), the shape LidarScan.sky_rays has
+    (common/sensors.py:57-82; the tracker's compute_sky_rays produces them from gaps in the scan)."""
+    gen = torch.Generator().manual_seed(seed)
+    el = torch.deg2rad(25.0 + 60.0 * torch.rand(n, generator=gen, dtype=torch.float64))
+    az = 2 * math.pi * torch.rand(n, generator=gen, dtype=torch.float64)
+    return torch.stack([torch.cos(el) * torch.cos(az), torch.cos(el) * torch.sin(az), torch.sin(el)], 0).float()
+
+
 def make_window(geom: str, K: int, seed: int = 0, n_beams: int = 64, n_azimuth: int = 1024):
     """K scans + their poses."""
     poses = keyframe_poses(geom, K)

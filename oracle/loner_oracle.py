@@ -291,16 +291,25 @@ def adam_update(p, g, m, v, step, lr, b1=0.9, b2=0.999, eps=1e-8):
 
 
 def mapping_iteration(scans, poses6, idx_per_kf, params, spec, grid, S, scale, shift, ray_range,
-                      perturb, u1, u2, noise, cfg: LossCfg, sampler="OGM"):
+                      perturb, u1, u2, noise, cfg: LossCfg, sampler="OGM", sky=None):
     """One pass of the hot loop mapping/optimizer.py:276-380 up to loss.backward():
     ray build per keyframe -> concat -> sample -> net -> render -> loss -> grads.
-    poses6: list of [6] tensors (leaf, may require grad); params: flat fp32 (requires grad)."""
+    poses6: list of [6] tensors (leaf, may require grad); params: flat fp32 (requires grad).
+    sky: optional (sky_dirs per keyframe [3,Ks], sky_idx per keyframe [n_sky]) - the keyframe's sky rays are
+    appended after its lidar rays, at distance ray_range[1] + 1 and built from the DETACHED pose
+    (mapping/keyframe.py:87-99, common/sensors.py:162-167, mapping/optimizer.py:299-305)."""
     rays_l, depth_l = [], []
-    for sc, p6, idx in zip(scans, poses6, idx_per_kf):
+    for k, (sc, p6, idx) in enumerate(zip(scans, poses6, idx_per_kf)):
         r, dep, _ = build_lidar_rays(sc.ray_directions, sc.distances, idx, pose6_to_matrix(p6),
                                      ray_range, scale, shift)
         rays_l.append(r)
         depth_l.append(dep)
+        if sky is not None and sky[1][k] is not None:
+            dirs = sky[0][k]
+            r, dep, _ = build_lidar_rays(dirs, torch.full_like(dirs[0], ray_range[1] + 1), sky[1][k],
+                                         pose6_to_matrix(p6.detach()), ray_range, scale, shift)
+            rays_l.append(r)
+            depth_l.append(dep)
     rays = torch.cat(rays_l).float()
     depths = torch.cat(depth_l).float()
     with torch.no_grad():

@@ -46,8 +46,25 @@ CASES = {
 }
 CASES["kf2_2x128_uni_l2los"] = dict(geom="garden", K=2, n=128, S=128, L=2, W=128, grid="zeros", prec="fp16", poses=True,
                                      rows=64, loss="L2_LOS", sampler="UNIFORM")   # the two branches no other case takes
+# sky rays: num_samples.sky picks per keyframe among LidarScan.sky_rays, built from the
+# detached pose at distance ray_range[1] + 1 (optimizer.py:299-305, keyframe.py:87-99, sensors.py:162-167)
+CASES["kf2_2x128_sky"] = dict(geom="garden", K=2, n=96, S=128, L=2, W=128, grid="trained", prec="fp16", poses=True,
+                               rows=64, n_sky=32, sky_count=200)
 TABLE_SEED, TABLE_SCALE = 4242, 0.5
+# test-mode render + the depth-L1 metric: Model.forward(testing=True) at N_samples_test over a
+# chunked scan, then the L1 of analysis/compute_l1_depth.py:42-64
+TESTMODE = {
+    "testmode_2x128": dict(geom="garden", n=256, chunk=128, S_test=2048, L=2, W=128, grid="trained", prec="fp16"),
+}
 N_BEAMS, N_AZ = 16, 256   # 4,096-point scans keep the fixtures' regeneration cheap
+
+
+def sky_randoms(seed, K, n_sky, sky_count):
+    """Sky directions per keyframe and the replayed `torch.randint(0, sky_dirs.shape[1], (n_sky,))` draws."""
+    g = torch.Generator().manual_seed(seed + 2)
+    dirs = [synth.sky_directions(sky_count, seed + 100 + k) for k in range(K)]
+    idx = [torch.randint(0, sky_count, (n_sky,), generator=g) for _ in range(K)]
+    return dirs, idx
 
 
 def case_randoms(seed, n_per_kf, K, M, n_rays, S, sampler="OGM"):
@@ -113,9 +130,11 @@ def run_case(name, c, seed=1234):
             opt._ray_sampler.update_occ_grid(opt._occupancy_grid.detach())
         # the reference's own containers
         kfs = []
+        n_sky = c.get("n_sky", 0)
+        sky_dirs, sky_idx = sky_randoms(seed, c["K"], n_sky, c["sky_count"]) if n_sky else (None, [None] * c["K"])
         for k in range(c["K"]):
             sc = ns.sensors.LidarScan(scans[k].ray_directions.clone(), scans[k].distances.clone(),
-                                      scans[k].timestamps.clone())
+                                      scans[k].timestamps.clone(), sky_rays=sky_dirs[k].clone() if n_sky else None)
             fr = ns.frame.Frame(None, sc, None)
             p6 = synth.axis_angle_from_yaw_pose(poses[k])
             fr._lidar_pose = ns.pose.Pose(pose_tensor=p6.clone(), fixed=not (c["poses"] and k > 0))
@@ -125,8 +144,8 @@ def run_case(name, c, seed=1234):
         # pass 1 (no randomness needed): ray build, to learn the post-filter ray count
         idx, _, _, _ = case_randoms(seed, c["n"], c["K"], M, 1, c["S"], c.get("sampler", "OGM"))
         rays_l, dep_l = [], []
-        for kf, ix in zip(kfs, idx):
-            r, d = kf.build_lidar_rays(ix, ray_range, wc, False)
+        for kf, ix, six in zip(kfs, idx, sky_idx):
+            r, d = kf.build_lidar_rays(ix, ray_range, wc, False, sky_indices=six)
             rays_l.append(r)
             dep_l.append(d)
         rays = torch.vstack(rays_l).float()
@@ -162,6 +181,7 @@ def run_case(name, c, seed=1234):
                                                        "base_resolution")] if c.get("hash") else [], dtype=np.int64),
             table_seed=np.int64(TABLE_SEED), table_scale=np.float32(TABLE_SCALE),
             sampler=np.array(c.get("sampler", "OGM")),
+            sky=np.array([n_sky, c.get("sky_count", 0)], dtype=np.int64),
             rays=rays.detach().numpy(), depths=depths.numpy(),
             z_vals=res["samples_fine"][:rows].detach().numpy(),
             weights=res["weights_fine"][:rows].detach().numpy(),
@@ -187,9 +207,76 @@ def run_case(name, c, seed=1234):
         return out
 
 
+def run_testmode(name, c, seed=4321):
+    """Model.forward(testing=True) over a chunked scan exactly as analysis/compute_l1_depth.py:42-64 drives it
+    (LidarRayDirections.fetch_chunk_rays, ray_utils.py:262-267), with the two draws that stay active in test
+    mode replayed (sample_pdf's u, rendering_tcnn.py:48; raw noise, rendering_tcnn.py:104)."""
+    ns = rh.import_reference()
+    tcnn_standin.PRECISION["mode"] = c["prec"]
+    torch.manual_seed(0)
+    with tempfile.TemporaryDirectory() as tmp:
+        opt, wc, settings = build_reference_optimizer(ns, c["geom"], 128, c["L"], c["W"], tmp)
+        g = synth.GEOMETRY[c["geom"]]
+        scans, poses = synth.make_window(c["geom"], 1, seed=7, n_beams=N_BEAMS, n_azimuth=N_AZ)
+        n, S = c["n"], c["S_test"]
+        grid0 = synth.trained_occupancy_grid(c["geom"])
+        with torch.no_grad():
+            opt._occupancy_grid_model.occupancy_grid.copy_(grid0)
+        opt._ray_sampler.update_occ_grid(opt._occupancy_grid_model().detach())
+        model = opt._model
+        model.cfg["render"]["N_samples_test"] = S
+        assert model.cfg.render.N_samples_test == S
+        # a scan of the first n returns, spread over the whole sweep
+        sel = torch.arange(n) * (scans[0].distances.shape[0] // n)
+        scan = ns.sensors.LidarScan(scans[0].ray_directions[:, sel].clone(), scans[0].distances[sel].clone(),
+                                    scans[0].timestamps[sel].clone())
+        pose = ns.pose.Pose(pose_tensor=synth.axis_angle_from_yaw_pose(poses[0]).clone(), fixed=True)
+        dirs = ns.ray_utils.LidarRayDirections(scan, chunk_size=c["chunk"])
+        ray_range = torch.Tensor(list(g["ray_range"]))
+        g2 = torch.Generator().manual_seed(seed)
+        u2 = torch.rand(n, S // 2, generator=g2)
+        noise = torch.randn(n, S, generator=g2)
+        depth_m = torch.zeros(n, 1)
+        var = torch.zeros(n)
+        opa = torch.zeros(n)
+        rays_all = []
+        with torch.no_grad():
+            for ci in range(dirs.num_chunks):
+                rays = dirs.fetch_chunk_rays(ci, pose, wc, ray_range)
+                lo = ci * c["chunk"]
+                hi = lo + rays.shape[0]
+                assert hi - lo == min(c["chunk"], n - lo), "validity filter dropped a ray: pick another scan subset"
+                replay = rh.Replay()
+                replay.rand = [u2[lo:hi]]
+                replay.randn = [noise[lo:hi]]
+                with rh.injected_randomness(replay):
+                    res = model(rays.float(), opt._ray_sampler, wc.scale_factor, testing=True, return_variance=True,
+                                camera=False)
+                assert not replay.rand and not replay.randn
+                depth_m[lo:hi, :] = res["depth_fine"].unsqueeze(1) * wc.scale_factor
+                var[lo:hi] = res["variance"]
+                opa[lo:hi] = res["opacity_fine"]
+                rays_all.append(rays.float())
+            gt = scan.distances
+            good = torch.logical_and(gt.flatten() > ray_range[0], gt.flatten() < ray_range[1] - 0.25)
+            l1 = torch.nn.functional.l1_loss(depth_m[good].flatten(), gt[good.flatten()].flatten())
+        return dict(meta=np.array([seed, n, c["chunk"], S, c["L"], c["W"], N_BEAMS, N_AZ], dtype=np.int64),
+                    geom=np.array(c["geom"]), prec=np.array(c["prec"]), scale=np.float32(float(wc.scale_factor)),
+                    shift=wc.shift.numpy().astype(np.float32), params_seed=np.int64(1337),
+                    rays=torch.cat(rays_all).numpy(), sel=sel.numpy(), depth_m=depth_m[:, 0].numpy(),
+                    variance=var.numpy(), opacity=opa.numpy(), l1=np.float64(l1.item()), n_good=np.int64(int(good.sum())))
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     only = sys.argv[1:]
+    for name, c in TESTMODE.items():
+        if only and name not in only:
+            continue
+        out = run_testmode(name, c)
+        path = os.path.join(GOLDEN_DIR, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: l1={out['l1']:.6f} over {out['n_good']} rays -> {os.path.getsize(path)/1024:.0f} KiB")
     for name, c in CASES.items():
         if only and name not in only:
             continue

@@ -20,7 +20,17 @@ GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
 
 
 def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Training-iteration fixtures (the test-mode render fixtures `testmode_*` have their own loader)."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in names if not n.startswith("testmode_")]
+
+
+def sky_randoms(seed, K, n_sky, sky_count):
+    """Same protocol as oracle/make_golden.py::sky_randoms."""
+    g = torch.Generator().manual_seed(seed + 2)
+    dirs = [synth.sky_directions(sky_count, seed + 100 + k) for k in range(K)]
+    idx = [torch.randint(0, sky_count, (n_sky,), generator=g) for _ in range(K)]
+    return dirs, idx
 
 
 def case_randoms(seed, n_per_kf, K, M, n_rays, S, sampler="OGM"):
@@ -67,6 +77,9 @@ class Case:
             self.grid = synth.trained_occupancy_grid(self.geom)
         else:
             self.grid = torch.zeros(1, 1, 100, 100, 100)
+        self.n_sky, self.sky_count = ([int(v) for v in self.g["sky"]] if "sky" in self.g.files else (0, 0))
+        self.sky_dirs, self.sky_idx = (sky_randoms(seed, K, self.n_sky, self.sky_count) if self.n_sky
+                                       else (None, None))
         self.pose_grads = "grad_poses" in self.g.files
         self.loss_selection = str(self.g["loss_selection"]) if "loss_selection" in self.g.files else "L1_JS"
         # iteration_idx = 0 in the fixtures: the *_LOS margin is depth_eps * 0.95**0 = 3.0 (default_model_config.yaml:51-55)
@@ -77,7 +90,8 @@ class Case:
         poses6 = [p.clone().requires_grad_(self.pose_grads and k > 0) for k, p in enumerate(self.poses6)]
         rays, depths, res, out = orc.mapping_iteration(
             self.scans, poses6, self.idx, params, self.spec, self.grid, self.S, self.scale, self.shift,
-            self.ray_range, 1.0, self.u1, self.u2, self.noise, self.loss_cfg, sampler=self.sampler)
+            self.ray_range, 1.0, self.u1, self.u2, self.noise, self.loss_cfg, sampler=self.sampler,
+            sky=(self.sky_dirs, self.sky_idx) if self.n_sky else None)
         out["loss"].backward()
         s = res["samples_fine"].detach() * self.scale
         G = depths.reshape(-1, 1) * self.scale
@@ -85,3 +99,41 @@ class Case:
         grid_after = orc.occupancy_step(self.grid, res["points_fine"], s, G, 1e-4) if self.sampler == "OGM" else self.grid
         return dict(rays=rays, depths=depths, res=res, out=out, params=params, poses6=poses6,
                     grid_after=grid_after)
+
+
+class TestModeCase:
+    """tests/golden/testmode_*.npz: Model.forward(testing=True) over a chunked scan + the depth-L1 metric, minted
+    from the reference (oracle/make_golden.py::run_testmode)."""
+    __test__ = False
+
+    def __init__(self, name):
+        self.g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        seed, n, chunk, S, L, W, nb, naz = [int(v) for v in self.g["meta"]]
+        self.seed, self.n, self.chunk, self.S, self.L, self.W = seed, n, chunk, S, L, W
+        self.geom = str(self.g["geom"])
+        self.prec = str(self.g["prec"])
+        self.scale = float(self.g["scale"])
+        self.shift = torch.from_numpy(self.g["shift"])
+        self.ray_range = synth.GEOMETRY[self.geom]["ray_range"]
+        scans, poses = synth.make_window(self.geom, 1, seed=7, n_beams=nb, n_azimuth=naz)
+        sel = torch.from_numpy(self.g["sel"])
+        self.directions = scans[0].ray_directions[:, sel]
+        self.distances = scans[0].distances[sel]
+        self.pose6 = synth.axis_angle_from_yaw_pose(poses[0])
+        g2 = torch.Generator().manual_seed(seed)
+        self.u2 = torch.rand(n, S // 2, generator=g2)
+        self.noise = torch.randn(n, S, generator=g2)
+        self.spec = orc.NetSpec(n_frequencies=10, n_neurons=W, n_hidden_layers=L, precision=self.prec)
+        self.params = tcnn_standin.xavier_uniform_flat(self.spec.shapes, int(self.g["params_seed"]))
+        self.grid = synth.trained_occupancy_grid(self.geom)
+
+    def run_oracle(self):
+        """fetch_chunk_rays -> render (perturb = 0) -> depth-L1, through the oracle."""
+        rays, depths, keep = orc.build_lidar_rays(self.directions, self.distances, torch.arange(self.n),
+                                                  orc.pose6_to_matrix(self.pose6), self.ray_range, self.scale, self.shift)
+        assert bool(keep.all())
+        with torch.no_grad():
+            z = orc.ogm_samples(rays.float(), self.grid, self.S, 0.0, None, self.u2)
+            res = orc.render_rays(rays.float(), z, self.params, self.spec, self.noise)
+        l1 = orc.depth_l1_metric(res["depth_fine"], depths, self.scale, self.ray_range)
+        return rays.float(), depths, res, l1

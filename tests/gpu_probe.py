@@ -2,8 +2,10 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from loner_b200 import lib as L
-lib = L.load()
+import ctypes
+from loner_b200 import build, lib as L
+lib = ctypes.CDLL(build.build_probe())
+lib.loner_probe_tmem.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
 for warps in (4, 8, 16):
     for mode in (1, 2, 4):
         iters = 200

@@ -1,6 +1,6 @@
 // Hardware probes (not on the product path): TMEM -> register bandwidth of tcgen05.ld, used to
-// size the epilogues of mlp.cu.  Exposed through the C ABI as loner_probe_tmem so that the same
-// .so can be measured on the GPU box (tests/gpu_probe.py); results are recorded in DESIGN.md.
+// size the epilogues of mlp.cu.  Built into its own library (loner_b200.build.build_probe -> tests/probes/libloner_probe.so), NOT into the
+// product .so; run by tests/gpu_probe.py, results recorded in DESIGN.md.
 #include "common.cuh"
 #include "sm100.cuh"
 

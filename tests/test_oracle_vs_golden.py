@@ -42,3 +42,17 @@ def test_oracle_matches_reference_fixture(name):
     idx = torch.from_numpy(g["ogm_delta_idx"])
     if idx.numel():                      # empty with the uniform sampler: no occupancy grid is kept or stepped
         assert rel(d[idx], g["ogm_delta_val"]) < 1e-4
+
+
+def test_oracle_test_mode_render_and_depth_l1_match_reference_fixture():
+    """Model.forward(testing=True) at N_samples_test = 2048 over a chunked scan and the depth-L1 metric of
+    analysis/compute_l1_depth.py:42-64, minted from the reference (oracle/make_golden.py::run_testmode)."""
+    from golden_util import TestModeCase
+    c = TestModeCase("testmode_2x128")
+    rays, depths, res, l1 = c.run_oracle()
+    g = c.g
+    assert rel(rays, g["rays"]) < 1e-6
+    assert rel(res["depth_fine"] * c.scale, g["depth_m"]) < 1e-5
+    assert rel(res["opacity_fine"], g["opacity"]) < 1e-5
+    assert rel(res["variance"], g["variance"]) < 1e-5
+    assert abs(float(l1) - float(g["l1"])) / float(g["l1"]) < 1e-6
