@@ -86,7 +86,7 @@ int loner_sample_ogm(const float* rays, int64_t n, int32_t S, float perturb, con
  * :59-78).  Network description. */
 typedef struct {
   int32_t n_frequencies;   /* Frequency encoding, 3 input dims -> 6F features, padded to 16 with 1.0 */
-  int32_t n_neurons;       /* hidden width W: 128 or 256                                       */
+  int32_t n_neurons;       /* hidden width W: 64 (run zero-padded on the 128-wide kernels), 128 or 256 */
   int32_t n_hidden_layers; /* L >= 1 hidden layers                                             */
   int32_t reserved;
 } loner_net_t;

@@ -120,7 +120,9 @@ class EngineConfig:
 
 
 class MappingEngine:
-    def __init__(self, cfg: EngineConfig, device="cuda", params: torch.Tensor = None):
+    def __init__(self, cfg: EngineConfig, device="cuda", params: torch.Tensor = None, distributed: bool = True):
+        """distributed=False keeps this engine single-GPU inside a torch.distributed process (the reference run of
+        the multi-GPU gradient check)."""
         self.cfg = cfg
         self.dev = torch.device(device)
         if cfg.encoding not in ("Frequency", "HashGrid"):
@@ -157,7 +159,7 @@ class MappingEngine:
         self.kf_masks = []
         self.poses6 = []            # list of [6] leaf tensors on device
         self.pose_opt = None
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.world = dist.get_world_size() if distributed and dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
         # every rank draws its own rays and noise: the streams are keyed by (cfg.seed, rank)
         self._seed_base = (int(cfg.seed) * 1000003 + self.rank * 7368787) & 0xFFFFFFFFFFFF
@@ -181,11 +183,8 @@ class MappingEngine:
         """The flat exchange buffer for a K-keyframe window and its three views.  The kernels write the
         gradients and loss sums straight into it, so the multi-GPU all-reduce needs no staging copies."""
         if self._flat_K != K:
-            n = self.net.param_count
-            self._flat = torch.zeros(n + 12 * K + 4, device=self.dev, dtype=torch.float32)
-            self.d_params = self._flat[:n]
-            self._d_poses12 = self._flat[n:n + 12 * K].view(K, 12)
-            self._loss_acc = self._flat[n + 12 * K:]
+            self._flat = parallel.FlatGrads(self.net.param_count, K, self.dev)
+            self.d_params, self._d_poses12, self._loss_acc = self._flat.d_params, self._flat.d_poses12, self._flat.loss_acc
             self._flat_K = K
         return self._flat
 
@@ -500,7 +499,7 @@ class MappingEngine:
         """ONE in-place all-reduce of [MLP grads | pose grads | 4 loss sums], then Adam + fp16 repack."""
         cfg = self.cfg
         if self.world > 1:
-            dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+            self._flat.allreduce()
         self._last_d_poses12 = d_poses12
         if self.train_map:
             self.adam_t += 1

@@ -27,7 +27,7 @@ class Net:
         self.param_count = lib.loner_mlp_param_count(ctypes.byref(self.c))
         if self.param_count < 0:
             raise RuntimeError(f"unsupported sigma network {n_frequencies=} {n_neurons=} {n_hidden_layers=} "
-                               "(kernels implement Frequency<=10, width 128/256, 1..8 hidden layers)")
+                               "(kernels implement Frequency<=10, width 64/128/256, 1..8 hidden layers)")
         self.packed_bytes = lib.loner_mlp_packed_bytes(ctypes.byref(self.c))
         self.e_pad = (6 * self.n_frequencies + 15) // 16 * 16
 

@@ -30,6 +30,9 @@ def test_no_compute_entry_points_need_a_gpu_to_query_sizes():
     net = lib.NetT(10, 256, 4, 0)
     assert l.loner_mlp_param_count(ctypes.byref(net)) == 217088
     assert l.loner_mlp_packed_bytes(ctypes.byref(net)) == 2 * (64 * 256 * 2 + 3 * 256 * 256 * 2) + 256 * 4
-    bad = lib.NetT(10, 64, 1, 0)
+    small = lib.NetT(10, 64, 2, 0)          # BASELINE config 1 (2 x 64): runs zero-padded on the 128-wide kernels
+    assert l.loner_mlp_param_count(ctypes.byref(small)) == 64 * 64 + 64 * 64 + 16 * 64
+    assert l.loner_mlp_packed_bytes(ctypes.byref(small)) == 2 * (64 * 128 * 2 + 128 * 128 * 2) + 128 * 4
+    bad = lib.NetT(10, 96, 1, 0)
     assert l.loner_mlp_param_count(ctypes.byref(bad)) == -1
     assert l.loner_error_string(2).decode().startswith("configuration not supported")

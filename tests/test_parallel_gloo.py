@@ -34,9 +34,14 @@ def _worker(rank, world, port, q):
         local_grad = (rays[lo:hi] * w).sum(0)               # d/dw-like partial gradient
         local_pose = rays[lo:hi, :6].sum(0)
         local_acc = torch.tensor([float(hi - lo), 1.0, 2.0, 3.0])
-        ex = parallel.FlatExchange([(7,), (6,), (4,)], "cpu")
-        grad, pose, acc = ex.reduce([local_grad, local_pose, local_acc])
-        q.put((rank, counts.tolist(), grad.clone(), pose.clone(), acc.clone(), (lo, hi)))
+        ex = parallel.FlatGrads(7, 1, "cpu")                 # the buffer the engine's kernels accumulate into
+        ex.zero_()
+        ex.d_params += local_grad
+        ex.d_poses12[0, :6] += local_pose
+        ex.loss_acc += local_acc
+        ex.allreduce()
+        assert ex.flat.numel() == 7 + 12 + 4 and ex.d_params.data_ptr() == ex.flat.data_ptr()      # views, no copies
+        q.put((rank, counts.tolist(), ex.d_params.clone(), ex.d_poses12[0, :6].clone(), ex.loss_acc.clone(), (lo, hi)))
     finally:
         dist.destroy_process_group()
 
