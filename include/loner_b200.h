@@ -88,8 +88,12 @@ typedef struct {
   int32_t n_frequencies;   /* Frequency encoding, 3 input dims -> 6F features, padded to 16 with 1.0 */
   int32_t n_neurons;       /* hidden width W: 64 (run zero-padded on the 128-wide kernels), 128 or 256 */
   int32_t n_hidden_layers; /* L >= 1 hidden layers                                             */
-  int32_t reserved;
+  int32_t flags;           /* 0 = production kernels; LONER_NET_* bits select the A/B variants */
 } loner_net_t;
+/* forward / dgrad as single CTAs (cta_group::1) instead of CTA pairs sharing the weight operand (cta_group::2) */
+#define LONER_NET_SINGLE_CTA 1
+/* dgrad stashes dZ_L and wgrad reads it, instead of wgrad rebuilding it from the ReLU masks, d_sigma and w_out */
+#define LONER_NET_STASH_DZL 2
 
 int64_t loner_mlp_param_count(const loner_net_t* net);       /* flat fp32 params, [out,in] row-major per layer */
 int64_t loner_mlp_packed_bytes(const loner_net_t* net);      /* fp16 tensor-core image of the params */

@@ -14,7 +14,6 @@
 //   async copies (cp.async.bulk) of contiguous ranges; no tensor maps.
 //   Accumulators live in TMEM (tcgen05.mma, one issuing thread), epilogues read them back with
 //   tcgen05.ld.
-#include <cstdlib>
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -31,12 +30,12 @@ constexpr int kBlk = 16384;           // bytes of one [128 x 64] fp16 column blo
 // matrices zero-padded: padded neurons output relu(0) = 0, their mask bits are 0, and every padded
 // weight gradient is a product with one of those zeros; only pack / reduce know the real layout.
 struct Net {
-  int F, E, Epad, W, L, nb, Wr;
+  int F, E, Epad, W, L, nb, Wr, flags;
 };
 
 __host__ inline bool net_from(const loner_net_t* n, Net& o) {
   if (!n) return false;
-  o.F = n->n_frequencies; o.Wr = n->n_neurons; o.L = n->n_hidden_layers;
+  o.F = n->n_frequencies; o.Wr = n->n_neurons; o.L = n->n_hidden_layers; o.flags = n->flags;
   if (o.F < 1 || o.F > 10) return false;
   if (!(o.Wr == 64 || o.Wr == 128 || o.Wr == 256)) return false;
   if (o.L < 1 || o.L > 8) return false;
@@ -126,48 +125,62 @@ __global__ void pack_kernel(Net net, const float* __restrict__ params, uint8_t* 
 //    The next step is cta_group::2 (each SM holds half of B): -64 KB operands, -64 KB ring per tile-layer.
 constexpr int kPipeThreads = 320;
 constexpr int kGroupThreads = 256;
-constexpr int kRingSlots = 3;
-constexpr int kSlotBytes = 32768;
-constexpr int kPipeSmem = 2 * 65536 + kRingSlots * kSlotBytes + 2432;
+constexpr int kRingBytes = 98304;                    // weight ring: 3 x 32 KB (one CTA) or 6 x 16 KB (CTA pair)
+constexpr int kPipeExtra = 2576;
+constexpr int kPipeSmem = 2 * 65536 + kRingBytes + kPipeExtra;
 
 // Shared-memory map of the two pipelined kernels.  Everything is an ADDRESS COMPUTATION (no arrays of
 // pointers): a table indexed by a run-time slot number would live in local memory, and local loads
 // miss the (tiny, 28 KB) L1 behind a saturated HBM.
+// kCtas = 2: the CTA pair variant (cta_group::2) - each CTA stages only ITS half (N/2 columns) of every weight
+// chunk, so the ring has twice the slots at half the size, and the leader also watches `w_peer`, the barriers the
+// peer's relay warp arrives on when the peer's half of a slot has landed.
+template <int kCtas>
 struct PipeSmem {
+  static constexpr uint32_t kSlots = kCtas == 2 ? 6 : 3;
+  static constexpr uint32_t kSlotBytes = kRingBytes / kSlots;
+  static constexpr uint32_t kX = 131072u + kRingBytes;      // wout | part | barriers | tmem slot | encoding table
   uint8_t* base;
   uint32_t base_u32;
   __device__ __forceinline__ uint8_t* tileA_ptr(int t) const { return base + t * 65536; }
   __device__ __forceinline__ uint32_t tileA(int t) const { return base_u32 + (uint32_t)t * 65536u; }
-  __device__ __forceinline__ uint32_t ring(uint32_t slot) const { return base_u32 + 131072u + slot * (uint32_t)kSlotBytes; }
-  __device__ __forceinline__ float* wout() const { return reinterpret_cast<float*>(base + 131072 + kRingSlots * kSlotBytes); }
+  __device__ __forceinline__ uint32_t ring(uint32_t slot) const { return base_u32 + 131072u + slot * kSlotBytes; }
+  __device__ __forceinline__ float* wout() const { return reinterpret_cast<float*>(base + kX); }
   __device__ __forceinline__ float* part() const { return wout() + 256; }   // [2][128] per-row partial sums (upper -> lower column half)
-  __device__ __forceinline__ uint32_t bars() const { return base_u32 + 131072u + kRingSlots * kSlotBytes + 2048u; }
+  __device__ __forceinline__ uint32_t bars() const { return base_u32 + kX + 2048u; }
   __device__ __forceinline__ uint32_t w_full(uint32_t i) const { return bars() + 8u * i; }
-  __device__ __forceinline__ uint32_t w_empty(uint32_t i) const { return bars() + 8u * (kRingSlots + i); }
-  __device__ __forceinline__ uint32_t a_ready(int t) const { return bars() + 8u * (2 * kRingSlots + t); }
-  __device__ __forceinline__ uint32_t acc_full(int t) const { return bars() + 8u * (2 * kRingSlots + 2 + t); }
+  __device__ __forceinline__ uint32_t w_empty(uint32_t i) const { return bars() + 8u * (kSlots + i); }
+  __device__ __forceinline__ uint32_t a_ready(int t) const { return bars() + 8u * (2 * kSlots + t); }
+  __device__ __forceinline__ uint32_t acc_full(int t) const { return bars() + 8u * (2 * kSlots + 2 + t); }
+  __device__ __forceinline__ uint32_t w_peer(uint32_t i) const { return bars() + 8u * (2 * kSlots + 4 + i); }
+  __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(base + kX + 2304); }
   // encoding table: feature pair p -> {kind, 2^f}; kind 0..2 = input dimension, 3 = padding ones, 4 = zeros
-  __device__ __forceinline__ uint2* enc_tab() const {
-    return reinterpret_cast<uint2*>(base + 131072 + kRingSlots * kSlotBytes + 2176);
-  }
-  __device__ __forceinline__ uint32_t* tmem_slot() const {
-    return reinterpret_cast<uint32_t*>(base + 131072 + kRingSlots * kSlotBytes + 2048 + 8 * (2 * kRingSlots + 4));
-  }
+  __device__ __forceinline__ uint2* enc_tab() const { return reinterpret_cast<uint2*>(base + kX + 2320); }
 };
 
-__device__ __forceinline__ PipeSmem carve(uint8_t* base) {
-  PipeSmem p;
+template <int kCtas>
+__device__ __forceinline__ PipeSmem<kCtas> carve(uint8_t* base) {
+  PipeSmem<kCtas> p;
   p.base = base;
   p.base_u32 = smem_u32(base);
   return p;
 }
 
-__device__ __forceinline__ void pipe_init(const PipeSmem& sm, int tid, int warp, const float* wout_src, int W,
+template <int kCtas>
+__device__ __forceinline__ void pipe_init(const PipeSmem<kCtas>& sm, int tid, int warp, const float* wout_src, int W,
                                           const Net& net) {
-  if (warp == 1) tmem_alloc<512>(smem_u32(sm.tmem_slot()));
+  constexpr uint32_t kSlots = PipeSmem<kCtas>::kSlots;
+  if (warp == 1) {
+    if (kCtas == 2) tmem_alloc2<512>(smem_u32(sm.tmem_slot()));
+    else tmem_alloc<512>(smem_u32(sm.tmem_slot()));
+  }
   if (tid == 0) {
-    for (int i = 0; i < kRingSlots; ++i) { mbar_init(sm.w_full(i), 1); mbar_init(sm.w_empty(i), 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(sm.a_ready(t), kGroupThreads); mbar_init(sm.acc_full(t), 1); }
+    for (uint32_t i = 0; i < kSlots; ++i) {
+      mbar_init(sm.w_full(i), 1); mbar_init(sm.w_empty(i), 1);
+      if (kCtas == 2) mbar_init(sm.w_peer(i), 1);
+    }
+    // pair: one arrive per epilogue WARP of either CTA (8 + 8); single CTA: one per epilogue thread
+    for (int t = 0; t < 2; ++t) { mbar_init(sm.a_ready(t), kCtas == 2 ? 16 : kGroupThreads); mbar_init(sm.acc_full(t), 1); }
     fence_mbar_init();
   }
   for (int j = tid; j < W; j += kPipeThreads) sm.wout()[j] = wout_src[j];
@@ -180,7 +193,31 @@ __device__ __forceinline__ void pipe_init(const PipeSmem& sm, int tid, int warp,
   }
   tc_fence_before();
   __syncthreads();
+  if (kCtas == 2) cluster_sync_all();    // the peer's barriers exist before any remote arrive / multicast commit
   tc_fence_after();
+}
+
+// An epilogue thread has finished (and fenced) its part of tile t's next A operand.
+template <int kCtas>
+__device__ __forceinline__ void arrive_a(uint32_t a_ready_addr, int lane) {
+  if (kCtas == 2) {                      // a_ready_addr = the LEADER's barrier (shared::cluster address)
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(a_ready_addr);
+  } else {
+    mbar_arrive(a_ready_addr);
+  }
+}
+
+template <int kCtas>
+__device__ __forceinline__ void pipe_teardown(uint32_t tmem, int warp) {
+  tc_fence_before();
+  __syncthreads();
+  if (kCtas == 2) {
+    cluster_sync_all();                  // the peer may still read this CTA's operands / arrive on its barriers
+    if (warp == 1) tmem_dealloc2<512>(tmem);
+  } else {
+    if (warp == 1) tmem_dealloc<512>(tmem);
+  }
 }
 
 __device__ __forceinline__ void epi_bar() {   // the 256 epilogue threads
@@ -317,7 +354,6 @@ struct FwdArgs {
   float* sigma;          // [P]
   uint8_t* acts;         // activation stash or null
   uint8_t* masks;        // relu bit masks or null
-  int share_w;           // weight chunks serve both tiles of a pair (1) or are fetched per tile (0)
 };
 
 // sin/cos(pi * 2^f * x).  2^f * x is exact in fp32, and so is its reduction r to [-1, 1]; sin(pi r) and
@@ -356,74 +392,108 @@ __device__ __forceinline__ void encode_row(uint32_t sA, int r, int half, const f
   }
 }
 
-template <int W, bool kStash>
+// Work units of the pipelined kernels.  Single CTA: a unit is a PAIR of tiles (X, Y), CTA b takes pairs b, b + grid, ...
+// CTA pair: a unit is a QUAD of tiles; cluster c takes quads c, c + clusters, ...; the CTA of rank r owns the pair
+// 2 q + r of the quad, and the leader's M = 256 MMAs cover X = (X_0, X_1), then Y = (Y_0, Y_1).
+template <int kCtas>
+struct Units {
+  int64_t first, stride, count;     // in units
+  uint32_t rank;
+  __device__ __forceinline__ Units(int64_t tiles) {
+    if (kCtas == 2) {
+      rank = cluster_ctarank();
+      first = blockIdx.x >> 1; stride = gridDim.x >> 1; count = (tiles + 3) / 4;
+    } else {
+      rank = 0; first = blockIdx.x; stride = gridDim.x; count = (tiles + 1) / 2;
+    }
+  }
+  __device__ __forceinline__ int64_t pair(int64_t unit) const { return kCtas == 2 ? 2 * unit + rank : unit; }
+};
+
+template <int W, bool kStash, int kCtas>
 __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-  const PipeSmem sm = carve(smem_raw);
+  using Smem = PipeSmem<kCtas>;
+  const Smem sm = carve<kCtas>(smem_raw);
   const Net net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pipe_init(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W, net);
+  pipe_init<kCtas>(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W, net);
   const uint32_t tmem = *sm.tmem_slot();
-  constexpr uint32_t nslots = kRingSlots;
-  const int64_t pairs = (a.tiles + 1) / 2;
+  constexpr uint32_t nslots = Smem::kSlots;
+  const Units<kCtas> units(a.tiles);
   constexpr int kNb = W / 64;
   constexpr uint32_t kChunkBytes = kNb * 8192;      // 64 K-rows x W out-features, fp16
+  constexpr uint32_t kMyBytes = kChunkBytes / kCtas;   // pair: this CTA stages column blocks [rank*kNb/2, (rank+1)*kNb/2)
 
   if (warp == 0) {
     // ---------------- producer (whole warp, converged): one contiguous bulk copy per 64-row weight chunk
-    const uint8_t* fimg = a.packed + packed_fwd_base(net);
+    const uint8_t* fimg = a.packed + packed_fwd_base(net) + units.rank * kMyBytes;
     uint32_t g = 0;
-    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+    for (int64_t u = units.first; u < units.count; u += units.stride) {
       for (int l = 0; l < net.L; ++l) {
         const int nch = (l == 0) ? 1 : kNb;
-        const int reps = a.share_w ? 1 : 2;      // chunks fetched once per tile PAIR, or once per tile
-        for (int t = 0; t < reps; ++t) {
+        for (int t = 0; t < 2; ++t) {            // every tile fetches its own chunks: X[all K] then Y[all K]
           for (int c = 0; c < nch; ++c, ++g) {
             const uint32_t slot = g % nslots, use = g / nslots;
             if (use > 0) mbar_wait_warp(sm.w_empty(slot), (use - 1) & 1);
-            mbar_expect_tx_warp(sm.w_full(slot), kChunkBytes);
-            bulk_g2s_warp(sm.ring(slot), fimg + fwd_off(net, l) + (int64_t)c * kChunkBytes, kChunkBytes, sm.w_full(slot));
+            mbar_expect_tx_warp(sm.w_full(slot), kMyBytes);
+            bulk_g2s_warp(sm.ring(slot), fimg + fwd_off(net, l) + (int64_t)c * kChunkBytes, kMyBytes, sm.w_full(slot));
           }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && units.rank == 0) {
     // ---------------- MMA issuer (whole warp, converged; one lane is elected inside each asm statement)
-    constexpr uint32_t idesc = make_idesc_f16(128, W, 0, 1);
+    constexpr uint32_t idesc = make_idesc_f16(128 * kCtas, W, 0, 1);
     uint32_t g = 0, par_a = 0u;
-    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+    for (int64_t u = units.first; u < units.count; u += units.stride) {
       for (int l = 0; l < net.L; ++l) {
         const int nch = (l == 0) ? 1 : kNb;
         const int ksteps0 = (l == 0) ? net.Epad / 16 : 4;   // layer 0 contracts over Epad (<= 64) features
-        // share_w: X[c0,c1] Y[c0,c1] X[c2,c3] Y[c2,c3], a chunk serves both tiles; else X[all] Y[all]
-        const int cstep = a.share_w ? 2 : nch;
-        for (int c0 = 0; c0 < nch; c0 += cstep) {
-          const int c1 = min(c0 + cstep, nch);
-          for (int t = 0; t < 2; ++t) {
-            if (c0 == 0) { mbar_wait_warp(sm.a_ready(t), par_a); tc_fence_after(); }
-            for (int c = c0; c < c1; ++c) {
-              const uint32_t gc = a.share_w ? g + c : g + t * nch + c, slot = gc % nslots;
-              if (t == 0 || !a.share_w) { mbar_wait_warp(sm.w_full(slot), (gc / nslots) & 1); tc_fence_after(); }
-              const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
-              const uint32_t release = (t == 1 || !a.share_w) ? sm.w_empty(slot) : 0u;
-              if (ksteps0 == 4) {
-                umma_f16_x4_warp<2, 128>(tmem + t * 256, desc_lo_sw128(sa, 16), desc_hi_sw128(1024),
-                                         desc_lo_sw128(sb, 8192), desc_hi_sw128(1024), idesc, c > 0 ? 1u : 0u, release);
-              } else {
-                for (int ks = 0; ks < ksteps0; ++ks) {
-                  const uint64_t ad = make_desc_sw128(sa + ks * 32, 16, 1024);
-                  const uint64_t bd = make_desc_sw128(sb + ks * 2048, 8192, 1024);
-                  umma_f16_warp(tmem + t * 256, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
-                }
-                if (release) umma_commit_warp(release);
+        for (int t = 0; t < 2; ++t) {
+          if (kCtas == 2) mbar_wait_cluster_warp(sm.a_ready(t), par_a); else mbar_wait_warp(sm.a_ready(t), par_a);
+          tc_fence_after();
+          for (int c = 0; c < nch; ++c, ++g) {
+            const uint32_t slot = g % nslots, par_w = (g / nslots) & 1;
+            mbar_wait_warp(sm.w_full(slot), par_w);
+            if (kCtas == 2) mbar_wait_cluster_warp(sm.w_peer(slot), par_w);
+            tc_fence_after();
+            const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
+            if (ksteps0 == 4) {
+              if (kCtas == 2)
+                umma2_f16_x4_warp<2, 128>(tmem + t * 256, desc_lo_sw128(sa, 16), desc_hi_sw128(1024), desc_lo_sw128(sb, 8192),
+                                          desc_hi_sw128(1024), idesc, c > 0 ? 1u : 0u, sm.w_empty(slot));
+              else
+                umma_f16_x4_warp<2, 128>(tmem + t * 256, desc_lo_sw128(sa, 16), desc_hi_sw128(1024), desc_lo_sw128(sb, 8192),
+                                         desc_hi_sw128(1024), idesc, c > 0 ? 1u : 0u, sm.w_empty(slot));
+            } else {
+              for (int ks = 0; ks < ksteps0; ++ks) {
+                const uint64_t ad = make_desc_sw128(sa + ks * 32, 16, 1024);
+                const uint64_t bd = make_desc_sw128(sb + ks * 2048, 8192, 1024);
+                if (kCtas == 2) umma2_f16_warp(tmem + t * 256, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                else umma_f16_warp(tmem + t * 256, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
               }
+              if (kCtas == 2) umma2_commit_warp(sm.w_empty(slot)); else umma_commit_warp(sm.w_empty(slot));
             }
-            if (c1 == nch) umma_commit_warp(sm.acc_full(t));
           }
+          if (kCtas == 2) umma2_commit_warp(sm.acc_full(t)); else umma_commit_warp(sm.acc_full(t));
         }
-        g += a.share_w ? nch : 2 * nch;
         par_a ^= 1u;
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- relay (peer CTA of a pair): tells the leader when THIS CTA's half of a slot has landed
+    uint32_t g = 0;
+    for (int64_t u = units.first; u < units.count; u += units.stride) {
+      for (int l = 0; l < net.L; ++l) {
+        const int n = 2 * ((l == 0) ? 1 : kNb);
+        for (int i = 0; i < n; ++i, ++g) {
+          const uint32_t slot = g % nslots;
+          mbar_wait_warp(sm.w_full(slot), (g / nslots) & 1);
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(sm.w_peer(slot), 0));
+          __syncwarp();
+        }
       }
     }
   } else {
@@ -442,14 +512,17 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
     const uint32_t acc_base = tmem + ((uint32_t)(q * 32) << 16) + h * kCols;
     uint32_t par_acc = 0;
     const bool pos_mode = a.pos != nullptr;
+    const uint32_t a_rdy[2] = {kCtas == 2 ? mapa_u32(sm.a_ready(0), 0) : sm.a_ready(0),
+                               kCtas == 2 ? mapa_u32(sm.a_ready(1), 0) : sm.a_ready(1)};
     auto row_index = [&](int64_t pair, int t) {
       int64_t gs = (2 * pair + t) * kTile + row;
       return gs < a.P ? gs : a.P - 1;
     };
     RowIn nxt[2];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) nxt[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, row_index(blockIdx.x, t));
-    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+    for (int t = 0; t < 2; ++t) nxt[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, row_index(units.pair(units.first), t));
+    for (int64_t u = units.first; u < units.count; u += units.stride) {
+      const int64_t pair = units.pair(u);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int64_t tile = 2 * pair + t;
@@ -462,9 +535,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
         }
         fence_async_smem();
         if (kStash && elected) bulk_wait_read0();
-        mbar_arrive(sm.a_ready(t));
-        if (pair + gridDim.x < pairs)
-          nxt[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, row_index(pair + gridDim.x, t));
+        arrive_a<kCtas>(a_rdy[t], lane);
+        if (u + units.stride < units.count)
+          nxt[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, row_index(units.pair(u + units.stride), t));
         if (kStash) {
           epi_bar();
           if (elected && active) { bulk_s2g(a.acts + tile * act_tile_bytes(net), sA, (uint32_t)kBlk); bulk_commit(); }
@@ -517,7 +590,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
           }
           if (!last || kStash) fence_async_smem();     // the image becomes visible to the MMA / bulk-copy engines
           if (kStash && elected) bulk_wait_read0();
-          if (!last) mbar_arrive(sm.a_ready(t));
+          if (!last) arrive_a<kCtas>(a_rdy[t], lane);
           else if (h == 1) part[row] = sig;
           if (kStash || last) epi_bar();
           if (last && h == 0 && in) a.sigma[gs] = sig + part[row];
@@ -531,9 +604,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
     }
     if (kStash && elected) bulk_wait0();
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem);
+  pipe_teardown<kCtas>(tmem, warp);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -551,68 +622,84 @@ struct BwdArgs {
   const float* d_sigma;
   const uint8_t* masks;
   uint8_t* dz;           // dZ stash [tiles][L][nb*16 KB]
-  int share_w;
   int stash_last;        // 1: the dZ_L image is stashed too; 0: wgrad rebuilds it from masks, d_sigma, w_out
   float gscale;
   float* d_pos;          // [P,3] or null
 };
 
-template <int W, bool kDx>
+template <int W, bool kDx, int kCtas>
 __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-  const PipeSmem sm = carve(smem_raw);
+  using Smem = PipeSmem<kCtas>;
+  const Smem sm = carve<kCtas>(smem_raw);
   const Net net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pipe_init(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W, net);
+  pipe_init<kCtas>(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W, net);
   const uint32_t tmem = *sm.tmem_slot();
-  constexpr uint32_t nslots = kRingSlots;
-  const int64_t pairs = (a.tiles + 1) / 2;
+  constexpr uint32_t nslots = Smem::kSlots;
+  const Units<kCtas> units(a.tiles);
   constexpr bool want_dx = kDx;            // d_pos requested: one more GEMM (layer 0) and the encoding backward
   const int l_lo = want_dx ? 0 : 1;        // GEMMs run for l = L-1 .. l_lo : dA_l = dZ_{l+1} * W_l
   constexpr int kNb = W / 64;              // contraction (out-features of layer l) in 64-wide chunks
 
   if (warp == 0) {
-    // ---------------- producer (whole warp, converged)
+    // ---------------- producer (whole warp, converged).  Pair: this CTA stages rows [rank*K_l/2, (rank+1)*K_l/2)
+    // (its half of the GEMM's N = in-features) of every column block.
     uint32_t g = 0;
-    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+    for (int64_t u = units.first; u < units.count; u += units.stride) {
       for (int l = net.L - 1; l >= l_lo; --l) {
         const uint32_t bytes = (uint32_t)layer_K(net, l) * 128u;     // one column block: K_l rows x 128 B
-        const int reps = a.share_w ? 1 : 2;
-        for (int t = 0; t < reps; ++t) {
+        const uint32_t mine = bytes / kCtas;
+        for (int t = 0; t < 2; ++t) {
           for (int c = 0; c < kNb; ++c, ++g) {
             const uint32_t slot = g % nslots, use = g / nslots;
             if (use > 0) mbar_wait_warp(sm.w_empty(slot), (use - 1) & 1);
-            mbar_expect_tx_warp(sm.w_full(slot), bytes);
-            bulk_g2s_warp(sm.ring(slot), a.packed + packed_off(net, l) + (int64_t)c * bytes, bytes, sm.w_full(slot));
+            mbar_expect_tx_warp(sm.w_full(slot), mine);
+            bulk_g2s_warp(sm.ring(slot), a.packed + packed_off(net, l) + (int64_t)c * bytes + units.rank * mine, mine,
+                          sm.w_full(slot));
           }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && units.rank == 0) {
     // ---------------- MMA issuer (whole warp, converged)
     uint32_t g = 0, par_a = 0u;
-    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+    for (int64_t u = units.first; u < units.count; u += units.stride) {
       for (int l = net.L - 1; l >= l_lo; --l) {
-        const uint32_t idesc = make_idesc_f16(128, layer_K(net, l), 0, 0);
-        const int cstep = a.share_w ? 2 : kNb;
-        for (int c0 = 0; c0 < kNb; c0 += cstep) {
-          const int c1 = min(c0 + cstep, kNb);
-          for (int t = 0; t < 2; ++t) {
-            if (c0 == 0) { mbar_wait_warp(sm.a_ready(t), par_a); tc_fence_after(); }
-            for (int c = c0; c < c1; ++c) {
-              const uint32_t gc = a.share_w ? g + c : g + t * kNb + c, slot = gc % nslots;
-              if (t == 0 || !a.share_w) { mbar_wait_warp(sm.w_full(slot), (gc / nslots) & 1); tc_fence_after(); }
-              const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
-              const uint32_t release = (t == 1 || !a.share_w) ? sm.w_empty(slot) : 0u;
+        const uint32_t idesc = make_idesc_f16(128 * kCtas, layer_K(net, l), 0, 0);
+        for (int t = 0; t < 2; ++t) {
+          if (kCtas == 2) mbar_wait_cluster_warp(sm.a_ready(t), par_a); else mbar_wait_warp(sm.a_ready(t), par_a);
+          tc_fence_after();
+          for (int c = 0; c < kNb; ++c, ++g) {
+            const uint32_t slot = g % nslots, par_w = (g / nslots) & 1;
+            mbar_wait_warp(sm.w_full(slot), par_w);
+            if (kCtas == 2) mbar_wait_cluster_warp(sm.w_peer(slot), par_w);
+            tc_fence_after();
+            const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
+            if (kCtas == 2)
+              umma2_f16_x4_warp<2, 2>(tmem + t * 256, desc_lo_sw128(sa, 16), desc_hi_sw128(1024), desc_lo_sw128(sb, 16),
+                                      desc_hi_sw128(1024), idesc, c > 0 ? 1u : 0u, sm.w_empty(slot));
+            else
               umma_f16_x4_warp<2, 2>(tmem + t * 256, desc_lo_sw128(sa, 16), desc_hi_sw128(1024), desc_lo_sw128(sb, 16),
-                                     desc_hi_sw128(1024), idesc, c > 0 ? 1u : 0u, release);
-            }
-            if (c1 == kNb) umma_commit_warp(sm.acc_full(t));
+                                     desc_hi_sw128(1024), idesc, c > 0 ? 1u : 0u, sm.w_empty(slot));
           }
+          if (kCtas == 2) umma2_commit_warp(sm.acc_full(t)); else umma_commit_warp(sm.acc_full(t));
         }
-        g += a.share_w ? kNb : 2 * kNb;
         par_a ^= 1u;
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- relay (peer CTA of a pair)
+    uint32_t g = 0;
+    for (int64_t u = units.first; u < units.count; u += units.stride) {
+      for (int l = net.L - 1; l >= l_lo; --l) {
+        for (int i = 0; i < 2 * kNb; ++i, ++g) {
+          const uint32_t slot = g % nslots;
+          mbar_wait_warp(sm.w_full(slot), (g / nslots) & 1);
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(sm.w_peer(slot), 0));
+          __syncwarp();
+        }
       }
     }
   } else {
@@ -644,8 +731,15 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
     uint32_t mw[2][kMw];      // masks of the NEXT step of each tile, fetched one step ahead
     float ds[2];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) { load_masks(2 * (int64_t)blockIdx.x + t, net.L - 1, mw[t]); ds[t] = load_ds(2 * (int64_t)blockIdx.x + t); }
-    for (int64_t pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+    for (int t = 0; t < 2; ++t) {
+      load_masks(2 * units.pair(units.first) + t, net.L - 1, mw[t]);
+      ds[t] = load_ds(2 * units.pair(units.first) + t);
+    }
+    const uint32_t a_rdy[2] = {kCtas == 2 ? mapa_u32(sm.a_ready(0), 0) : sm.a_ready(0),
+                               kCtas == 2 ? mapa_u32(sm.a_ready(1), 0) : sm.a_ready(1)};
+    const int64_t next_tile = 2 * (int64_t)gridDim.x;     // this thread's tile t of the NEXT unit (both variants)
+    for (int64_t u = units.first; u < units.count; u += units.stride) {
+      const int64_t pair = units.pair(u);
       RowIn rin[2];
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
@@ -675,12 +769,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
         if (net.L >= 2) {
           load_masks(tile, net.L - 2, mw[t]);      // for step (t, L-1)
         } else if (!want_dx) {                     // single hidden layer, no GEMM steps: next pair's first step
-          load_masks(tile + 2 * (int64_t)gridDim.x, net.L - 1, mw[t]);
-          ds[t] = load_ds(tile + 2 * (int64_t)gridDim.x);
+          load_masks(tile + next_tile, net.L - 1, mw[t]);
+          ds[t] = load_ds(tile + next_tile);
         }
         fence_async_smem();
         if (elected) bulk_wait_read0();
-        mbar_arrive(sm.a_ready(t));
+        arrive_a<kCtas>(a_rdy[t], lane);
         epi_bar();
         if (a.stash_last && elected && active) {
           bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(net.L - 1) * kNb * kBlk, stile, (uint32_t)(kNb * kBlk));
@@ -714,12 +808,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
             if (l >= 2) {
               load_masks(tile, l - 2, mw[t]);
             } else if (!want_dx) {
-              load_masks(tile + 2 * (int64_t)gridDim.x, net.L - 1, mw[t]);
-              ds[t] = load_ds(tile + 2 * (int64_t)gridDim.x);
+              load_masks(tile + next_tile, net.L - 1, mw[t]);
+              ds[t] = load_ds(tile + next_tile);
             }
             fence_async_smem();
             if (elected) bulk_wait_read0();
-            if (feeds_gemm) mbar_arrive(sm.a_ready(t));
+            if (feeds_gemm) arrive_a<kCtas>(a_rdy[t], lane);
             epi_bar();
             if (elected && active) {
               bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(l - 1) * kNb * kBlk, stile, (uint32_t)(kNb * kBlk));
@@ -759,8 +853,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
               }
             }
             tc_fence_before();
-            load_masks(tile + 2 * (int64_t)gridDim.x, net.L - 1, mw[t]);
-            ds[t] = load_ds(tile + 2 * (int64_t)gridDim.x);
+            load_masks(tile + next_tile, net.L - 1, mw[t]);
+            ds[t] = load_ds(tile + next_tile);
           }
         }
         par_acc ^= 1u;
@@ -768,22 +862,26 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
     }
     if (elected) bulk_wait0();
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem);
+  pipe_teardown<kCtas>(tmem, warp);
 }
 
 // ------------------------------------------------------------------------------------------
 // wgrad: dW_l[n,k] = sum_s dZ_{l+1}[s,n] * A_l[s,k], one CTA per (layer, range of tiles),
-// accumulators resident in TMEM over the whole range, operands streamed in half tiles.
+// accumulators resident in TMEM over the whole range, operands streamed in half tiles (64 samples).
+//  * CTAs of the LAST hidden layer do not read dZ_L: it is relu'(Z_L) * d_sigma * w_out - a bit mask
+//    times a rank-1 matrix - and eight otherwise idle warps rebuild its half-tile image in shared
+//    memory from the mask words, d_sigma and w_out while the producer streams A_{L-1}
+//    (-64 KB/tile written by dgrad, -64 KB/tile read here).
+//  * CTAs of layer 0 (the lightest stream: A_0 is 16 KB per tile) also stream A_L and accumulate the
+//    OUTPUT layer's gradient dW_out[n] = sum_s d_sigma[s] * A_L[s,n] on the CUDA cores of those same
+//    warps, reduced deterministically like every other partial (round 1: a separate 0.5 ms kernel that
+//    ended in atomics).
 struct WgradArgs {
   Net net;
   const uint8_t* acts;
   const uint8_t* dz;
   int64_t tiles;
-  float* partials;           // [items][K_l*N_l]
-  // dZ_L = relu'(Z_L) * d_sigma * w_out is rank-1 times a bit mask: the CTAs of layer L-1 rebuild its
-  // image in shared memory from these instead of reading 64 KB/tile that dgrad would have to write.
+  float* partials;           // [items][K_l*N_l] per layer, then [items of layer 0][W] for dW_out
   const uint8_t* masks;
   const float* d_sigma;
   const float* wout;         // [W] fp32 values of the fp16-rounded output weights (packed image)
@@ -791,13 +889,14 @@ struct WgradArgs {
   int64_t P;
   int gen_last;              // 1: CTAs of layer L-1 rebuild dZ_L; 0: they read dgrad's stash of it
   int item_begin[9];         // first item of each layer (prefix), item_begin[L] = total
-  int64_t part_off[9];       // float offset of each layer's first partial
+  int64_t part_off[10];      // float offset of each layer's first partial; [L] = dW_out partials; [L+1] = total
 };
 
 constexpr int kWgStages = 3;
-constexpr int kWgStageBytes = 65536;    // 64 samples: A half (<= 32 KB) | dZ half (<= 32 KB)
-constexpr int kWgThreads = 320;     // warp 0 producer, warp 1 MMA, warps 2-5 epilogue (+ generators), warps 6-9 generators
-constexpr int kWgGen = 256;         // generator threads
+constexpr int kWgThreads = 320;     // warp 0 producer, warp 1 MMA, warps 2-9 helpers (generate dZ_L / accumulate dW_out), 2-5 epilogue
+// stage of a layer > 0 CTA:  X = A_l half (32 KB) | Y = dZ_{l+1} half (32 KB)
+// stage of a layer-0 CTA:    X = A_0 half (8 KB)  | Y = dZ_1 half (32 KB) | Z = A_L half (32 KB)
+constexpr int kWgStageBytes = 73728;
 constexpr int kWgSmem = 1024 + kWgStages * kWgStageBytes + 2048;
 
 __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArgs a) {
@@ -824,9 +923,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
   const uint32_t done_bar = smem_u32(&bars[2 * kWgStages]);
 
   const bool gen_y = a.gen_last && (l == net.L - 1);   // this CTA rebuilds dZ_L instead of loading it
+  const bool do_out = (l == 0);                        // this CTA also streams A_L and accumulates dW_out
+  // stage geometry ("X" = A_l half image, "Y" = dZ_{l+1} half image, "Z" = A_L half image)
+  const int nbA = (l == 0) ? 1 : net.nb;          // column blocks of A_l
+  const int nbY = net.nb;
+  const uint32_t offY = (l == 0) ? 8192u : 32768u, offZ = 40960u;
+  const uint32_t bytesA = (uint32_t)nbA * 8192, bytesY = (uint32_t)nbY * 8192;
   if (warp == 0) tmem_alloc<512>(smem_u32(s_tmem));
   if (tid == 32) {
-    for (int s = 0; s < kWgStages; ++s) { mbar_init(full_bar(s), gen_y ? 2 : 1); mbar_init(empty_bar(s), 1); }
+    // full: the producer's expect_tx arrive (+ the helpers' arrive when they write Y); empty: the MMA commit
+    // (+ the helpers' arrive when they read Z)
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(full_bar(s), gen_y ? 2 : 1); mbar_init(empty_bar(s), do_out ? 2 : 1); }
     mbar_init(done_bar, 1);
     fence_mbar_init();
   }
@@ -836,11 +943,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  // per-stage operand geometry.  "X" = A_l image (64-sample half), "Y" = dZ_{l+1} image half.
-  const int nbA = (l == 0) ? 1 : net.nb;          // column blocks of A_l
-  const int nbY = net.nb;
-  const uint32_t bytesA = (uint32_t)nbA * 8192, bytesY = (uint32_t)nbY * 8192;
   const int64_t actA_off = (l == 0) ? 0 : (int64_t)kBlk + (int64_t)(l - 1) * net.nb * kBlk;
+  const int64_t actL_off = (int64_t)kBlk + (int64_t)(net.L - 1) * net.nb * kBlk;
   const int64_t dzY_off = (int64_t)l * net.nb * kBlk;
   const int64_t n_half = (t1 - t0) * 2;
 
@@ -852,13 +956,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
       mbar_wait_warp(empty_bar(s), ph ^ 1u);
       const int64_t tile = t0 + (i >> 1);
       const int hf = (int)(i & 1);
-      const uint32_t dstA = smem_u32(base + s * kWgStageBytes), dstY = dstA + 32768;
-      mbar_expect_tx_warp(full_bar(s), gen_y ? bytesA : bytesA + bytesY);
-      const uint8_t* srcA = a.acts + tile * act_tile_bytes(net) + actA_off + hf * 8192;
+      const uint32_t dstA = smem_u32(base + s * kWgStageBytes), dstY = dstA + offY, dstZ = dstA + offZ;
+      mbar_expect_tx_warp(full_bar(s), bytesA + (gen_y ? 0u : bytesY) + (do_out ? bytesY : 0u));
+      const uint8_t* tile_acts = a.acts + tile * act_tile_bytes(net);
+      const uint8_t* srcA = tile_acts + actA_off + hf * 8192;
       const uint8_t* srcY = a.dz + tile * dz_tile_bytes(net) + dzY_off + hf * 8192;
+      const uint8_t* srcZ = tile_acts + actL_off + hf * 8192;
       for (int cb = 0; cb < nbA; ++cb) bulk_g2s_warp(dstA + cb * 8192, srcA + (int64_t)cb * kBlk, 8192, full_bar(s));
       if (!gen_y)
         for (int cb = 0; cb < nbY; ++cb) bulk_g2s_warp(dstY + cb * 8192, srcY + (int64_t)cb * kBlk, 8192, full_bar(s));
+      if (do_out)
+        for (int cb = 0; cb < nbY; ++cb) bulk_g2s_warp(dstZ + cb * 8192, srcZ + (int64_t)cb * kBlk, 8192, full_bar(s));
     }
   } else if (warp == 1) {
     // ---- MMA issuer (whole warp, converged).  Both operands MN-major: 64-element MN blocks 8 KB apart
@@ -872,7 +980,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
       const uint32_t ph = (uint32_t)((i / kWgStages) & 1);
       mbar_wait_warp(full_bar(s), ph);
       tc_fence_after();
-      const uint32_t sX = smem_u32(base + s * kWgStageBytes), sY = sX + 32768;
+      const uint32_t sX = smem_u32(base + s * kWgStageBytes), sY = sX + offY;
       for (int mb = 0; mb < n_mblk; ++mb) {
         const uint32_t aaddr = (swapped ? sY : sX) + mb * 2 * 8192;
         const uint32_t baddr = (swapped ? sX : sY);
@@ -884,18 +992,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
     umma_commit_warp(done_bar);
   }
   __syncwarp();
-  if (warp >= 2 && gen_y) {
-    // ---- generators (8 warps; four of them are the epilogue warps, idle during the main loop):
-    // thread = (row of the 64-sample half tile, quarter of the columns)
+  float out_acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) out_acc[k] = 0.f;
+  if (warp >= 2 && (gen_y || do_out)) {
+    // ---- helpers (8 warps; four of them are the epilogue warps, idle during the main loop)
     const int g = tid - 64;                       // 0..255
+    // (a) generator mapping: thread = (row of the 64-sample half tile, quarter of the columns)
     const int r = g >> 2, qc = g & 3;
     const int cpt = net.W / 4;                    // columns per thread: 64 (W=256) or 32 (W=128)
     const int mwords = net.W / 32;
-    // inputs of a stage (d_sigma of the row, its mask words) are fetched two stages ahead: their
-    // latency under a saturated HBM is longer than a stage
-    auto fetch = [&](int64_t i, float& ds, uint32_t& m0, uint32_t& m1) {
+    // (b) dW_out mapping: thread = (16-byte chunk j of a row = 8 columns, rows rg, rg+8, ...): the lanes of a warp
+    // read the 32 chunks of ONE row (conflict-free 128-bit loads), the swizzle term (r & 7) = rg is per-thread constant
+    const int oj = g & 31, rg = g >> 5;
+    const bool out_on = do_out && (oj < net.nb * 8);
+    const uint32_t out_off = (uint32_t)(oj >> 3) * 8192u + ((uint32_t)((oj & 7) ^ rg) << 4);
+    // inputs of a stage are fetched two stages ahead: their latency under a saturated HBM is longer than a stage
+    auto fetch_gen = [&](int64_t i, float& ds, uint32_t& m0, uint32_t& m1) {
       ds = 0.f; m0 = 0u; m1 = 0u;
-      if (i >= n_half) return;
+      if (!gen_y || i >= n_half) return;
       const int64_t tile = t0 + (i >> 1);
       const int row = (int)(i & 1) * 64 + r;
       const int64_t gs = tile * kTile + row;
@@ -905,45 +1020,101 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
       m0 = __float_as_uint(ldg_now(mrow));
       if (cpt > 32) m1 = __float_as_uint(ldg_now(mrow + 1));
     };
-    float ds_a, ds_b;
+    auto fetch_out = [&](int64_t i, float (&dso)[8]) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dso[k] = 0.f;
+      if (!do_out || i >= n_half) return;
+      const int64_t gs0 = (t0 + (i >> 1)) * kTile + (int64_t)(i & 1) * 64 + rg;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if (gs0 + 8 * k < a.P) dso[k] = ldg_now(a.d_sigma + gs0 + 8 * k);
+    };
+    float ds_a, ds_b, dso_a[8];
     uint32_t ma0, ma1, mb0, mb1;
-    fetch(0, ds_a, ma0, ma1);
-    fetch(1, ds_b, mb0, mb1);
+    fetch_gen(0, ds_a, ma0, ma1);
+    fetch_gen(1, ds_b, mb0, mb1);
+    fetch_out(0, dso_a);
     for (int64_t i = 0; i < n_half; ++i) {
       const int s = (int)(i % kWgStages);
       const uint32_t ph = (uint32_t)((i / kWgStages) & 1);
-      const float ds = ds_a;
-      const uint32_t mw0 = ma0, mw1 = ma1;
-      ds_a = ds_b; ma0 = mb0; ma1 = mb1;
-      fetch(i + 2, ds_b, mb0, mb1);
-      mbar_wait(empty_bar(s), ph ^ 1u);
-      const uint32_t sY = smem_u32(base + s * kWgStageBytes) + 32768 + (uint32_t)r * 128;
-      const uint32_t xs = (uint32_t)(r & 7) << 4;
+      const uint32_t stage = smem_u32(base + s * kWgStageBytes);
+      if (gen_y) {
+        const float ds = ds_a;
+        const uint32_t mw0 = ma0, mw1 = ma1;
+        ds_a = ds_b; ma0 = mb0; ma1 = mb1;
+        fetch_gen(i + 2, ds_b, mb0, mb1);
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t srow = stage + offY + (uint32_t)r * 128u;
+        const uint32_t xs = (uint32_t)(r & 7) << 4;
 #pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        if (it * 32 < cpt) {
-          const uint32_t bits = it == 0 ? mw0 : mw1;
-          const int col0 = qc * cpt + it * 32;
+        for (int it = 0; it < 2; ++it) {
+          if (it * 32 < cpt) {
+            const uint32_t bits = it == 0 ? mw0 : mw1;
+            const int col0 = qc * cpt + it * 32;
+            uint32_t hh[16];
+#define LONER_GEN(P)                                                                      \
+  {                                                                                       \
+    const float2 w2 = *reinterpret_cast<const float2*>(s_wout + col0 + 2 * P);            \
+    hh[P] = cvt_sat_h2(ds * w2.x, ds * w2.y) & half2_mask<P>(bits);                       \
+  }
+            LONER_GEN(0) LONER_GEN(1) LONER_GEN(2) LONER_GEN(3) LONER_GEN(4) LONER_GEN(5) LONER_GEN(6) LONER_GEN(7)
+            LONER_GEN(8) LONER_GEN(9) LONER_GEN(10) LONER_GEN(11) LONER_GEN(12) LONER_GEN(13) LONER_GEN(14) LONER_GEN(15)
+#undef LONER_GEN
+            // same image as dgrad's store32, with 8 KB (64-row) column blocks
+            const uint32_t cb_off = (uint32_t)(col0 >> 6) * 8192u;
+            const uint32_t j0 = ((uint32_t)(col0 & 63) >> 3) << 4;
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int i0 = ch * 8 + 2 * e;
-              const int pr = ch * 4 + e;                   // pair index inside the 32-column mask word
-              const float2 w2 = *reinterpret_cast<const float2*>(s_wout + col0 + i0);
-              const float g0 = ((bits >> pr) & 1u) ? ds * w2.x : 0.f;
-              const float g1 = ((bits >> (16 + pr)) & 1u) ? ds * w2.y : 0.f;
-              w[e] = cvt_sat_h2(g0, g1);
-            }
-            const int c0 = col0 + ch * 8;
-            sts128(sY + (uint32_t)(c0 >> 6) * 8192u + ((((uint32_t)(c0 & 63) >> 3) << 4) ^ xs), w[0], w[1], w[2], w[3]);
+            for (int k = 0; k < 4; ++k)
+              sts128(srow + cb_off + ((j0 + 16u * k) ^ xs), hh[4 * k], hh[4 * k + 1], hh[4 * k + 2], hh[4 * k + 3]);
           }
         }
+        fence_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // all helper threads have written and fenced
+        if (g == 0) mbar_arrive(full_bar(s));
       }
-      fence_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");      // all generator threads have written and fenced
-      if (g == 0) mbar_arrive(full_bar(s));
+      if (do_out) {
+        float dso[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dso[k] = dso_a[k];
+        fetch_out(i + 1, dso_a);
+        mbar_wait(full_bar(s), ph);                         // the A_L half has landed
+        if (out_on) {
+          const uint32_t zrow = stage + offZ + out_off + (uint32_t)rg * 128u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(zrow + (uint32_t)k * 1024u));
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w0));
+            const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&w1));
+            const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w2));
+            const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&w3));
+            out_acc[0] = fmaf(dso[k], f0.x, out_acc[0]); out_acc[1] = fmaf(dso[k], f0.y, out_acc[1]);
+            out_acc[2] = fmaf(dso[k], f1.x, out_acc[2]); out_acc[3] = fmaf(dso[k], f1.y, out_acc[3]);
+            out_acc[4] = fmaf(dso[k], f2.x, out_acc[4]); out_acc[5] = fmaf(dso[k], f2.y, out_acc[5]);
+            out_acc[6] = fmaf(dso[k], f3.x, out_acc[6]); out_acc[7] = fmaf(dso[k], f3.y, out_acc[7]);
+          }
+        }
+        __syncwarp();
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // every helper has read its part of Z
+        if (g == 0) mbar_arrive(empty_bar(s));              // second arrival: the MMA commit is the first
+      }
+    }
+  }
+  if (warp >= 2 && do_out) {
+    // ---- dW_out partial of this CTA: sum the eight row groups through the (now idle) first stage
+    mbar_wait(done_bar, 0);                                 // all MMAs (the last readers of the stages) are done
+    const int g = tid - 64;
+    const int oj = g & 31, rg = g >> 5;
+    float* red = reinterpret_cast<float*>(base);            // [8][W]
+    if (oj < net.nb * 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[rg * net.W + oj * 8 + k] = out_acc[k];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (g < net.W) {
+      float sum = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sum += red[q * net.W + g];
+      a.partials[a.part_off[net.L] + (int64_t)item * net.W + g] = (n_half == 0) ? 0.f : sum;
     }
   }
   if (warp >= 2 && warp < 6) {
@@ -980,10 +1151,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-// d_params += (sum over a layer's items of its partials) / gscale
+// d_params += (sum over a layer's items of its partials) / gscale; blockIdx.y == L: the output layer's row
 __global__ void wgrad_reduce_kernel(Net net, const float* __restrict__ partials, WgradArgs w, float inv_gscale,
                                     float* __restrict__ d_params) {
   const int l = blockIdx.y;
+  if (l == net.L) {     // dW_out: one partial [W] per item of layer 0; d_sigma entered unscaled
+    const int n_items = w.item_begin[1] - w.item_begin[0];
+    const float* p = partials + w.part_off[net.L];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < net.Wr; c += gridDim.x * blockDim.x) {
+      float s = 0.f;
+      for (int g = 0; g < n_items; ++g) s += p[(int64_t)g * net.W + c];
+      d_params[param_off(net, net.L) + c] += s;
+    }
+    return;
+  }
   const int K = layer_K(net, l), Kr = layer_Kr(net, l);
   const int64_t sz = (int64_t)K * net.W;
   const int n_items = w.item_begin[l + 1] - w.item_begin[l];
@@ -997,65 +1178,10 @@ __global__ void wgrad_reduce_kernel(Net net, const float* __restrict__ partials,
   }
 }
 
-// dW_out[j] = sum_s d_sigma[s] * A_L[s,j]   (row 0 of the padded [16, W] output matrix).
-// HBM-streaming: a warp reads 4 image rows (4 x 128 B) per instruction; lane = (row%4, 16-byte
-// logical chunk j), so each lane owns 8 fixed columns per column block.
-__global__ void __launch_bounds__(256) dwout_kernel(Net net, const uint8_t* __restrict__ acts,
-                                                    const float* __restrict__ d_sigma, int64_t P, int64_t tiles,
-                                                    float* __restrict__ d_params) {
-  __shared__ float red[256];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t gw = (int64_t)blockIdx.x * 8 + warp, nw = (int64_t)gridDim.x * 8;
-  const int j = lane & 7, rsub = lane >> 3;
-  float acc[4][8];
-#pragma unroll
-  for (int cb = 0; cb < 4; ++cb)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[cb][i] = 0.f;
-  const int64_t aL = (int64_t)kBlk + (int64_t)(net.L - 1) * net.nb * kBlk;
-  for (int64_t tile = gw; tile < tiles; tile += nw) {
-    const uint8_t* img = acts + tile * act_tile_bytes(net) + aL;
-#pragma unroll 8
-    for (int r0 = 0; r0 < kTile; r0 += 4) {
-      const int r = r0 + rsub;
-      const int64_t gs = tile * kTile + r;
-      const float ds = gs < P ? __ldg(d_sigma + gs) : 0.f;
-      const int slot = (j ^ (r & 7)) * 16;
-#pragma unroll
-      for (int cb = 0; cb < 4; ++cb) {
-        if (cb < net.nb) {
-          const uint4 v = *reinterpret_cast<const uint4*>(img + cb * kBlk + r * 128 + slot);
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-            acc[cb][2 * i] = fmaf(ds, f.x, acc[cb][2 * i]);
-            acc[cb][2 * i + 1] = fmaf(ds, f.y, acc[cb][2 * i + 1]);
-          }
-        }
-      }
-    }
-  }
-  for (int c = threadIdx.x; c < 256; c += blockDim.x) red[c] = 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int cb = 0; cb < 4; ++cb)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float v = acc[cb][i];
-      v += __shfl_xor_sync(kFull, v, 8);
-      v += __shfl_xor_sync(kFull, v, 16);
-      if (rsub == 0 && cb < net.nb) atomicAdd(&red[cb * 64 + j * 8 + i], v);
-    }
-  __syncthreads();
-  for (int c = threadIdx.x; c < net.Wr; c += blockDim.x)
-    if (red[c] != 0.f) atomicAdd(d_params + param_off(net, net.L) + c, red[c]);
-}
-
 // ------------------------------------------------------------------------------------------
 struct WgradPlan {
   int item_begin[9];
-  int64_t part_off[9];
+  int64_t part_off[10];
   int total_items;
   int64_t total_floats;
 };
@@ -1070,17 +1196,24 @@ inline int device_sm_count() {
   return sms;
 }
 
-inline WgradPlan plan_wgrad(const Net& net) {
+inline WgradPlan plan_wgrad(const Net& net, bool gen_last) {
   // The kernel is HBM-bound (it streams the A_l and dZ_{l+1} images once): give every layer a share
-  // of the SMs proportional to the BYTES it reads per tile, not to its flops.
+  // of the SMs proportional to the BYTES it reads per tile, not to its flops.  In 8 KB column blocks per
+  // half tile: layer 0 reads A_0 (1) + dZ_1 (nb) + A_L (nb, for dW_out); a middle layer A_l + dZ_{l+1} (2 nb);
+  // the last layer only A_{L-1} when it rebuilds dZ_L (weighted 1.25 nb: its helper warps pace it slightly).
   const int sms = device_sm_count();
   WgradPlan p;
-  double total = 0;
-  for (int l = 0; l < net.L; ++l) total += (double)((l == 0 ? 1 : net.nb) + net.nb);
+  double wgt[8], total = 0;
+  for (int l = 0; l < net.L; ++l) {
+    const bool last = (l == net.L - 1);
+    double w = (l == 0 ? 1.0 : (double)net.nb) + ((gen_last && last) ? 0.25 * net.nb : (double)net.nb) + (l == 0 ? (double)net.nb : 0.0);
+    wgt[l] = w;
+    total += w;
+  }
   int used = 0;
   int64_t off = 0;
   for (int l = 0; l < net.L; ++l) {
-    int g = (int)((double)sms * ((l == 0 ? 1 : net.nb) + net.nb) / total);
+    int g = (int)((double)sms * wgt[l] / total);
     if (g < 1) g = 1;
     p.item_begin[l] = used;
     p.part_off[l] = off;
@@ -1088,7 +1221,9 @@ inline WgradPlan plan_wgrad(const Net& net) {
     off += (int64_t)g * layer_K(net, l) * net.W;
   }
   p.item_begin[net.L] = used;
-  p.part_off[net.L] = off;
+  p.part_off[net.L] = off;                                   // dW_out partials: one [W] row per item of layer 0
+  off += (int64_t)(p.item_begin[1] - p.item_begin[0]) * net.W;
+  p.part_off[net.L + 1] = off;
   p.total_items = used;
   p.total_floats = off;
   return p;
@@ -1110,20 +1245,33 @@ extern "C" int64_t loner_mlp_packed_bytes(const loner_net_t* n) {
   return packed_total(net);
 }
 static inline int64_t n_tiles(int64_t P) { return (P + kTile - 1) / kTile; }
-// dZ_L = relu'(Z_L) * d_sigma * w_out can be rebuilt inside wgrad instead of travelling through HBM
-// (LONER_WGRAD_GEN=1); measured slower than reading dgrad's stash, so it is off by default.
-// MMA order of the pipelined kernels.  Default: every tile fetches its own weight chunks (X[all] Y[all]);
-// LONER_MMA_ORDER=pair shares each chunk between the two tiles of a pair (X[c0,c1] Y[c0,c1] X[c2,c3]
-// Y[c2,c3]): half the L2->SM weight traffic, but a tile's epilogue then overlaps only a quarter of the
-// other tile's tensor work.  A/B on the GPU (tests/gpu_ab.py, C2): training forward 2.61 vs 2.75 ms,
-// dgrad 1.90 vs 2.24 ms, inference 1.59 vs 1.57 ms.
-static inline int share_weights() {
-  static const int v = [] { const char* m = getenv("LONER_MMA_ORDER"); return (m && m[0] == 'p') ? 1 : 0; }();
-  return v;
-}
-static inline bool wgrad_rebuilds_last() {
-  static const int on = [] { const char* m = getenv("LONER_WGRAD_GEN"); return (m && m[0] == '1') ? 1 : 0; }();
-  return on != 0;
+// Kernel variants are selected by loner_net_t.flags (include/loner_b200.h), never by the environment.
+static inline int pipe_ctas(const Net& net) { return (net.flags & LONER_NET_SINGLE_CTA) ? 1 : 2; }
+static inline bool wgrad_rebuilds_last(const Net& net) { return (net.flags & LONER_NET_STASH_DZL) == 0; }
+
+// Launch of a pipelined kernel: one CTA per SM, as CTA pairs (clusters of 2 on one TPC) or single CTAs.
+template <class Kern, class Args>
+static void launch_pipe(Kern kern, const Args& args, int64_t tiles, int ctas, cudaStream_t st) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem);
+  const int sms = device_sm_count();
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kPipeThreads);
+  cfg.dynamicSmemBytes = kPipeSmem;
+  cfg.stream = st;
+  if (ctas == 2) {
+    const int64_t quads = (tiles + 3) / 4;
+    const int64_t clusters = quads < sms / 2 ? quads : sms / 2;
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    const int64_t pairs = (tiles + 1) / 2;
+    cfg.gridDim = dim3((unsigned)(pairs < sms ? pairs : sms));
+  }
+  cudaLaunchKernelEx(&cfg, kern, args);
 }
 extern "C" int64_t loner_mlp_act_bytes(const loner_net_t* n, int64_t P) {
   Net net;
@@ -1133,7 +1281,7 @@ extern "C" int64_t loner_mlp_act_bytes(const loner_net_t* n, int64_t P) {
 extern "C" int64_t loner_mlp_bwd_scratch_bytes(const loner_net_t* n, int64_t P) {
   Net net;
   if (!net_from(n, net) || P < 0) return -1;
-  const WgradPlan p = plan_wgrad(net);
+  const WgradPlan p = plan_wgrad(net, wgrad_rebuilds_last(net));
   return n_tiles(P) * dz_tile_bytes(net) + p.total_floats * 4;
 }
 
@@ -1158,16 +1306,13 @@ extern "C" int loner_mlp_fwd(const loner_net_t* n, const void* packed, const flo
   a.s_shift = (S > 0 && (S & (S - 1)) == 0) ? __builtin_ctz((unsigned)S) : -1;
   a.tiles = n_tiles(P); a.sigma = sigma; a.acts = (uint8_t*)acts;
   a.masks = acts ? (uint8_t*)acts + a.tiles * act_tile_bytes(net) : nullptr;
-  a.share_w = share_weights();
-  const int sms = device_sm_count();
-  const int64_t pairs = (a.tiles + 1) / 2;
-  const unsigned grid = (unsigned)(pairs < sms ? pairs : sms);
-  auto launch = [&](auto kern) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem);
-    kern<<<grid, kPipeThreads, kPipeSmem, (cudaStream_t)stream>>>(a);
-  };
-  if (net.W == 256) { if (acts) launch(mlp_fwd_kernel<256, true>); else launch(mlp_fwd_kernel<256, false>); }
-  else              { if (acts) launch(mlp_fwd_kernel<128, true>); else launch(mlp_fwd_kernel<128, false>); }
+  const int ctas = pipe_ctas(net);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LONER_FWD(W_, S_) \
+  (ctas == 2 ? launch_pipe(mlp_fwd_kernel<W_, S_, 2>, a, a.tiles, 2, st) : launch_pipe(mlp_fwd_kernel<W_, S_, 1>, a, a.tiles, 1, st))
+  if (net.W == 256) { if (acts) LONER_FWD(256, true); else LONER_FWD(256, false); }
+  else              { if (acts) LONER_FWD(128, true); else LONER_FWD(128, false); }
+#undef LONER_FWD
   LONER_CHECK_LAUNCH();
   return LONER_OK;
 }
@@ -1187,21 +1332,19 @@ extern "C" int loner_mlp_dgrad(const loner_net_t* n, const void* packed, const f
   if (P == 0) return LONER_OK;
   if (!d_sigma || !(grad_scale > 0.f) || (d_pos && !pos && (!rays || !z_vals || S <= 0))) return LONER_E_BAD_ARG;
   const int64_t tiles = n_tiles(P);
-  const int sms = device_sm_count();
   BwdArgs b;
   b.net = net; b.packed = (const uint8_t*)packed; b.pos = pos; b.rays = rays; b.z = z_vals; b.S = S; b.P = P;
   b.s_shift = (S > 0 && (S & (S - 1)) == 0) ? __builtin_ctz((unsigned)S) : -1;
   b.tiles = tiles; b.d_sigma = d_sigma; b.masks = (const uint8_t*)acts + tiles * act_tile_bytes(net);
   b.dz = (uint8_t*)scratch; b.gscale = grad_scale; b.d_pos = d_pos;
-  b.stash_last = wgrad_rebuilds_last() ? 0 : 1;
-  b.share_w = share_weights();
-  const int64_t pairs = (tiles + 1) / 2;
-  auto launch = [&](auto kern) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem);
-    kern<<<(unsigned)(pairs < sms ? pairs : sms), kPipeThreads, kPipeSmem, (cudaStream_t)stream>>>(b);
-  };
-  if (net.W == 256) { if (d_pos) launch(mlp_dgrad_kernel<256, true>); else launch(mlp_dgrad_kernel<256, false>); }
-  else              { if (d_pos) launch(mlp_dgrad_kernel<128, true>); else launch(mlp_dgrad_kernel<128, false>); }
+  b.stash_last = wgrad_rebuilds_last(net) ? 0 : 1;
+  const int ctas = pipe_ctas(net);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LONER_DGRAD(W_, D_) \
+  (ctas == 2 ? launch_pipe(mlp_dgrad_kernel<W_, D_, 2>, b, tiles, 2, st) : launch_pipe(mlp_dgrad_kernel<W_, D_, 1>, b, tiles, 1, st))
+  if (net.W == 256) { if (d_pos) LONER_DGRAD(256, true); else LONER_DGRAD(256, false); }
+  else              { if (d_pos) LONER_DGRAD(128, true); else LONER_DGRAD(128, false); }
+#undef LONER_DGRAD
   LONER_CHECK_LAUNCH();
   return LONER_OK;
 }
@@ -1214,23 +1357,21 @@ extern "C" int loner_mlp_wgrad(const loner_net_t* n, const void* packed, int64_t
   if (P == 0) return LONER_OK;
   if (!d_sigma || !d_params || !(grad_scale > 0.f)) return LONER_E_BAD_ARG;
   const int64_t tiles = n_tiles(P);
-  const int sms = device_sm_count();
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* dz = (uint8_t*)scratch;
   float* partials = (float*)(dz + tiles * dz_tile_bytes(net));
-  const WgradPlan plan = plan_wgrad(net);
+  const WgradPlan plan = plan_wgrad(net, wgrad_rebuilds_last(net));
   WgradArgs w;
   w.net = net; w.acts = (const uint8_t*)acts; w.dz = dz; w.tiles = tiles; w.partials = partials;
-  w.masks = (const uint8_t*)acts + tiles * act_tile_bytes(net); w.d_sigma = d_sigma; w.gen_last = wgrad_rebuilds_last() ? 1 : 0;
+  w.masks = (const uint8_t*)acts + tiles * act_tile_bytes(net); w.d_sigma = d_sigma; w.gen_last = wgrad_rebuilds_last(net) ? 1 : 0;
   w.wout = reinterpret_cast<const float*>((const uint8_t*)packed + packed_wout_off(net)); w.gscale = grad_scale; w.P = P;
-  for (int i = 0; i <= net.L; ++i) { w.item_begin[i] = plan.item_begin[i]; w.part_off[i] = plan.part_off[i]; }
+  for (int i = 0; i <= net.L; ++i) w.item_begin[i] = plan.item_begin[i];
+  for (int i = 0; i <= net.L + 1; ++i) w.part_off[i] = plan.part_off[i];
   cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
   mlp_wgrad_kernel<<<(unsigned)plan.total_items, kWgThreads, kWgSmem, st>>>(w);
   LONER_CHECK_LAUNCH();
-  dim3 rgrid(64, net.L);
+  dim3 rgrid(64, net.L + 1);
   wgrad_reduce_kernel<<<rgrid, 256, 0, st>>>(net, partials, w, 1.0f / grad_scale, d_params);
-  LONER_CHECK_LAUNCH();
-  dwout_kernel<<<(unsigned)(sms * 4), 256, 0, st>>>(net, (const uint8_t*)acts, d_sigma, P, tiles, d_params);
   LONER_CHECK_LAUNCH();
   return LONER_OK;
 }

@@ -196,6 +196,114 @@ __device__ __forceinline__ void umma_f16_x4_warp(uint32_t d_tmem, uint32_t a_lo,
       : "memory");
 }
 
+// ------------------------------------------------------------------ CTA pairs (cta_group::2)
+// Two CTAs of a cluster (same TPC) execute ONE M=256 MMA: each holds its 128 rows of A, HALF of B (N/2
+// columns) and the 128 x N accumulator rows of its own tile in its own TMEM.  Only the leader (cluster rank 0)
+// issues; barriers of the peer are reached with mapa + shared::cluster arrives, MMA completion is multicast.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta_rank) {   // this CTA's smem address -> rank's
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // release at cluster scope
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 26); ++it)
+    if (mbar_try_wait_cluster(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_cluster_warp(uint32_t bar, uint32_t parity) {
+  mbar_wait_cluster(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_result_addr) {   // executed by one warp of EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result_addr), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// leader only, converged warp: one M=256 MMA over both CTAs
+__device__ __forceinline__ void umma2_f16_warp(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the SAME shared-memory offset in both CTAs when all prior MMAs of this thread are done
+__device__ __forceinline__ void umma2_commit_warp(uint32_t bar) {
+  asm volatile("{\n\t.reg .pred e;\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\telect.sync _|e, 0xffffffff;\n\t"
+               "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}" ::"r"(bar)
+               : "memory");
+}
+template <int kAStep, int kBStep>
+__device__ __forceinline__ void umma2_f16_x4_warp(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                  uint32_t b_hi, uint32_t idesc, uint32_t accumulate,
+                                                  uint32_t commit_bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q, e;\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .b32 al, bl;\n\t"
+      ".reg .b16 m;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "add.u32 al, %1, %8;\n\t"
+      "add.u32 bl, %3, %9;\n\t"
+      "mov.b64 da, {al, %2};\n\t"
+      "mov.b64 db, {bl, %4};\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+      "add.u32 al, al, %8;\n\t"
+      "add.u32 bl, bl, %9;\n\t"
+      "mov.b64 da, {al, %2};\n\t"
+      "mov.b64 db, {bl, %4};\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+      "add.u32 al, al, %8;\n\t"
+      "add.u32 bl, bl, %9;\n\t"
+      "mov.b64 da, {al, %2};\n\t"
+      "mov.b64 db, {bl, %4};\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "and.pred q, q, e;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], m;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(commit_bar), "n"(kAStep), "n"(kBStep)
+      : "memory");
+}
+
 // 32 consecutive fp32 columns of this thread's TMEM lane (lane = 32*(warp%4) + laneid)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(

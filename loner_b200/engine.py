@@ -97,6 +97,7 @@ class EngineConfig:
     n_sky: int = 0                      # num_samples.sky picks per keyframe among its sky directions (optimizer.py:299-303)
     chunk_rays: int = 16384             # render.chunk (default_model_config.yaml:19); the stash is ~4.3 KB per sample
     seed: int = 0
+    net_flags: int = None               # LONER_NET_* kernel A/B variants (None: ops.DEFAULT_NET_FLAGS)
 
     def los_lambda_at(self, global_step):
         """optimizer.py:448-452: the LOS weight, optionally decayed with the optimiser's global step."""
@@ -132,7 +133,7 @@ class MappingEngine:
             self.net = ops.HashNet(cfg.n_levels, 2, cfg.log2_hashmap_size, cfg.base_resolution, cfg.per_level_scale,
                                    cfg.n_neurons, cfg.n_hidden_layers)
         else:
-            self.net = ops.Net(cfg.n_frequencies, cfg.n_neurons, cfg.n_hidden_layers)
+            self.net = ops.Net(cfg.n_frequencies, cfg.n_neurons, cfg.n_hidden_layers, flags=cfg.net_flags)
         if params is None:
             params = xavier_uniform_flat(self.net.layer_shapes(), 1337)
             if self.hash:           # tcnn: table ~ U(-1e-4, 1e-4), after the network matrices

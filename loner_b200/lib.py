@@ -15,7 +15,7 @@ _vp, _i32, _i64, _u64, _f32 = _c.c_void_p, _c.c_int32, _c.c_int64, _c.c_uint64, 
 
 
 class NetT(_c.Structure):
-    _fields_ = [("n_frequencies", _i32), ("n_neurons", _i32), ("n_hidden_layers", _i32), ("reserved", _i32)]
+    _fields_ = [("n_frequencies", _i32), ("n_neurons", _i32), ("n_hidden_layers", _i32), ("flags", _i32)]
 
 
 class PickSegT(_c.Structure):

@@ -16,12 +16,18 @@ def _f32(t):
     return t.contiguous()
 
 
+NET_SINGLE_CTA, NET_STASH_DZL = 1, 2      # LONER_NET_* (include/loner_b200.h)
+DEFAULT_NET_FLAGS = NET_SINGLE_CTA | NET_STASH_DZL
+
+
 class Net:
     """Sigma-head description (Frequency encoding + bias-free ReLU MLP) mirrored from the
     reference's nerf_config keys (models/nerf_tcnn.py:29-38)."""
 
-    def __init__(self, n_frequencies=10, n_neurons=256, n_hidden_layers=4):
-        self.c = L.NetT(int(n_frequencies), int(n_neurons), int(n_hidden_layers), 0)
+    def __init__(self, n_frequencies=10, n_neurons=256, n_hidden_layers=4, flags=None):
+        """flags: LONER_NET_* bits of include/loner_b200.h (kernel A/B variants); None = DEFAULT_NET_FLAGS."""
+        self.flags = DEFAULT_NET_FLAGS if flags is None else int(flags)
+        self.c = L.NetT(int(n_frequencies), int(n_neurons), int(n_hidden_layers), self.flags)
         self.n_frequencies, self.n_neurons, self.n_hidden_layers = int(n_frequencies), int(n_neurons), int(n_hidden_layers)
         lib = L.load()
         self.param_count = lib.loner_mlp_param_count(ctypes.byref(self.c))
@@ -114,7 +120,7 @@ def pack_points(ray_directions, distances):
 
 KF_DETACHED = 0x40000000
 KF_MASK = 0x3FFFFFFF
-MLP_BWD_LAUNCHES = 4          # dgrad, wgrad, wgrad partial reduce, dW_out
+MLP_BWD_LAUNCHES = 3          # dgrad, wgrad (incl. dW_out), partial-sum reduce
 PICK_RANDOM, PICK_FIXED, PICK_MASK = 0, 1, 2
 
 

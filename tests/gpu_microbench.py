@@ -6,7 +6,8 @@ from loner_b200 import ops, synth, engine as eng
 
 N, S, W, L = int(os.environ.get("MB_N", 8192)), 512, 256, 4
 dev = "cuda"
-net = ops.Net(10, W, L)
+FLAGS = int(os.environ.get("MB_FLAGS", ops.DEFAULT_NET_FLAGS))      # LONER_NET_* kernel variants
+net = ops.Net(10, W, L, flags=FLAGS)
 params = eng.xavier_uniform_flat(net.layer_shapes(), 1337).to(dev)
 packed = ops.mlp_pack(net, params)
 wc = synth.world_cube("canteen")
@@ -49,7 +50,7 @@ res["mlp_dgrad_dpos"] = timeit(lambda: ops.mlp_dgrad(net, packed, P, rl["d_sigma
 dp = torch.zeros(net.param_count, device=dev)
 res["mlp_wgrad_all"] = timeit(lambda: ops.mlp_wgrad(net, packed, P, rl["d_sigma"], acts, gs, dp, scratch))
 f_fwd = 2 * (64 * W + (L - 1) * W * W + W)
-print(json.dumps({k: round(v, 4) for k, v in res.items()}))
+print(json.dumps(dict(flags=FLAGS, **{k: round(v, 4) for k, v in res.items()})))
 if os.environ.get("MB_SHORT"): sys.exit(0)
 print("fwd TF/s stash %.0f infer %.0f | stash GB %.2f dz GB %.2f" % (
     f_fwd * P / res["mlp_fwd_stash"] / 1e9, f_fwd * P / res["mlp_fwd_infer"] / 1e9,

@@ -126,16 +126,3 @@ def test_ray_selection_strategies():
             assert int(rp.min()) >= 0 and int(rp.max()) < M and rp.unique().numel() > 200
         loss = e.step([0], 256)
         assert torch.isfinite(loss)
-
-
-@pytest.mark.parametrize("env", [{"LONER_MMA_ORDER": "pair"}, {"LONER_WGRAD_GEN": "1"}])
-def test_alternate_kernel_paths_keep_parity(env):
-    """The environment switches of mlp.cu (weight chunks shared by a tile pair; dZ_L rebuilt inside wgrad)
-    are read once per process: the MLP parity tests and one reference fixture run again in a sub-process."""
-    import subprocess
-    here = os.path.dirname(os.path.abspath(__file__))
-    cmd = [sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(here, "test_gpu_kernels.py"),
-           os.path.join(here, "test_gpu_step.py"), "-k", "mlp or kf2_4x256_fp16"]
-    out = subprocess.run(cmd, env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-1000:]
-    assert " passed" in out.stdout

@@ -18,10 +18,22 @@ DEV = "cuda"
 
 
 def _case_device_inputs(c: Case):
-    points = torch.cat([ops.pack_points(s.ray_directions, s.distances) for s in c.scans]).to(DEV)
-    M = c.M
-    ray_kf = torch.cat([torch.full((c.n,), k, dtype=torch.int32) for k in range(c.K)]).to(DEV)
-    ray_point = torch.cat([c.idx[k] + k * M for k in range(c.K)]).to(DEV)
+    """Keyframe store as the engine lays it out: per keyframe the lidar returns, then (sky fixtures) the sky
+    directions at ray_range[1] + 1 (sensors.py:162-167); per keyframe n lidar picks, then n_sky sky picks flagged
+    LONER_KF_DETACHED."""
+    M, Ks = c.M, c.sky_count
+    chunks, ray_kf, ray_point = [], [], []
+    for k in range(c.K):
+        chunks.append(ops.pack_points(c.scans[k].ray_directions, c.scans[k].distances))
+        ray_kf.append(torch.full((c.n,), k, dtype=torch.int32))
+        ray_point.append(c.idx[k] + k * (M + Ks))
+        if c.n_sky:
+            chunks.append(ops.pack_points(c.sky_dirs[k], torch.full((Ks,), float(c.ray_range[1]) + 1.0)))
+            ray_kf.append(torch.full((c.n_sky,), k | ops.KF_DETACHED, dtype=torch.int32))
+            ray_point.append(c.sky_idx[k] + k * (M + Ks) + M)
+    points = torch.cat(chunks).to(DEV)
+    ray_kf = torch.cat(ray_kf).to(DEV)
+    ray_point = torch.cat(ray_point).to(DEV)
     poses12 = torch.stack([torch.cat([orc.pose6_to_matrix(p)[:3, :3].reshape(-1), orc.pose6_to_matrix(p)[:3, 3]])
                            for p in c.poses6]).to(DEV)
     return points, ray_kf, ray_point, poses12
@@ -85,13 +97,18 @@ def _rand_pos(P, seed):
     return (torch.rand(P, 3, generator=g) * 1.6 - 0.8)
 
 
-@pytest.mark.parametrize("W,L,P", [(256, 4, 1000), (128, 2, 640), (256, 1, 128)])
-def test_mlp_forward_layers(W, L, P):
+# kernel variants (loner_net_t.flags): CTA pairs + dZ_L rebuilt inside wgrad, and the round-1 single-CTA pipeline
+VARIANTS = [0, ops.NET_SINGLE_CTA | ops.NET_STASH_DZL, ops.NET_STASH_DZL, ops.NET_SINGLE_CTA]
+
+
+@pytest.mark.parametrize("flags", VARIANTS[:2])
+@pytest.mark.parametrize("W,L,P", [(256, 4, 1000), (128, 2, 640), (256, 1, 128), (256, 4, 128 * 7 + 5), (64, 2, 300)])
+def test_mlp_forward_layers(W, L, P, flags):
     spec = orc.NetSpec(n_frequencies=10, n_neurons=W, n_hidden_layers=L, precision="fp16")
     params = tcnn_standin.xavier_uniform_flat(spec.shapes, 1337)
     # make activations / sigma O(1) so that errors are visible
     params = params * 1.5
-    net = ops.Net(10, W, L)
+    net = ops.Net(10, W, L, flags=flags)
     assert net.param_count == params.numel()
     packed = ops.mlp_pack(net, params.to(DEV))
     pos = _rand_pos(P, 3)
@@ -99,7 +116,8 @@ def test_mlp_forward_layers(W, L, P):
     torch.cuda.synchronize()
     enc, ref_acts, ref_sigma = oracle_layers(pos, params, spec)
     tiles = (P + 127) // 128
-    nb = W // 64
+    Wk = max(W, 128)                      # a 64-wide network runs zero-padded on the 128-wide kernels
+    nb = Wk // 64
     tile_bytes = 16384 * (1 + L * nb)
     worst = {}
     for t in range(tiles):
@@ -109,6 +127,8 @@ def test_mlp_forward_layers(W, L, P):
         worst["enc"] = max(worst.get("enc", 0), float((a0 - enc[lo:hi].half().float()).abs().max()))
         for l in range(L):
             al = decode_image(blob[16384 + l * nb * 16384: 16384 + (l + 1) * nb * 16384], nb)[: hi - lo]
+            assert not al[:, W:].any()        # padded neurons stay exactly zero
+            al = al[:, :W]
             ref = ref_acts[l][lo:hi].half().float()
             worst[f"A{l+1}"] = max(worst.get(f"A{l+1}", 0), float((al - ref).abs().max() / (ref.abs().max() + 1e-9)))
     es = relerr(sigma, ref_sigma)
@@ -124,11 +144,12 @@ def test_mlp_forward_layers(W, L, P):
     assert torch.equal(sigma, sigma2)
 
 
-@pytest.mark.parametrize("W,L,P", [(256, 4, 1000), (128, 2, 640), (256, 1, 300), (128, 8, 260)])
-def test_mlp_backward_matches_autograd(W, L, P):
+@pytest.mark.parametrize("flags", VARIANTS)
+@pytest.mark.parametrize("W,L,P", [(256, 4, 1000), (128, 2, 640), (256, 1, 300), (128, 8, 260), (64, 2, 700)])
+def test_mlp_backward_matches_autograd(W, L, P, flags):
     spec = orc.NetSpec(n_frequencies=10, n_neurons=W, n_hidden_layers=L, precision="fp16")
     params = (tcnn_standin.xavier_uniform_flat(spec.shapes, 1337) * 1.5)
-    net = ops.Net(10, W, L)
+    net = ops.Net(10, W, L, flags=flags)
     pos = _rand_pos(P, 4)
     g = torch.Generator().manual_seed(9)
     d_sigma = torch.randn(P, generator=g) * 1e-4
@@ -151,8 +172,8 @@ def test_mlp_backward_matches_autograd(W, L, P):
         if li == len(spec.shapes) - 1:
             a, b = a[:ni], b[:ni]                  # only row 0 of the padded output matrix is used
         e = norm_relerr(a, b)
-        print(f"[mlp bwd W={W} L={L}] layer {li} dW norm-rel err {e:.2e} (|ref| {float(b.norm()):.3e})")
-        assert e < 1e-2                            # fp16 gradients with loss scale vs fp32 autograd
+        print(f"[mlp bwd W={W} L={L} flags={flags}] layer {li} dW norm-rel err {e:.2e} (|ref| {float(b.norm()):.3e})")
+        assert e < 2e-3                            # fp16 dZ (power-of-two loss scale) vs fp32 autograd; measured ~1e-4..1e-3
         off += no * ni
     e = norm_relerr(d_pos, pos_ref.grad)
     print(f"[mlp bwd W={W} L={L}] d_pos norm-rel err {e:.2e}")
@@ -161,8 +182,7 @@ def test_mlp_backward_matches_autograd(W, L, P):
     d_params2 = torch.zeros(net.param_count, device=DEV)
     assert ops.mlp_bwd(net, packed, P, d_sigma.to(DEV), acts, 2.0 ** 12, d_params2, pos=posd, want_dpos=False) is None
     n_hidden = sum(no * ni for no, ni in spec.shapes[:-1])
-    assert torch.equal(d_params2[:n_hidden], d_params[:n_hidden])                  # deterministic reduction
-    assert norm_relerr(d_params2[n_hidden:], d_params[n_hidden:]) < 1e-5            # dW_out: atomics, order varies
+    assert torch.equal(d_params2, d_params)            # deterministic reductions everywhere (dW_out included: no atomics)
 
 
 def _loss_cfg(scale):
