@@ -6,9 +6,14 @@
   python bench.py --impl reference --steps 3 --warmup 1          # reference arm: CPU port on host cores
 
 A step = one full mapping iteration over one batch of synthetic rays: ray pick + ray build +
-occupancy-guided sampling + Frequency/MLP forward + volume render + JS-margin loss + backward +
+occupancy-guided sampling + encoding/MLP forward + volume render + JS-margin loss + backward +
 Adam (+ occupancy-grid update every 10th step), exactly the loop body of
 /root/reference/src/mapping/optimizer.py:276-384.  Prints ONE JSON line (rank 0).
+
+The line's headline (`value`, `roofline`, `e2e`) is BASELINE.json configs[1] (C2) per GPU.  It also carries:
+`hash` (the sigma head the reference SHIPS, at the C2 size and at the reference's default operating point),
+`api` (the reference-facing FusedOptimizer.iterate_optimizer), and at N > 1 `grad_check` (k-GPU == 1-GPU
+gradients on one global ray set), `c5` (BASELINE configs[4], weak) and at N = 4 `c4` (configs[3], strong).
 """
 import argparse
 import json
@@ -17,6 +22,7 @@ import subprocess
 import sys
 import threading
 import time
+import types
 
 import torch
 
@@ -29,19 +35,48 @@ WORKLOADS = {
                label="C2 canteen geometry, synthetic 64x1024 scan, 8192 rays/GPU x 512 samples, 4x256 MLP (Frequency-10)"),
     "c3": dict(geom="garden", K=8, rays_per_gpu=16384, S=512, W=256, L=4, poses=False,
                label="C3 garden geometry, 8-keyframe window, 16384 rays/GPU x 512 samples, 4x256 MLP"),
+    # configs[3]: 65536 rays x 256 samples in total, ray-sharded (strong scaling); rays_per_gpu = 65536 / N
+    "c4": dict(geom="quad", K=8, rays_total=65536, S=256, W=256, L=4, poses=False,
+               label="C4 Newer College quad geometry, 65536 rays x 256 samples in total, ray-sharded, 4x256 MLP"),
     "c5": dict(geom="canteen", K=16, rays_per_gpu=32768, S=512, W=256, L=4, poses=True,
                label="C5 weak scaling, 16-keyframe window, 32768 rays/GPU x 512 samples, joint pose+map"),
+    "c1": dict(geom="canteen", K=1, rays_per_gpu=2048, S=128, W=64, L=2, poses=False,
+               label="C1 single scan, 2048 rays x 128 samples, 2x64 MLP"),
     "smoke": dict(geom="canteen", K=2, rays_per_gpu=512, S=128, W=128, L=2, poses=True, label="smoke"),
     # the sigma head the reference SHIPS (cfg/nerf_config/default_nerf_hash.yaml) at the C2 size
     "c2hash": dict(geom="canteen", K=1, rays_per_gpu=8192, S=512, W=64, L=1, poses=False, encoding="HashGrid",
                    label="C2 geometry and size with the reference's shipped sigma head: HashGrid (16 levels x 2, 2^18) + 1x64 MLP"),
+    # the reference's own operating point: window of 8 keyframes x 512 rays x 512 samples, joint optimisation
+    # (cfg/defaults.yaml:60,70; default_model_config.yaml:12), shipped HashGrid head
+    "refdefault": dict(geom="canteen", K=8, rays_per_gpu=4096, S=512, W=64, L=1, poses=True, encoding="HashGrid",
+                       label="reference default operating point: 8 keyframes x 512 rays x 512 samples, HashGrid + 1x64, joint pose+map"),
 }
 
 
-def flops_per_sample(E_pad, W, L, poses):
-    f_fwd = 2 * (E_pad * W + (L - 1) * W * W + W)
-    f_train = 3 * f_fwd - (0 if poses else 2 * E_pad * W)
-    return f_fwd, f_train
+def rays_per_gpu(wl, world):
+    return wl["rays_per_gpu"] if "rays_per_gpu" in wl else wl["rays_total"] // world
+
+
+def flops_per_sample(wl):
+    """Algorithmic FLOPs per sample: F_fwd = 2 (E_pad W + (L-1) W^2 + W); a training step is
+    fwd + dgrad + wgrad, the first-layer dgrad only when input gradients (poses) are needed."""
+    W, L = wl["W"], wl["L"]
+    e_pad = 32 if wl.get("encoding") == "HashGrid" else 64
+    f_fwd = 2 * (e_pad * W + (L - 1) * W * W + W)
+    f_train = 3 * f_fwd - (0 if wl["poses"] else 2 * e_pad * W)
+    return e_pad, f_fwd, f_train
+
+
+def describe(wl, world):
+    hashed = wl.get("encoding") == "HashGrid"
+    return {"workload": wl["label"], "geometry": wl["geom"], "keyframes": wl["K"], "rays_per_gpu": rays_per_gpu(wl, world),
+            "samples_per_ray": wl["S"], "mlp": f"{wl['L']}x{wl['W']}",
+            "encoding": "HashGrid(16 levels x 2 features, 2^18 entries) -> 32" if hashed else "Frequency(10) -> 64",
+            "pose_optimisation": wl["poses"], "sampler": "OGM", "parallelism": f"ray-sharded dp{world}",
+            "l2_policy": ("no stash (the backward recomputes); the 14.8 MB table and its 29.7 MB gradient are meant to stay in L2; "
+                          "z/sigma/d_sigma streams (50 MB/step) exceed nothing: steps are back to back, no flush"
+                          if hashed else
+                          "activation + gradient stash (>8 GB per step) streams through HBM: inputs larger than L2, no flush needed")}
 
 
 def load_peaks():
@@ -117,26 +152,31 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def ncu_traffic_bytes(kernel_substr):
+NCU_SUMMARY = ("profiles/r2_ncu_summary.csv", "profiles/r1_ncu_summary.csv")
+
+
+def ncu_traffic_bytes(kernel_substr, stash=True):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full
-    capture (profiles/r1_ncu_summary.csv, C2 workload); None if absent."""
+    capture (C2-sized launch); (None, None) if absent."""
     import csv
-    path = os.path.join(REPO, "profiles", "r1_ncu_summary.csv")
-    if not os.path.exists(path):
-        return None
-    rows = list(csv.reader(open(path)))
-    hdr, units = rows[0], rows[1]
-    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-    # the training step runs the stash variant of the forward kernel: mlp_fwd_kernel<W, true>
-    need = [kernel_substr + "_kernel"] + ([", 1>"] if kernel_substr == "mlp_fwd" else [])
-    for r in rows[2:]:
-        if all(n in r[ki] for n in need):
-            return float(r[ri]) * mult.get(units[ri], 1.0) + float(r[wi]) * mult.get(units[wi], 1.0)
-    return None
+    for rel in NCU_SUMMARY:
+        path = os.path.join(REPO, rel)
+        if not os.path.exists(path):
+            continue
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        for r in rows[2:]:
+            if kernel_substr not in r[ki]:
+                continue
+            if kernel_substr == "mlp_fwd" and stash != (", 1" in r[ki] or "true" in r[ki]):
+                continue           # the training step runs the stash variant: mlp_fwd_kernel<W, true, ...>
+            return float(r[ri]) * mult.get(units[ri], 1.0) + float(r[wi]) * mult.get(units[wi], 1.0), rel
+    return None, None
 
 
-def build_engine(wl, device, seed):
+def build_engine(wl, device, seed, world=1):
     from loner_b200 import engine as eng
     from loner_b200 import synth
     wc = synth.world_cube(wl["geom"])
@@ -218,6 +258,170 @@ def cpu_port_rays_per_sec(wl, n_rays, iters, warmup, tune=True):
     return n_per * K / med, med
 
 
+# ---------------------------------------------------------------------------------------------- timing helpers
+class Timing:
+    def __init__(self, dev, world):
+        self.dev, self.world = dev, world
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warmup):
+        """W untimed calls, then EXACTLY `steps` calls between two CUDA events on the launching stream, bracketed by
+        barrier + synchronize on both sides; returns (max-over-ranks ms for all steps, wall clock window)."""
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        w0 = time.time()
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        self.barrier()
+        w1 = time.time()
+        ms = torch.tensor([a.elapsed_time(b)], device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), (w0, w1)
+
+
+def run_workload(wl, tm, rank, steps, warmup, sections=False):
+    """Times the engine step of one workload; returns dict(value rays/s over all ranks, ms_per_step, ...)."""
+    e = build_engine(wl, tm.dev, seed=1000 + rank, world=tm.world)
+    window = list(range(wl["K"]))
+    n_per_kf = rays_per_gpu(wl, tm.world) // wl["K"]
+    N = n_per_kf * wl["K"]
+    for _ in range(max(warmup, 3)):
+        e.step(window, n_per_kf, optimize_poses=wl["poses"])
+    if sections:
+        tm.barrier()
+        e.timers = {}
+    l0 = e.launches
+    ms, wall = tm.timed(lambda: e.step(window, n_per_kf, optimize_poses=wl["poses"]), steps, 0)
+    launches = e.launches - l0
+    secs = {}
+    if sections:
+        secs = {k: (sum(a.elapsed_time(b) for a, b in v) / len(v), len(v)) for k, v in e.timers.items()}
+        e.timers = None
+    return dict(engine=e, N=N, n_per_kf=n_per_kf, window=window, ms_per_step=ms / steps, wall=wall, launches=launches,
+                value=N * tm.world / (ms / steps * 1e-3), sections=secs)
+
+
+def kernel_table(wl, secs, per_chunk, peaks, net_flags):
+    """Per-section roofline entries: what bounds the kernel family, its algorithmic work per launch, the achieved rate
+    and the fraction of the measured peak."""
+    W, L, S = wl["W"], wl["L"], wl["S"]
+    e_pad, f_fwd, _ = flops_per_sample(wl)
+    hashed = wl.get("encoding") == "HashGrid"
+    nb = max(W, 128) // 64
+    gen = not (net_flags & 2)
+    spec = {
+        "sample": ("hbm", None, 4.0, "writes z [N,S]; the 4 MB occupancy grid is gathered from L2"),
+        "render_loss": ("hbm", None, 12.0, "reads sigma and z, writes d_sigma (noise from Philox)"),
+        "ogm_update": ("hbm", None, 4.0, "reads z; trilinear scatter into the L2-resident grid (atomics), every 10th step"),
+        "adam_pack": ("hbm", None, None, "217 K parameters: launch-latency bound"),
+    }
+    if hashed:
+        spec["mlp_fwd"] = ("l2-gather", 2 * (32 * 64 + 64), 512.0, "hash_fwd: 128 gathers x 4 B per sample from the L2-resident table")
+        spec["mlp_dgrad"] = ("l2-atomic", 6 * (32 * 64 + 64), 1536.0, "hash_bwd: re-gathers 128 x 4 B and issues 128 x 8 B vector atomics per sample")
+    else:
+        stash = 16384 * (1 + L * nb) / 128 + L * (max(W, 128) // 32) * 4
+        dz = 16384 * nb * (L - (1 if gen else 0)) / 128
+        rd = 16384 * ((1 + nb + nb) + (L - 2) * 2 * nb + (nb if gen else 2 * nb)) / 128 if L >= 2 else 16384 * (1 + nb + (0 if gen else nb)) / 128
+        spec["mlp_fwd"] = ("tensor", f_fwd, stash, "tcgen05 forward; also writes the activation stash (design traffic, bytes_per_sample)")
+        spec["mlp_dgrad"] = ("tensor", 2 * ((L - 1) * W * W + (e_pad * W if wl["poses"] else 0)), dz,
+                             "tcgen05 dgrad; also writes the dZ stash (design traffic)")
+        spec["mlp_wgrad"] = ("hbm", 2 * (e_pad * W + (L - 1) * W * W + W), rd,
+                             "tcgen05 wgrad incl. dW_out: streams the stash once (design traffic), accumulators in TMEM")
+    out = {}
+    for k, (t, cnt) in secs.items():
+        bound, flops, byts, what = spec.get(k, ("hbm", None, None, ""))
+        ent = {"ms": round(t, 4), "launch_groups_timed": cnt, "bound": bound, "what": what}
+        if flops:
+            ent["tflops"] = round(flops * per_chunk / (t * 1e-3) / 1e12, 1)
+            ent["frac_of_sustained_tensor_peak"] = round(ent["tflops"] / peaks["tflops_sustained"], 4)
+        if byts:
+            ent["bytes_per_sample"] = round(byts, 1)
+            ent["gbs"] = round(byts * per_chunk / (t * 1e-3) / 1e9, 1)
+            ent["frac_of_hbm_peak"] = round(ent["gbs"] / peaks["hbm_gbs"], 4)
+        out[k] = ent
+    return out
+
+
+class _Cfg(dict):
+    def __getattr__(self, k):
+        v = self[k]
+        return _Cfg(v) if isinstance(v, dict) else v
+
+
+def api_optimizer_rate(wl, tm, steps):
+    """The reference-facing call: FusedOptimizer(settings, ...).iterate_optimizer(window, OptimizationSettings) on
+    reference-shaped keyframe objects (LidarScan buffers on the HOST, poses as 6-vectors), as Mapper.update drives it
+    (mapping/mapper.py:104).  Keyframe scans cross to the device once, when first seen; every call ends with the
+    reference's own host reads (loss finiteness, depth_eps)."""
+    from loner_b200 import synth
+    from loner_b200.dropin.mapping_optimizer import FusedOptimizer, OptimizationSettings
+    wc = synth.world_cube(wl["geom"])
+    n_per_kf = rays_per_gpu(wl, tm.world) // wl["K"]
+    hashed = wl.get("encoding") == "HashGrid"
+    enc = (dict(otype="HashGrid", n_levels=16, n_features_per_level=2, log2_hashmap_size=18, base_resolution=16,
+                per_level_scale=2.0) if hashed else dict(otype="Frequency", n_frequencies=10))
+    st = _Cfg(freeze_poses=False, skip_pose_refinement=True, num_samples=dict(lidar=n_per_kf, sky=0),
+              rays_selection=dict(strategy="RANDOM"), samples_selection=dict(strategy="OGM"),
+              keyframe_schedule=(dict(num_keyframes=-1, iteration_schedule=(
+                  dict(num_iterations=steps, freeze_poses=not wl["poses"], freeze_sigma_mlp=False, freeze_rgb_mlp=True),)),),
+              model_config=dict(
+                  model=dict(ray_range=list(synth.GEOMETRY[wl["geom"]]["ray_range"]), num_colors=3, model_type="nerf_decoupled",
+                             nerf_config=dict(pos_encoding_sigma=enc, sigma_network=dict(otype="CutlassMLP", n_neurons=wl["W"],
+                                                                                         n_hidden_layers=wl["L"])),
+                             render=dict(N_samples_train=wl["S"], N_samples_test=2048, perturb=1.0, raw_noise_std=1.0,
+                                         chunk=16384, netchunk=0, retraw=True, white_bkgd=False),
+                             occ_model=dict(voxel_size=100, lr=1e-4, N_iters_acc=10)),
+                  train=dict(lrate_sigma_mlp=0.01, lrate_pose=0.001, lrate_gamma=1.0),
+                  loss=dict(loss_selection="L1_JS", JS_loss=dict(min_js_score=1.0, max_js_score=10.0, alpha=1.0),
+                            decay_los_lambda=False, los_lambda=1000.0, min_depth_eps=0.5, depthloss_lambda=0.005)))
+    world_cube = types.SimpleNamespace(scale_factor=torch.tensor(wc.scale_factor), shift=torch.tensor(wc.shift))
+    opt = FusedOptimizer(st, None, world_cube, tm.dev.index, False, True, False)
+    scans, poses = synth.make_window(wl["geom"], wl["K"], seed=0)
+
+    class Pose:
+        def __init__(self, p6):
+            self._t = p6.clone()
+
+        def get_pose_tensor(self):
+            return self._t
+
+    class KF:
+        def __init__(self, scan, p6, t):
+            self._scan, self._pose, self._time, self.is_anchored = scan, Pose(p6), t, (t == 0.0)
+
+        def get_lidar_scan(self):
+            return self._scan
+
+        def get_lidar_pose(self):
+            return self._pose
+
+        def get_time(self):
+            return torch.tensor(self._time)
+
+    kfs = [KF(scans[k], synth.axis_angle_from_yaw_pose(poses[k]), 3.0 * k) for k in range(wl["K"])]
+    opt._engine.grid.copy_(synth.trained_occupancy_grid(wl["geom"])[0, 0])
+    opt.iterate_optimizer(kfs, OptimizationSettings(num_iterations=3, freeze_poses=not wl["poses"]))   # registers the scans (H2D)
+    ms, _ = tm.timed(lambda: opt.iterate_optimizer(kfs, OptimizationSettings(num_iterations=steps, freeze_poses=not wl["poses"])),
+                     1, 0)
+    N = n_per_kf * wl["K"]
+    return {"value": N * tm.world * steps / (ms * 1e-3), "unit": "rays/s", "iterations_per_call": steps,
+            "api": "FusedOptimizer.iterate_optimizer(keyframe_window, OptimizationSettings) - the reference Optimizer's entry point "
+                   "(mapping/optimizer.py:144); on-device ray pick/build, loss finiteness + depth_eps read back per call",
+            "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8.0 / steps}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -227,23 +431,26 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample-rays", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the hash / api / c5 / c4 sub-objects")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    f_fwd, f_train = flops_per_sample(64, wl["W"], wl["L"], wl["poses"])
-    config = {"workload": wl["label"], "geometry": wl["geom"], "keyframes": wl["K"], "rays_per_gpu": wl["rays_per_gpu"],
-              "samples_per_ray": wl["S"], "mlp": f"{wl['L']}x{wl['W']}", "encoding": "Frequency(10) -> 64",
-              "pose_optimisation": wl["poses"], "sampler": "OGM", "parallelism": f"ray-sharded dp{args.gpus}",
-              "l2_policy": "activation stash (>8 GB/step) streams through HBM: inputs larger than L2, no flush needed"}
+    e_pad, f_fwd, f_train = flops_per_sample(wl)
+    config = describe(wl, max(world, args.gpus) if args.impl == "reference" else world)
 
     if args.impl == "reference":
-        # reference arm: the reference's own CPU path restated (oracle/), all host threads, bounded sample
+        # reference arm: the reference's own CPU path restated (oracle/), all host threads, bounded sample.
+        # The rate is per ray: the step below runs `cpu_sample_rays` rays of the SAME workload (same scans, network,
+        # samples per ray), not the full rays_per_gpu batch - a full C2 batch takes ~1 min per step on the host.
         if rank != 0:
             return
         n = args.cpu_sample_rays
         rps, med = cpu_port_rays_per_sec(wl, n, args.steps, args.warmup)
+        config["cpu_sample_rays"] = n
+        config["note"] = (f"CPU arm: each step = one full mapping iteration over {n} rays of this workload (bounded sample); "
+                          "rays/s is per ray and is compared with the GPU arm's full-batch rate")
         line = {"impl": "reference", "metric": "rays/sec", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
@@ -261,122 +468,112 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    e = build_engine(wl, dev, seed=1000 + rank)
-    window = list(range(wl["K"]))
-    n_per_kf = wl["rays_per_gpu"] // wl["K"]
-    N = n_per_kf * wl["K"]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    tm = Timing(dev, world)
+    from loner_b200 import ops
 
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    for _ in range(max(args.warmup, 3)):
-        e.step(window, n_per_kf, optimize_poses=wl["poses"])
-    barrier()
-    e.timers = {}
-    launches0 = e.launches
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    wall0 = time.time()
-    t_start.record()
-    for _ in range(args.steps):
-        loss = e.step(window, n_per_kf, optimize_poses=wl["poses"])
-    t_end.record()
-    barrier()
-    wall1 = time.time()
-    clock_info = clocks.stop(wall0, wall1) if rank == 0 else None
-    ms = torch.tensor([t_start.elapsed_time(t_end)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    launches = e.launches - launches0
-    sections = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in e.timers.items()}
-    e.timers = None
-    loss_val = float(loss.item())
+    main_run = run_workload(wl, tm, rank, args.steps, args.warmup, sections=True)
+    e, N, n_per_kf, window = main_run["engine"], main_run["N"], main_run["n_per_kf"], main_run["window"]
+    clock_info = clocks.stop(*main_run["wall"]) if rank == 0 else None
+    loss_val = float(e.step(window, n_per_kf, optimize_poses=wl["poses"]).item())
 
-    # ---- e2e: reference-facing call with HOST rays/depths (pinned), H2D every step, loss read back
+    # ---- e2e: the step fed with HOST rays/depths (pinned), H2D every step, loss read back every step
     rays_h = e.last["rays"].detach().cpu().pin_memory()
     depths_h = e.last["depths"].detach().cpu().pin_memory()
-    for _ in range(3):
-        e.step_from_host(rays_h, depths_h)
-    barrier()
     e2e_steps = max(3, min(args.steps, 10))
-    ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ta.record()
-    for _ in range(e2e_steps):
-        e.step_from_host(rays_h, depths_h)
-    tb.record()
-    barrier()
-    ms2 = torch.tensor([ta.elapsed_time(tb)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_rps = N * world * e2e_steps / (float(ms2.item()) * 1e-3)
+    ms2, _ = tm.timed(lambda: e.step_from_host(rays_h, depths_h), e2e_steps, 3)
+    e2e_rps = N * world * e2e_steps / (ms2 * 1e-3)
 
     # ---- forward-only (test-mode render: sampler + MLP inference + volume render), same rays
     rays_d = e.last["rays"]
-    for _ in range(3):
-        e.render(rays_d, seed=1)
-    barrier()
-    fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fa.record()
-    for _ in range(e2e_steps):
-        e.render(rays_d, seed=2)
-    fb.record()
-    barrier()
-    ms3 = torch.tensor([fa.elapsed_time(fb)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
-    fwd_ms = float(ms3.item()) / e2e_steps
+    ms3, _ = tm.timed(lambda: e.render(rays_d, seed=2), e2e_steps, 3)
+    fwd_ms = ms3 / e2e_steps
+    net_flags = getattr(e.net, "flags", 0)
+    del e
+    main_run["engine"] = None
+    torch.cuda.empty_cache()
+
+    extras = {}
+    if not args.no_extras and args.workload == "c2":
+        # the configuration the reference ships (HashGrid + 1x64): C2 size and the reference's default operating point
+        hs = {}
+        for name in ("c2hash", "refdefault"):
+            r = run_workload(WORKLOADS[name], tm, rank, max(5, min(args.steps, 10)), 3, sections=True)
+            hs[name] = {"rays_per_s": r["value"], "ms_per_step": r["ms_per_step"], "config": describe(WORKLOADS[name], world),
+                        "sections_ms": {k: round(v[0], 4) for k, v in r["sections"].items()}}
+            r["engine"] = None
+            torch.cuda.empty_cache()
+        extras["hash"] = hs
+        extras["api"] = api_optimizer_rate(wl, tm, max(5, min(args.steps, 20)))
+        torch.cuda.empty_cache()
+        if world > 1:
+            from loner_b200 import engine as eng, parallel, synth
+            swl = WORKLOADS["smoke"]
+            wcs = synth.world_cube(swl["geom"])
+            sscans, sposes = synth.make_window(swl["geom"], 3, seed=3, n_beams=16, n_azimuth=256)
+
+            def make(distributed):
+                cfg = eng.EngineConfig(scale=wcs.scale_factor, shift=wcs.shift, ray_range=(1.0, 50.0), n_neurons=128,
+                                       n_hidden_layers=2, n_samples=128, chunk_rays=256)
+                en = eng.MappingEngine(cfg, device=dev, distributed=distributed)
+                for k in range(3):
+                    en.add_keyframe(sscans[k].ray_directions, sscans[k].distances, synth.axis_angle_from_yaw_pose(sposes[k]))
+                en.grid.copy_(synth.trained_occupancy_grid(swl["geom"])[0, 0])
+                return en
+
+            extras["grad_check"] = parallel.grad_check(make, [0, 1, 2], 160, 128, optimize_poses=True)
+            extras["grad_check"]["what"] = ("k-GPU sharded step vs the same global ray set on one GPU: relative difference of "
+                                            "loss, MLP gradient, pose gradient (3 keyframes x 160 rays per rank, 2x128, poses on)")
+            for name in (["c5"] + (["c4"] if world == 4 else [])):
+                r = run_workload(WORKLOADS[name], tm, rank, max(4, min(args.steps, 8)), 3)
+                _, _, ft = flops_per_sample(WORKLOADS[name])
+                extras[name] = {"rays_per_s": r["value"], "ms_per_step": r["ms_per_step"],
+                                "scaling": "strong" if "rays_total" in WORKLOADS[name] else "weak",
+                                "config": describe(WORKLOADS[name], world),
+                                "achieved_tflops_per_gpu": round(ft * r["N"] * WORKLOADS[name]["S"] / (r["ms_per_step"] * 1e-3) / 1e12, 1)}
+                r["engine"] = None
+                torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peaks = load_peaks()
-    ms_per_step = ms_total / args.steps
-    value = N * world / (ms_per_step * 1e-3)
+    ms_per_step = main_run["ms_per_step"]
+    value = main_run["value"]
     P = N * wl["S"]
-    per_chunk = min(N, e.cfg.chunk_rays) * wl["S"]
-    kern = {}
-    flops = {"mlp_fwd": f_fwd, "mlp_dgrad": 2 * ((wl["L"] - 1) * wl["W"] ** 2 + (64 * wl["W"] if wl["poses"] else 0)),
-             "mlp_wgrad": 2 * (64 * wl["W"] + (wl["L"] - 1) * wl["W"] ** 2 + wl["W"])}
-    for k, t in sections.items():
-        kern[k] = {"ms": round(t, 4)}
-        if k in flops:
-            kern[k]["tflops"] = round(flops[k] * per_chunk / (t * 1e-3) / 1e12, 1)
+    per_chunk = min(N, 16384) * wl["S"]
+    secs = main_run["sections"]
+    kern = kernel_table(wl, secs, per_chunk, peaks, net_flags)
     hashed = wl.get("encoding") == "HashGrid"
-    if hashed:          # E_pad = 32, no hidden-to-hidden layers; forward and the recomputing backward
-        f_fwd = 2 * (32 * 64 + 64)
-        f_train = 4 * f_fwd
-        flops = {"mlp_fwd": f_fwd, "mlp_dgrad": 3 * f_fwd}
-    dom = max((k for k in sections if k in flops), key=lambda k: sections[k])
-    achieved = flops[dom] * per_chunk / (sections[dom] * 1e-3) / 1e12
-    traffic = ncu_traffic_bytes(dom) if args.workload == "c2" else None
-    roofline = {"kernel": dom, "bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["tflops_sustained"],
-                "unit": "TFLOP/s", "frac": round(achieved / peaks["tflops_sustained"], 4), "traffic": traffic,
-                "traffic_note": "DRAM bytes of one launch from profiles/r1_ncu_summary.csv (ncu --set full); the "
-                                "algorithmic HBM need of this kernel is 8 B/sample, the rest is the activation "
-                                "stash the backward design requires (DESIGN.md section 4)",
-                "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                "algorithmic_flops_per_sample": flops[dom], "samples_per_launch": per_chunk,
-                "step": {"algorithmic_tflop_per_step": round(f_train * P / 1e12, 3),
-                         "achieved_tflops": round(f_train * P / (ms_per_step * 1e-3) / 1e12, 1),
-                         "frac_of_sustained_peak": round(f_train * P / (ms_per_step * 1e-3) / 1e12 / peaks["tflops_sustained"], 4)},
-                "kernels": kern}
+    dom = max((k for k in secs if k.startswith("mlp_")), key=lambda k: secs[k][0])
     if hashed:
-        # gather/scatter-bound: per sample the backward re-gathers 128 x 4 B and issues 128 x 8 B vector atomics
-        # (the forward gathers 128 x 4 B); the 14.8 MB fp16 table and its 29.7 MB fp32 gradient live in L2
-        nbytes = {"mlp_fwd": 512, "mlp_dgrad": 1536}[dom]
-        gbs = nbytes * per_chunk / (sections[dom] * 1e-3) / 1e9
-        roofline = {"kernel": "hash_bwd" if dom == "mlp_dgrad" else "hash_fwd", "bound": "hbm", "achieved": round(gbs, 1),
-                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 4), "traffic": None,
-                    "traffic_note": "algorithmic gather + atomic bytes per launch; they are served by L2 (table 14.8 MB, "
-                                    "gradient table 29.7 MB), reported against the measured HBM copy peak",
-                    "peak_source": peaks["source"], "algorithmic_bytes_per_sample": nbytes, "samples_per_launch": per_chunk,
+        kd = kern[dom]
+        roofline = {"kernel": "hash_bwd" if dom == "mlp_dgrad" else "hash_fwd", "bound": "hbm", "achieved": kd["gbs"],
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": kd["frac_of_hbm_peak"], "traffic": None,
+                    "traffic_note": "algorithmic gather + atomic bytes per launch; they are served by L2 (fp16 table 14.8 MB, fp32 "
+                                    "gradient table 29.7 MB), so this fraction of the HBM copy peak is a lower bound on how busy the "
+                                    "memory system is, not an HBM utilisation",
+                    "peak_source": peaks["source"], "algorithmic_bytes_per_sample": kd["bytes_per_sample"],
+                    "samples_per_launch": per_chunk, "kernels": kern}
+    else:
+        traffic, src = ncu_traffic_bytes(dom)
+        kd = kern[dom]
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": kd["tflops"], "peak": peaks["tflops_sustained"],
+                    "unit": "TFLOP/s", "frac": kd["frac_of_sustained_tensor_peak"], "traffic": traffic,
+                    "traffic_note": f"DRAM bytes of one C2-sized launch of this kernel from {src} (ncu --set full); the kernel's "
+                                    "algorithmic HBM need is ~8 B/sample, the rest is the activation / gradient stash of the backward "
+                                    "design (DESIGN.md section 4)",
+                    "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                    "algorithmic_flops_per_sample": kd and (2 * (e_pad * wl["W"] + (wl["L"] - 1) * wl["W"] ** 2 + wl["W"]) if dom != "mlp_dgrad"
+                                                             else 2 * ((wl["L"] - 1) * wl["W"] ** 2 + (e_pad * wl["W"] if wl["poses"] else 0))),
+                    "samples_per_launch": per_chunk,
+                    "step": {"algorithmic_tflop_per_step": round(f_train * P / 1e12, 3),
+                             "achieved_tflops": round(f_train * P / (ms_per_step * 1e-3) / 1e12, 1),
+                             "frac_of_sustained_peak": round(f_train * P / (ms_per_step * 1e-3) / 1e12 / peaks["tflops_sustained"], 4),
+                             "frac_of_burst_peak": round(f_train * P / (ms_per_step * 1e-3) / 1e12 / peaks["tflops_burst"], 4)},
                     "kernels": kern}
     line = {"metric": "rays/sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -384,11 +581,12 @@ def main():
             "data": "synthetic", "config": config, "loss": loss_val, "clocks": clock_info,
             "e2e": {"value": e2e_rps, "unit": "rays/s", "h2d_bytes_per_step": int(rays_h.numel() * 4 + depths_h.numel() * 4),
                     "d2h_bytes_per_step": 4, "api": "MappingEngine.step_from_host(rays[N,13], depths[N]) (pinned host)"},
-            "gpu_launches": launches, "roofline": roofline,
+            "gpu_launches": main_run["launches"], "roofline": roofline,
             "forward_only": {"rays_per_s": N * world / (fwd_ms * 1e-3), "ms": fwd_ms,
                              "tflops": round(f_fwd * P / (fwd_ms * 1e-3) / 1e12, 1),
                              "frac_of_sustained_peak": round(f_fwd * P / (fwd_ms * 1e-3) / 1e12 / peaks["tflops_sustained"], 4),
                              "what": "MappingEngine.render: OGM sampler + MLP inference + volume render, no stash"}}
+    line.update(extras)
     if not args.no_cpu_baseline:
         n = args.cpu_sample_rays
         rps, med = cpu_port_rays_per_sec(wl, n, 3, 1)

@@ -452,12 +452,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
         const int nch = (l == 0) ? 1 : kNb;
         const int ksteps0 = (l == 0) ? net.Epad / 16 : 4;   // layer 0 contracts over Epad (<= 64) features
         for (int t = 0; t < 2; ++t) {
-          if (kCtas == 2) mbar_wait_cluster_warp(sm.a_ready(t), par_a); else mbar_wait_warp(sm.a_ready(t), par_a);
+          mbar_wait_warp(sm.a_ready(t), par_a);
           tc_fence_after();
           for (int c = 0; c < nch; ++c, ++g) {
             const uint32_t slot = g % nslots, par_w = (g / nslots) & 1;
             mbar_wait_warp(sm.w_full(slot), par_w);
-            if (kCtas == 2) mbar_wait_cluster_warp(sm.w_peer(slot), par_w);
+            if (kCtas == 2) mbar_wait_warp(sm.w_peer(slot), par_w);
             tc_fence_after();
             const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
             if (ksteps0 == 4) {
@@ -669,12 +669,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
       for (int l = net.L - 1; l >= l_lo; --l) {
         const uint32_t idesc = make_idesc_f16(128 * kCtas, layer_K(net, l), 0, 0);
         for (int t = 0; t < 2; ++t) {
-          if (kCtas == 2) mbar_wait_cluster_warp(sm.a_ready(t), par_a); else mbar_wait_warp(sm.a_ready(t), par_a);
+          mbar_wait_warp(sm.a_ready(t), par_a);
           tc_fence_after();
           for (int c = 0; c < kNb; ++c, ++g) {
             const uint32_t slot = g % nslots, par_w = (g / nslots) & 1;
             mbar_wait_warp(sm.w_full(slot), par_w);
-            if (kCtas == 2) mbar_wait_cluster_warp(sm.w_peer(slot), par_w);
+            if (kCtas == 2) mbar_wait_warp(sm.w_peer(slot), par_w);
             tc_fence_after();
             const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
             if (kCtas == 2)
@@ -896,7 +896,15 @@ constexpr int kWgStages = 3;
 constexpr int kWgThreads = 320;     // warp 0 producer, warp 1 MMA, warps 2-9 helpers (generate dZ_L / accumulate dW_out), 2-5 epilogue
 // stage of a layer > 0 CTA:  X = A_l half (32 KB) | Y = dZ_{l+1} half (32 KB)
 // stage of a layer-0 CTA:    X = A_0 half (8 KB)  | Y = dZ_1 half (32 KB) | Z = A_L half (32 KB)
-constexpr int kWgStageBytes = 73728;
+// The helpers' small per-row inputs travel by bulk copy too (a register prefetch of global loads turns into a
+// wait of a full HBM latency per stage - the loop-carried copy of the prefetched value waits for its load):
+//  * layer-0 CTAs: d_sigma of the 64 rows (256 B) rides in the stage's tail [73728, 73984);
+//  * dZ_L-rebuilding CTAs (layer > 0, stage tail [65536, 74752) unused): a ring of kWgIn input slots
+//    (ReLU mask words of the half tile, 8 W bytes, + d_sigma, 256 B) with its own barriers, fetched kWgIn - 1
+//    stages ahead, so generating Y needs only an EMPTY stage and overlaps the latency of the stage's A load.
+constexpr int kWgStageBytes = 74752;
+constexpr int kWgIn = 6;
+constexpr int kWgInBytes = 2304;
 constexpr int kWgSmem = 1024 + kWgStages * kWgStageBytes + 2048;
 
 __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArgs a) {
@@ -905,7 +913,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
   uint8_t* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   float* s_wout = reinterpret_cast<float*>(base + kWgStages * kWgStageBytes);          // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_wout + 256);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 1 + 2 * kWgIn);
   const Net net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -921,6 +929,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
   auto empty_bar = [&](int s) { return smem_u32(&bars[kWgStages + s]); };
   const uint32_t done_bar = smem_u32(&bars[2 * kWgStages]);
+  auto in_full = [&](int j) { return smem_u32(&bars[2 * kWgStages + 1 + j]); };
+  auto in_empty = [&](int j) { return smem_u32(&bars[2 * kWgStages + 1 + kWgIn + j]); };
+  auto in_slot = [&](int j) { return base + (j % kWgStages) * kWgStageBytes + 65536 + (j / kWgStages) * kWgInBytes; };   // masks | d_sigma
 
   const bool gen_y = a.gen_last && (l == net.L - 1);   // this CTA rebuilds dZ_L instead of loading it
   const bool do_out = (l == 0);                        // this CTA also streams A_L and accumulates dW_out
@@ -934,6 +945,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
     // full: the producer's expect_tx arrive (+ the helpers' arrive when they write Y); empty: the MMA commit
     // (+ the helpers' arrive when they read Z)
     for (int s = 0; s < kWgStages; ++s) { mbar_init(full_bar(s), gen_y ? 2 : 1); mbar_init(empty_bar(s), do_out ? 2 : 1); }
+    for (int j = 0; j < kWgIn; ++j) { mbar_init(in_full(j), 1); mbar_init(in_empty(j), 1); }
     mbar_init(done_bar, 1);
     fence_mbar_init();
   }
@@ -947,17 +959,37 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
   const int64_t actL_off = (int64_t)kBlk + (int64_t)(net.L - 1) * net.nb * kBlk;
   const int64_t dzY_off = (int64_t)l * net.nb * kBlk;
   const int64_t n_half = (t1 - t0) * 2;
+  const uint32_t mask_bytes = 8u * (uint32_t)net.W;      // ReLU mask words of one half tile (64 rows x W/32 words)
+  // rows of half tile i all inside [0, P): its 64 d_sigma values can be fetched as one 256-byte bulk copy
+  auto rows_full = [&](int64_t i) { return (t0 + (i >> 1)) * kTile + (i & 1) * 64 + 64 <= a.P; };
 
   if (warp == 0) {
     // ---- producer (whole warp, converged): bulk loads, one column block (64 rows x 128 B = 8 KB) per copy
+    auto issue_in = [&](int64_t j) {     // mask words + d_sigma of half tile j -> input slot j % kWgIn
+      const int sl = (int)(j % kWgIn);
+      mbar_wait_warp(in_empty(sl), (uint32_t)(((j / kWgIn) & 1) ^ 1));
+      const int64_t tile = t0 + (j >> 1);
+      const int hf = (int)(j & 1);
+      const bool full = rows_full(j);
+      const uint32_t dst = smem_u32(in_slot(sl));
+      mbar_expect_tx_warp(in_full(sl), mask_bytes + (full ? 256u : 0u));
+      bulk_g2s_warp(dst, a.masks + tile * mask_tile_bytes(net) + ((int64_t)(net.L - 1) * kTile + hf * 64) * (net.W / 32) * 4,
+                    mask_bytes, in_full(sl));
+      if (full) bulk_g2s_warp(dst + 2048u, a.d_sigma + tile * kTile + hf * 64, 256u, in_full(sl));
+    };
+    if (gen_y)
+      for (int64_t j = 0; j < kWgIn - 1 && j < n_half; ++j) issue_in(j);
     for (int64_t i = 0; i < n_half; ++i) {
+      if (gen_y && i + kWgIn - 1 < n_half) issue_in(i + kWgIn - 1);
       const int s = (int)(i % kWgStages);
       const uint32_t ph = (uint32_t)((i / kWgStages) & 1);
       mbar_wait_warp(empty_bar(s), ph ^ 1u);
       const int64_t tile = t0 + (i >> 1);
       const int hf = (int)(i & 1);
       const uint32_t dstA = smem_u32(base + s * kWgStageBytes), dstY = dstA + offY, dstZ = dstA + offZ;
-      mbar_expect_tx_warp(full_bar(s), bytesA + (gen_y ? 0u : bytesY) + (do_out ? bytesY : 0u));
+      const bool ds_bulk = do_out && rows_full(i);
+      mbar_expect_tx_warp(full_bar(s), bytesA + (gen_y ? 0u : bytesY) + (do_out ? bytesY : 0u) + (ds_bulk ? 256u : 0u));
+      if (ds_bulk) bulk_g2s_warp(dstA + 73728u, a.d_sigma + tile * kTile + hf * 64, 256u, full_bar(s));
       const uint8_t* tile_acts = a.acts + tile * act_tile_bytes(net);
       const uint8_t* srcA = tile_acts + actA_off + hf * 8192;
       const uint8_t* srcY = a.dz + tile * dz_tile_bytes(net) + dzY_off + hf * 8192;
@@ -1007,41 +1039,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
     const int oj = g & 31, rg = g >> 5;
     const bool out_on = do_out && (oj < net.nb * 8);
     const uint32_t out_off = (uint32_t)(oj >> 3) * 8192u + ((uint32_t)((oj & 7) ^ rg) << 4);
-    // inputs of a stage are fetched two stages ahead: their latency under a saturated HBM is longer than a stage
-    auto fetch_gen = [&](int64_t i, float& ds, uint32_t& m0, uint32_t& m1) {
-      ds = 0.f; m0 = 0u; m1 = 0u;
-      if (!gen_y || i >= n_half) return;
-      const int64_t tile = t0 + (i >> 1);
-      const int row = (int)(i & 1) * 64 + r;
-      const int64_t gs = tile * kTile + row;
-      if (gs < a.P) ds = ldg_now(a.d_sigma + gs) * a.gscale;
-      const float* mrow = reinterpret_cast<const float*>(a.masks + tile * mask_tile_bytes(net)) +
-                          ((int64_t)(net.L - 1) * kTile + row) * mwords + qc * (cpt / 32);
-      m0 = __float_as_uint(ldg_now(mrow));
-      if (cpt > 32) m1 = __float_as_uint(ldg_now(mrow + 1));
-    };
-    auto fetch_out = [&](int64_t i, float (&dso)[8]) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) dso[k] = 0.f;
-      if (!do_out || i >= n_half) return;
-      const int64_t gs0 = (t0 + (i >> 1)) * kTile + (int64_t)(i & 1) * 64 + rg;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) if (gs0 + 8 * k < a.P) dso[k] = ldg_now(a.d_sigma + gs0 + 8 * k);
-    };
-    float ds_a, ds_b, dso_a[8];
-    uint32_t ma0, ma1, mb0, mb1;
-    fetch_gen(0, ds_a, ma0, ma1);
-    fetch_gen(1, ds_b, mb0, mb1);
-    fetch_out(0, dso_a);
     for (int64_t i = 0; i < n_half; ++i) {
       const int s = (int)(i % kWgStages);
       const uint32_t ph = (uint32_t)((i / kWgStages) & 1);
       const uint32_t stage = smem_u32(base + s * kWgStageBytes);
+      const int64_t gs_half = (t0 + (i >> 1)) * kTile + (i & 1) * 64;       // first row of this half tile
+      const bool full = rows_full(i);
       if (gen_y) {
-        const float ds = ds_a;
-        const uint32_t mw0 = ma0, mw1 = ma1;
-        ds_a = ds_b; ma0 = mb0; ma1 = mb1;
-        fetch_gen(i + 2, ds_b, mb0, mb1);
+        const int sl = (int)(i % kWgIn);
+        mbar_wait(in_full(sl), (uint32_t)((i / kWgIn) & 1));
+        const uint8_t* in = in_slot(sl);
+        const uint32_t* mrow = reinterpret_cast<const uint32_t*>(in) + r * mwords + qc * (cpt / 32);
+        const uint32_t mw0 = mrow[0], mw1 = cpt > 32 ? mrow[1] : 0u;
+        float ds = full ? reinterpret_cast<const float*>(in + 2048)[r] : (gs_half + r < a.P ? __ldg(a.d_sigma + gs_half + r) : 0.f);
+        ds *= a.gscale;
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t srow = stage + offY + (uint32_t)r * 128u;
         const uint32_t xs = (uint32_t)(r & 7) << 4;
@@ -1068,29 +1079,28 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
           }
         }
         fence_async_smem();
-        asm volatile("bar.sync 1, 256;" ::: "memory");      // all helper threads have written and fenced
-        if (g == 0) mbar_arrive(full_bar(s));
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // all helper threads have read their inputs, written and fenced
+        if (g == 0) { mbar_arrive(full_bar(s)); mbar_arrive(in_empty(sl)); }
       }
       if (do_out) {
-        float dso[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) dso[k] = dso_a[k];
-        fetch_out(i + 1, dso_a);
-        mbar_wait(full_bar(s), ph);                         // the A_L half has landed
+        mbar_wait(full_bar(s), ph);                         // the A_L half (and its d_sigma) have landed
         if (out_on) {
+          const float* sds = reinterpret_cast<const float*>(base + s * kWgStageBytes + 73728);
           const uint32_t zrow = stage + offZ + out_off + (uint32_t)rg * 128u;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
+            const int row = rg + 8 * k;
+            const float dsk = full ? sds[row] : (gs_half + row < a.P ? __ldg(a.d_sigma + gs_half + row) : 0.f);
             uint32_t w0, w1, w2, w3;
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(zrow + (uint32_t)k * 1024u));
             const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w0));
             const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&w1));
             const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w2));
             const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&w3));
-            out_acc[0] = fmaf(dso[k], f0.x, out_acc[0]); out_acc[1] = fmaf(dso[k], f0.y, out_acc[1]);
-            out_acc[2] = fmaf(dso[k], f1.x, out_acc[2]); out_acc[3] = fmaf(dso[k], f1.y, out_acc[3]);
-            out_acc[4] = fmaf(dso[k], f2.x, out_acc[4]); out_acc[5] = fmaf(dso[k], f2.y, out_acc[5]);
-            out_acc[6] = fmaf(dso[k], f3.x, out_acc[6]); out_acc[7] = fmaf(dso[k], f3.y, out_acc[7]);
+            out_acc[0] = fmaf(dsk, f0.x, out_acc[0]); out_acc[1] = fmaf(dsk, f0.y, out_acc[1]);
+            out_acc[2] = fmaf(dsk, f1.x, out_acc[2]); out_acc[3] = fmaf(dsk, f1.y, out_acc[3]);
+            out_acc[4] = fmaf(dsk, f2.x, out_acc[4]); out_acc[5] = fmaf(dsk, f2.y, out_acc[5]);
+            out_acc[6] = fmaf(dsk, f3.x, out_acc[6]); out_acc[7] = fmaf(dsk, f3.y, out_acc[7]);
           }
         }
         __syncwarp();
@@ -1247,7 +1257,8 @@ extern "C" int64_t loner_mlp_packed_bytes(const loner_net_t* n) {
 static inline int64_t n_tiles(int64_t P) { return (P + kTile - 1) / kTile; }
 // Kernel variants are selected by loner_net_t.flags (include/loner_b200.h), never by the environment.
 static inline int pipe_ctas(const Net& net) { return (net.flags & LONER_NET_SINGLE_CTA) ? 1 : 2; }
-static inline bool wgrad_rebuilds_last(const Net& net) { return (net.flags & LONER_NET_STASH_DZL) == 0; }
+// (a single hidden layer keeps the stash: its one wgrad CTA type already fills its stages with A_0, dZ_1 and A_1)
+static inline bool wgrad_rebuilds_last(const Net& net) { return (net.flags & LONER_NET_STASH_DZL) == 0 && net.L >= 2; }
 
 // Launch of a pipelined kernel: one CTA per SM, as CTA pairs (clusters of 2 on one TPC) or single CTAs.
 template <class Kern, class Args>

@@ -80,7 +80,7 @@ def test_model_forward_backward_matches_oracle():
                     grays=norm_relerr(rays.grad[:, :6], r.grad[:, :6]))
         print("dropin: " + " ".join(f"{k} {v:.2e}" for k, v in errs.items()))
         assert errs["z"] < 1e-6 and errs["depth"] < 1e-4 and errs["weights"] < 2e-4 and errs["loss"] < 1e-4
-        assert errs["gparams"] < 2e-2 and errs["grays"] < 5e-2
+        assert errs["gparams"] < 2e-3 and errs["grays"] < 5e-2      # measured (B200): 1.9e-4 and 1.1e-2
         # state_dict round trip and torch.optim.Adam on the flat parameter (optimizer.py:263-267)
         sd = model.state_dict()
         assert "nerf_model._model_sigma.params" in sd

@@ -81,7 +81,7 @@ def test_hash_backward_matches_autograd(name):
     for k, (a, b) in parts.items():
         e = norm_relerr(d_params[a:b], p_ref.grad[a:b])
         print(f"[hash bwd {name}] {k} norm-rel err {e:.2e} (|ref| {float(p_ref.grad[a:b].norm()):.3e})")
-        assert e < 1e-2
+        assert e < 3e-3                      # measured (B200): dW1 2-5e-4, dW_out 2e-5, d_table 1e-7
     assert float(d_params[nw1 + 64:net.n_network_params].abs().max()) == 0.0      # rows 1..15 of the padded output matrix
     e = norm_relerr(d_pos, pos_ref.grad)
     print(f"[hash bwd {name}] d_pos norm-rel err {e:.2e}")
@@ -139,7 +139,7 @@ def test_hash_step_matches_reference_fixture():
     gp = e.d_params.cpu()
     en = norm_relerr(gp, r["params"].grad)
     print(f"[hash step] d_params norm-rel {en:.2e} |g| {float(gp.norm()):.3e} vs fixture {float(g['grad_params_norm']):.3e}")
-    assert en < 2e-2
+    assert en < 5e-3                         # measured (B200): 1.5e-3 (fp16 dh stash vs the oracle's fp32 backward)
     mine = torch.stack([p.grad.cpu() if p.grad is not None else torch.zeros(6) for p in e.poses6])
     ep = norm_relerr(mine, g["grad_poses"])
     print(f"[hash step] pose grads norm-rel vs reference fixture {ep:.2e}")

@@ -173,11 +173,13 @@ def test_mlp_backward_matches_autograd(W, L, P, flags):
             a, b = a[:ni], b[:ni]                  # only row 0 of the padded output matrix is used
         e = norm_relerr(a, b)
         print(f"[mlp bwd W={W} L={L} flags={flags}] layer {li} dW norm-rel err {e:.2e} (|ref| {float(b.norm()):.3e})")
-        assert e < 2e-3                            # fp16 dZ (power-of-two loss scale) vs fp32 autograd; measured ~1e-4..1e-3
+        # fp16 dZ (power-of-two loss scale) vs the oracle's fp32 backward; the rounding of every layer of the chain adds
+        # up: measured (B200) 0.4-3e-4 for L <= 2, <= 1.3e-3 for L = 4, 2.1e-3 for L = 8
+        assert e < 5e-4 * max(4, 2 * L)
         off += no * ni
     e = norm_relerr(d_pos, pos_ref.grad)
     print(f"[mlp bwd W={W} L={L}] d_pos norm-rel err {e:.2e}")
-    assert e < 1e-2
+    assert e < 3e-3                                # measured <= 6.5e-4
     # the variant without d_pos (no layer-0 GEMM, different mask prefetch schedule) must give the same dW
     d_params2 = torch.zeros(net.param_count, device=DEV)
     assert ops.mlp_bwd(net, packed, P, d_sigma.to(DEV), acts, 2.0 ** 12, d_params2, pos=posd, want_dpos=False) is None

@@ -60,12 +60,13 @@ def test_step_matches_reference_fixture(name):
     cos = float(torch.dot(gp, r["params"].grad) / (gp.norm() * r["params"].grad.norm()))
     print(f"[{name}] d_params norm-rel {en:.2e} cosine {cos:.6f} |g| {float(gp.norm()):.3e} vs fixture "
           f"{float(g['grad_params_norm']):.3e}")
-    assert en < 2e-2 and cos > 0.9995
+    assert en < 2e-3 and cos > 0.99999          # measured (B200): 0.9e-4 .. 4.1e-4
     if c.pose_grads:
         mine = torch.stack([p.grad.cpu() if p.grad is not None else torch.zeros(6) for p in e.poses6])
         ep = norm_relerr(mine, g["grad_poses"])
         print(f"[{name}] pose grads norm-rel vs reference fixture {ep:.2e}")
-        # fp16 input-gradient chain (like tcnn's) summed over N*S samples with heavy cancellation
+        # fp16 input-gradient chain (like tcnn's) summed over N*S samples with heavy cancellation: measured (B200)
+        # 0.5e-2 .. 2.7e-2 on these fixtures (the oracle's own fp16-vs-fp32 difference is of the same size)
         assert ep < 5e-2
     # Adam moved the parameters exactly as torch.optim.Adam would with these gradients
     p_ref, _, _ = orc.adam_update(params0.cpu(), gp, torch.zeros_like(gp), torch.zeros_like(gp), 1, 0.01)
