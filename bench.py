@@ -18,6 +18,7 @@ gradients on one global ray set), `c5` (BASELINE configs[4], weak) and at N = 4 
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -170,8 +171,10 @@ def ncu_traffic_bytes(kernel_substr, stash=True):
         for r in rows[2:]:
             if kernel_substr not in r[ki]:
                 continue
-            if kernel_substr == "mlp_fwd" and stash != (", 1" in r[ki] or "true" in r[ki]):
-                continue           # the training step runs the stash variant: mlp_fwd_kernel<W, true, ...>
+            if kernel_substr == "mlp_fwd":      # the training step runs the stash variant: mlp_fwd_kernel<W, true, ...>
+                m = re.search(r"<\s*\d+\s*,\s*(\w+)", r[ki])
+                if m is None or stash != (m.group(1) in ("1", "true")):
+                    continue
             return float(r[ri]) * mult.get(units[ri], 1.0) + float(r[wi]) * mult.get(units[wi], 1.0), rel
     return None, None
 
