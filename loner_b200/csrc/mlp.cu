@@ -1030,8 +1030,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
   if (warp >= 2 && (gen_y || do_out)) {
     // ---- helpers (8 warps; four of them are the epilogue warps, idle during the main loop)
     const int g = tid - 64;                       // 0..255
-    // (a) generator mapping: thread = (row of the 64-sample half tile, quarter of the columns)
-    const int r = g >> 2, qc = g & 3;
+    // (a) generator mapping: warp = (32-row half of the 64-sample half tile, quarter of the columns), lane = row.
+    // Lanes on distinct ROWS make the swizzled 128-bit stores conflict-free (like dgrad's epilogue) and the w_out
+    // reads warp-uniform broadcasts; with lanes spread over column quarters instead every store took 16 and every
+    // w_out load 8 shared-memory wavefronts (ncu), ~3000 clk per stage - the whole cost of round 1's variant.
+    const int r = ((g >> 5) & 1) * 32 + lane, qc = g >> 6;
     const int cpt = net.W / 4;                    // columns per thread: 64 (W=256) or 32 (W=128)
     const int mwords = net.W / 32;
     // (b) dW_out mapping: thread = (16-byte chunk j of a row = 8 columns, rows rg, rg+8, ...): the lanes of a warp
@@ -1317,7 +1320,10 @@ extern "C" int loner_mlp_fwd(const loner_net_t* n, const void* packed, const flo
   a.s_shift = (S > 0 && (S & (S - 1)) == 0) ? __builtin_ctz((unsigned)S) : -1;
   a.tiles = n_tiles(P); a.sigma = sigma; a.acts = (uint8_t*)acts;
   a.masks = acts ? (uint8_t*)acts + a.tiles * act_tile_bytes(net) : nullptr;
-  const int ctas = pipe_ctas(net);
+  // CTA pairs pay off where the shared-memory data pipe is the limit (the training forward: operands + epilogue +
+  // ring + stash copy); the inference forward is bound by the X/Y hand-off latency, which the pair's remote
+  // arrives lengthen (measured 1.48 vs 1.34 ms at C2), so it stays on single CTAs.
+  const int ctas = acts ? pipe_ctas(net) : 1;
   cudaStream_t st = (cudaStream_t)stream;
 #define LONER_FWD(W_, S_) \
   (ctas == 2 ? launch_pipe(mlp_fwd_kernel<W_, S_, 2>, a, a.tiles, 2, st) : launch_pipe(mlp_fwd_kernel<W_, S_, 1>, a, a.tiles, 1, st))
