@@ -1213,13 +1213,17 @@ inline WgradPlan plan_wgrad(const Net& net, bool gen_last) {
   // The kernel is HBM-bound (it streams the A_l and dZ_{l+1} images once): give every layer a share
   // of the SMs proportional to the BYTES it reads per tile, not to its flops.  In 8 KB column blocks per
   // half tile: layer 0 reads A_0 (1) + dZ_1 (nb) + A_L (nb, for dW_out); a middle layer A_l + dZ_{l+1} (2 nb);
-  // the last layer only A_{L-1} when it rebuilds dZ_L (weighted 1.25 nb: its helper warps pace it slightly).
+  // the last layer only A_{L-1} (nb) when it rebuilds dZ_L.
   const int sms = device_sm_count();
   WgradPlan p;
   double wgt[8], total = 0;
   for (int l = 0; l < net.L; ++l) {
     const bool last = (l == net.L - 1);
-    double w = (l == 0 ? 1.0 : (double)net.nb) + ((gen_last && last) ? 0.25 * net.nb : (double)net.nb) + (l == 0 ? (double)net.nb : 0.0);
+    // (a dZ_L-rebuilding CTA keeps only 3 x 32 KB of loads in flight instead of 3 x 64 KB, so under a saturated HBM it
+    // streams at about half the rate of the others: weighted as if it still read dZ_L.  Sweep on a B200, C2, wgrad ms:
+    // weight 0.25 nb 3.04, 0.75 nb 2.34, 1.0 nb 2.26, 1.25 nb 2.26, 1.5 nb 2.26)
+    double w = (l == 0 ? 1.0 : (double)net.nb) + (double)net.nb + (l == 0 ? (double)net.nb : 0.0);
+    (void)last;
     wgt[l] = w;
     total += w;
   }

@@ -17,7 +17,7 @@ def _f32(t):
 
 
 NET_SINGLE_CTA, NET_STASH_DZL = 1, 2      # LONER_NET_* (include/loner_b200.h)
-DEFAULT_NET_FLAGS = NET_SINGLE_CTA | NET_STASH_DZL
+DEFAULT_NET_FLAGS = 0                       # production: CTA pairs, dZ_L rebuilt inside wgrad
 
 
 class Net:

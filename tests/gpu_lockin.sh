@@ -1,12 +1,19 @@
-# One GPU call that refreshes everything under profiles/ (run through gpurun from the repo root).
-set -x
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 300 python bench.py --steps 40 --warmup 5 > gpurun_out/r1_bench_c2.json 2> gpurun_out/r1_bench_c2.err; tail -c 300 gpurun_out/r1_bench_c2.json
-timeout 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 300 python tests/gpu_ab.py > gpurun_out/r1_ab.jsonl 2>&1; cat gpurun_out/r1_ab.jsonl
-timeout 300 python bench.py --workload c3 --steps 20 --warmup 4 > gpurun_out/r1_bench_c3.json 2>/dev/null; cut -c1-150 gpurun_out/r1_bench_c3.json
-timeout 300 python bench.py --workload c5 --steps 10 --warmup 3 > gpurun_out/r1_bench_c5.json 2>/dev/null; cut -c1-150 gpurun_out/r1_bench_c5.json
-timeout 200 python bench.py --workload c2hash --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r1_bench_c2hash.json 2>/dev/null; cut -c1-150 gpurun_out/r1_bench_c2hash.json
-timeout 100 python tests/gpu_hash_bench.py 2>&1 | tail -1
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/r1_launches_bench.log 2>&1; tail -1 gpurun_out/r1_launches.csv | cut -c1-120
-MB_N=8192 timeout 500 ncu --set full --import-source on --clock-control none -k regex:"mlp_(fwd|dgrad|wgrad_kernel)" --launch-skip 4 -c 4 -o gpurun_out/r1_prof -f python tests/gpu_profile_target.py 2>&1 | tail -2
+#!/bin/bash
+# One command that regenerates the round's GPU evidence under gpurun_out/ (run on the GPU box through gpurun):
+#   tests + bench + launch list + ncu --set full of every own kernel at the C2 size.
+# usage: bash tests/gpu_lockin.sh <tag>
+tag=${1:-r2}
+mkdir -p gpurun_out
+(timeout 1500 python -m pytest tests -m gpu -q -s > gpurun_out/${tag}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_pytest.log)
+tail -3 gpurun_out/${tag}_pytest.log
+(timeout 900 python bench.py --steps 40 --warmup 5 > gpurun_out/${tag}_bench_c2.json 2> gpurun_out/${tag}_bench_c2.err)
+(timeout 300 python tests/gpu_ab.py > gpurun_out/${tag}_ab.jsonl 2>&1)
+# launch list of a short bench run (every launch with its device time; shares, not absolutes)
+(timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file gpurun_out/${tag}_launches_raw.csv \
+   python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${tag}_launches_bench.log 2>&1)
+# full counters + source of every own kernel, one launch each, C2 size
+(MB_N=8192 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:loner -s 14 -c 13 \
+   -o gpurun_out/${tag}_prof python tests/gpu_profile_target.py > gpurun_out/${tag}_ncu.log 2>&1)
+ncu -i gpurun_out/${tag}_prof.ncu-rep --page raw --csv 2>/dev/null | python profiles/summarize_ncu.py > gpurun_out/${tag}_ncu_summary.csv
+cuobjdump -sass loner_b200/libloner_b200.so | grep -oE "UTCHMMA[.A-Z0-9]*|UTCBAR[.A-Z0-9]*|LDTM[.A-Z0-9x]*|UBLKCP[.A-Z0-9]*|UCGABAR[_A-Z]*|F2FP[.A-Z0-9_]*|HSET2[.A-Z0-9]*" | sort | uniq -c > gpurun_out/${tag}_sass_mnemonics.txt
+ls -la gpurun_out | tail -20

@@ -29,6 +29,7 @@ scratch = torch.empty(net.bwd_scratch_bytes(P), device=dev, dtype=torch.uint8)
 gs = ops.default_grad_scale(N, S)
 dp = torch.zeros(net.param_count, device=dev)
 m, v = torch.zeros_like(dp), torch.zeros_like(dp)
+params2 = params.clone()
 only = os.environ.get("MB_ONLY", "")
 for rep in range(2):      # rep 0 = warm-up
     counters = torch.zeros(2, dtype=torch.int32, device=dev)
@@ -43,7 +44,7 @@ for rep in range(2):      # rep 0 = warm-up
     ops.mlp_dgrad(net, packed, P, rl["d_sigma"], acts, gs, scratch, rays=rays, z=z)
     ops.mlp_wgrad(net, packed, P, rl["d_sigma"], acts, gs, dp, scratch)
     if not only:
-        ops.adam_step(net and dp * 0 + params, dp, m, v, 1, 0.01)
+        ops.adam_step(params2, dp, m, v, 1, 0.01)
         ops.mlp_pack(net, params)
         ops.ogm_grad(rays, z, depths, wc.scale_factor, 100, flags=flags)
         ops.render_fwd(sigma.view(N, S), z, rays, raw_noise_std=1.0, seed=3)
