@@ -499,11 +499,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
   } else {
     // ---------------- epilogue warps: thread = (sample row, column half); tile X, then tile Y.
     // Stash mode: every finished image (A_0 .. A_L) leaves its tile buffer as ONE bulk copy issued by
-    // the elected thread after the step's barrier.  The steps alternate X, Y, X, ...: before a step writes
-    // its tile buffer, the copy issued from that buffer TWO steps ago must have been read out, while the
-    // copy the previous step issued (other buffer) may still be streaming - stash_gate() waits for exactly
-    // that (round 1 waited for ALL copies, one step early: the copies never overlapped each other and the
-    // epilogue warps sat at the barrier behind the HBM write queue, 18 % of all stall samples).
+    // the elected thread after the step's barrier.  The elected thread waits for the reads of all
+    // earlier copies BEFORE that barrier, and the steps alternate X, Y, X, ... - so whenever a step
+    // starts writing a tile buffer, the copy issued from it two steps ago has been read out.
     const int e = warp - 2;
     const int h = e >> 2;
     const int q = warp & 3;
@@ -523,11 +521,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
     RowIn nxt[2];
 #pragma unroll
     for (int t = 0; t < 2; ++t) nxt[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, row_index(units.pair(units.first), t));
-    bool prev_copied = false;            // (elected thread) the previous step issued a stash copy
-    auto stash_gate = [&]() {            // the copy issued from this step's buffer two steps ago has been read out
-      if (elected) { if (prev_copied) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
-      epi_bar();
-    };
     for (int64_t u = units.first; u < units.count; u += units.stride) {
       const int64_t pair = units.pair(u);
 #pragma unroll
@@ -535,20 +528,19 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
         const int64_t tile = 2 * pair + t;
         const bool active = tile < a.tiles;
         const uint32_t sA = sm.tileA(t);
-        if (kStash) stash_gate();
         {
           float x[3];
           row_pos01(pos_mode, nxt[t], x);
           encode_row(sA, row, h, x, sm.enc_tab());
         }
         fence_async_smem();
+        if (kStash && elected) bulk_wait_read0();
         arrive_a<kCtas>(a_rdy[t], lane);
         if (u + units.stride < units.count)
           nxt[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, row_index(units.pair(u + units.stride), t));
         if (kStash) {
           epi_bar();
           if (elected && active) { bulk_s2g(a.acts + tile * act_tile_bytes(net), sA, (uint32_t)kBlk); bulk_commit(); }
-          prev_copied = active;
         }
       }
       for (int l = 0; l < net.L; ++l) {
@@ -564,7 +556,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
           float* part = sm.part() + t * 128;
           mbar_wait(sm.acc_full(t), par_acc);
           tc_fence_after();
-          if (kStash) stash_gate();
           float sig0 = 0.f, sig1 = 0.f;
           uint32_t mbits[kCols / 32];
           drain32<kCols>(acc_base + t * 256, [&](int i, uint32_t (&v)[32]) {
@@ -598,6 +589,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
             }
           }
           if (!last || kStash) fence_async_smem();     // the image becomes visible to the MMA / bulk-copy engines
+          if (kStash && elected) bulk_wait_read0();
           if (!last) arrive_a<kCtas>(a_rdy[t], lane);
           else if (h == 1) part[row] = sig;
           if (kStash || last) epi_bar();
@@ -606,7 +598,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
             bulk_s2g(a.acts + tile * act_tile_bytes(net) + kBlk + (int64_t)l * kNb * kBlk, sA, (uint32_t)(kNb * kBlk));
             bulk_commit();
           }
-          if (kStash) prev_copied = active;
         }
         par_acc ^= 1u;
       }
@@ -747,11 +738,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
     const uint32_t a_rdy[2] = {kCtas == 2 ? mapa_u32(sm.a_ready(0), 0) : sm.a_ready(0),
                                kCtas == 2 ? mapa_u32(sm.a_ready(1), 0) : sm.a_ready(1)};
     const int64_t next_tile = 2 * (int64_t)gridDim.x;     // this thread's tile t of the NEXT unit (both variants)
-    bool prev_copied = false;            // (elected thread) the previous step issued a stash copy
-    auto stash_gate = [&]() {            // see mlp_fwd_kernel: the copy issued from this buffer two steps ago has been read
-      if (elected) { if (prev_copied) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
-      epi_bar();
-    };
     for (int64_t u = units.first; u < units.count; u += units.stride) {
       const int64_t pair = units.pair(u);
       RowIn rin[2];
@@ -764,7 +750,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
         const uint32_t stile = sm.tileA(t);
         const uint32_t srow = stile + row * 128;
         if (want_dx && h == 0) rin[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, in ? gs : a.P - 1);
-        stash_gate();
         // dZ_L = d_sigma * w_out * relu'(Z_L)
 #pragma unroll
         for (int it = 0; it < kMw; ++it) {
@@ -788,13 +773,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
           ds[t] = load_ds(tile + next_tile);
         }
         fence_async_smem();
+        if (elected) bulk_wait_read0();
         arrive_a<kCtas>(a_rdy[t], lane);
         epi_bar();
         if (a.stash_last && elected && active) {
           bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(net.L - 1) * kNb * kBlk, stile, (uint32_t)(kNb * kBlk));
           bulk_commit();
         }
-        prev_copied = a.stash_last && active;
       }
       for (int l = net.L - 1; l >= l_lo; --l) {
 #pragma unroll
@@ -810,7 +795,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
           if (l >= 1) {
             // dZ_l = dA_l * relu'(Z_l)  -> fp16 image (next GEMM's A operand in smem, wgrad's B operand in HBM)
             const bool feeds_gemm = (l - 1 >= l_lo);
-            stash_gate();
             drain32<kCols>(acc_row + t * 256 + h * kCols, [&](int i, uint32_t (&v)[32]) {
               const uint32_t bits = mw[t][i];
 #define LONER_DZ(P) v[P] = cvt_sat_h2(__uint_as_float(v[2 * P]), __uint_as_float(v[2 * P + 1])) & half2_mask<P>(bits);
@@ -828,13 +812,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
               ds[t] = load_ds(tile + next_tile);
             }
             fence_async_smem();
+            if (elected) bulk_wait_read0();
             if (feeds_gemm) arrive_a<kCtas>(a_rdy[t], lane);
             epi_bar();
             if (elected && active) {
               bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(l - 1) * kNb * kBlk, stile, (uint32_t)(kNb * kBlk));
               bulk_commit();
             }
-            prev_copied = active;
           } else {
             // l == 0: dEnc [128 x Epad] -> d_pos through the sin/cos encoding (lower-half warps only)
             if (h == 0) {
@@ -871,7 +855,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
             tc_fence_before();
             load_masks(tile + next_tile, net.L - 1, mw[t]);
             ds[t] = load_ds(tile + next_tile);
-            prev_copied = false;               // this step wrote nothing to its tile buffer and issued no copy
           }
         }
         par_acc ^= 1u;
