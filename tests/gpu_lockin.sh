@@ -12,7 +12,7 @@ tail -3 gpurun_out/${tag}_pytest.log
 (timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file gpurun_out/${tag}_launches_raw.csv \
    python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${tag}_launches_bench.log 2>&1)
 # full counters + source of every own kernel, one launch each, C2 size
-(MB_N=8192 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:loner -s 14 -c 13 \
+(MB_N=8192 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'^(adam|mlp_|ogm_|pack|ray_|render|sample_|wgrad_|hash_|points_)' -s 14 -c 13 \
    -o gpurun_out/${tag}_prof python tests/gpu_profile_target.py > gpurun_out/${tag}_ncu.log 2>&1)
 ncu -i gpurun_out/${tag}_prof.ncu-rep --page raw --csv 2>/dev/null | python profiles/summarize_ncu.py > gpurun_out/${tag}_ncu_summary.csv
 cuobjdump -sass loner_b200/libloner_b200.so | grep -oE "UTCHMMA[.A-Z0-9]*|UTCBAR[.A-Z0-9]*|LDTM[.A-Z0-9x]*|UBLKCP[.A-Z0-9]*|UCGABAR[_A-Z]*|F2FP[.A-Z0-9_]*|HSET2[.A-Z0-9]*" | sort | uniq -c > gpurun_out/${tag}_sass_mnemonics.txt
