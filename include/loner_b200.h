@@ -183,6 +183,12 @@ int loner_render_loss(const float* sigma, const float* z_vals, const float* rays
                       float* weights, float* depth, float* opacity, float* variance, float* eps_dyn,
                       float* d_sigma, float* d_rays, void* stream);
 
+/* the scalar loss of Optimizer.compute_loss (mapping/optimizer.py:486-491, :568-580) and the mean margin `_depth_eps`
+ * (:503) from loss_acc / counts as loner_render_loss left them (after the multi-GPU all-reduce, if any):
+ * out6 = {loss, mean eps_dyn, depth loss, LOS loss, opacity loss, #valid rays}. */
+int loner_loss_finalize(const float* loss_acc, const int32_t* counts, float depthloss_lambda, float los_lambda,
+                        int32_t S, float* out6, void* stream);
+
 /* d_pos [n,S,3] -> d_rays [n,13] += (origin: sum_s d_pos; direction: sum_s z*d_pos). */
 int loner_points_bwd(const float* d_pos, const float* z_vals, int64_t n, int32_t S, float* d_rays,
                      void* stream);

@@ -91,7 +91,28 @@ ogm_grad_kernel(const float* __restrict__ rays, const float* __restrict__ z_vals
   flush();
 }
 
+// loss = depth_lambda * mean_opaque(sq depth err) + los_lambda * mean_{valid rays, samples}|w - w_gt| + mean_opaque|A - 1|
+// (optimizer.py:486-491, :568-580) from the sums the loss kernel accumulated, and the mean dynamic margin
+// `_depth_eps` (optimizer.py:503): one launch instead of a dozen 1-element ATen kernels per step.
+__global__ void loss_finalize_kernel(const float* __restrict__ acc, const int32_t* __restrict__ counts, float depth_lambda,
+                                     float los_lambda, int S, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float n_valid = (float)counts[0], n_opaque = (float)counts[1];
+  const float depth_loss = acc[0] / n_opaque, los = acc[1] / (n_valid * (float)S), opac = acc[2] / n_opaque;
+  out[0] = depth_lambda * depth_loss + los_lambda * los + opac;
+  out[1] = acc[3] / n_valid;
+  out[2] = depth_loss; out[3] = los; out[4] = opac; out[5] = n_valid;
+}
+
 }  // namespace loner
+
+extern "C" int loner_loss_finalize(const float* loss_acc, const int32_t* counts, float depthloss_lambda, float los_lambda,
+                                   int32_t S, float* out6, void* stream) {
+  if (!loss_acc || !counts || !out6 || S <= 0) return LONER_E_BAD_ARG;
+  loner::loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(loss_acc, counts, depthloss_lambda, los_lambda, S, out6);
+  LONER_CHECK_LAUNCH();
+  return LONER_OK;
+}
 
 extern "C" int loner_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
                                int32_t step, float lr, float beta1, float beta2, float eps, float grad_unscale,

@@ -6,6 +6,7 @@
 // get_weights_gt (/root/reference/src/models/losses.py:29-51),
 // calculate_JS_divergence (/root/reference/src/mapping/optimizer.py:614-626) and the autograd
 // backward of all of them w.r.t. sigma and |d|.
+#include <cstdint>
 #include "common.cuh"
 
 namespace loner {
@@ -234,6 +235,204 @@ render_kernel(const float* __restrict__ sigma, const float* __restrict__ z_vals,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Register variant of render_kernel for S = 32 * kSpl (kSpl = 4, 8, 12, 16: S = 128 ... 512, the training sizes).
+// Lane i owns the kSpl CONTIGUOUS samples [i kSpl, (i+1) kSpl): one 16-byte load per 4 samples, the
+// transmittance product and the backward suffix sums are sequential inside the lane plus ONE warp scan of the
+// lane totals (the smem variant above walks S/32 dependent warp scans), every per-sample quantity (z, w, T, e, r,
+// target weight) lives in registers and is computed once, and Philox is called once per PAIR of normals.
+// Same arithmetic per sample; only the association of the running product / sums differs (fp32 rounding level).
+template <int MODE, int kSpl>
+__global__ void __launch_bounds__(kRenderWarps * 32)
+render_reg_kernel(const float* __restrict__ sigma, const float* __restrict__ z_vals, const float* __restrict__ rays,
+                  const float* __restrict__ depths, const uint8_t* __restrict__ flags, int64_t n,
+                  const float* __restrict__ noise, float noise_std, uint64_t seed, const int32_t* __restrict__ counts,
+                  LossCfg cfg, float* __restrict__ loss_acc, float* __restrict__ weights, float* __restrict__ depth_out,
+                  float* __restrict__ opacity_out, float* __restrict__ variance_out, float* __restrict__ eps_out,
+                  float* __restrict__ d_sigma, float* __restrict__ d_rays) {
+  constexpr int S = 32 * kSpl;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kRenderWarps + warp;
+  if (ray >= n) return;
+  const int64_t base = ray * S + (int64_t)lane * kSpl;
+  const float* R = rays + ray * LONER_RAY_COLS;
+  const float dx = R[3], dy = R[4], dz = R[5], far = R[12];
+  const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);               // rendering_tcnn.py:100
+  const unsigned fl = flags ? flags[ray] : (LONER_FLAG_VALID | LONER_FLAG_OPAQUE);
+  auto store4 = [&](float* dst, const float (&v)[kSpl]) {
+#pragma unroll
+    for (int k = 0; k < kSpl; k += 4) *reinterpret_cast<float4*>(dst + base + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+  };
+  if (!(fl & LONER_FLAG_VALID)) {   // filtered-out row (ray_utils.py:321-322): contributes nothing
+    float zero[kSpl];
+#pragma unroll
+    for (int k = 0; k < kSpl; ++k) zero[k] = 0.f;
+    if (weights) store4(weights, zero);
+    if (MODE == 1) store4(d_sigma, zero);
+    if (lane == 0) {
+      if (depth_out) depth_out[ray] = 0.f;
+      if (opacity_out) opacity_out[ray] = 0.f;
+      if (variance_out) variance_out[ray] = 0.f;
+      if (eps_out) eps_out[ray] = 0.f;
+    }
+    return;
+  }
+  float z[kSpl], r[kSpl], e[kSpl], w[kSpl], T[kSpl];
+#pragma unroll
+  for (int k = 0; k < kSpl; k += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(z_vals + base + k);
+    const float4 b = *reinterpret_cast<const float4*>(sigma + base + k);
+    z[k] = a.x; z[k + 1] = a.y; z[k + 2] = a.z; z[k + 3] = a.w;
+    r[k] = b.x; r[k + 1] = b.y; r[k + 2] = b.z; r[k + 3] = b.w;       // sigma for now
+  }
+  if (noise_std > 0.f) {
+    if (noise) {
+#pragma unroll
+      for (int k = 0; k < kSpl; k += 4) {
+        const float4 c = *reinterpret_cast<const float4*>(noise + base + k);
+        r[k] = __fadd_rn(r[k], c.x * noise_std); r[k + 1] = __fadd_rn(r[k + 1], c.y * noise_std);
+        r[k + 2] = __fadd_rn(r[k + 2], c.z * noise_std); r[k + 3] = __fadd_rn(r[k + 3], c.w * noise_std);
+      }
+    } else {
+      const Philox rng(seed);
+#pragma unroll
+      for (int k = 0; k < kSpl; k += 2) {           // base + k is even: one Philox call serves indices (2c, 2c + 1)
+        const uint4 q = rng((uint64_t)((base + k) >> 1), 3u);
+        const float2 g = box_muller(q.x, q.y);
+        r[k] = __fadd_rn(r[k], g.x * noise_std);
+        r[k + 1] = __fadd_rn(r[k + 1], g.y * noise_std);
+      }
+    }
+  }
+  const float z_next_lane = __shfl_down_sync(kFull, z[0], 1);
+  // ---- forward                                        rendering_tcnn.py:93-129
+  float prod = 1.0f;                                     // running product of (1 - alpha + 1e-10) inside the lane
+#pragma unroll
+  for (int k = 0; k < kSpl; ++k) {
+    const float zn = (k + 1 < kSpl) ? z[k + 1] : z_next_lane;
+    const bool last = (lane == 31 && k == kSpl - 1);
+    float delta = last ? 1e10f : __fsub_rn(zn, z[k]);
+    delta = __fmul_rn(delta, dnorm);
+    r[k] = fmaxf(r[k], 0.f);
+    e[k] = expf(-__fmul_rn(delta, r[k]));
+    const float alpha = __fsub_rn(1.0f, e[k]);
+    T[k] = prod;                                         // exclusive, inside the lane
+    w[k] = alpha;
+    prod *= __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);   // rendering_tcnn.py:113-115
+  }
+  {
+    const float incl = warp_incl_scan_prod(prod, lane);
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 1.0f;
+#pragma unroll
+    for (int k = 0; k < kSpl; ++k) { T[k] *= excl; w[k] *= T[k]; }
+  }
+  float a_sum = 0.f, z_sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < kSpl; ++k) { a_sum += w[k]; z_sum += w[k] * z[k]; }
+  const float A = warp_sum(a_sum), Z = warp_sum(z_sum);
+  const float D = Z + (1.0f - A) * far;                                    // rendering_tcnn.py:125-129
+  const float scale = cfg.scale;
+  float ms = 0.f;
+#pragma unroll
+  for (int k = 0; k < kSpl; ++k) ms += (z[k] * scale) * w[k];
+  const float mean = warp_sum(ms) / (A + 1e-10f);
+  float var_out = 0.f, var_js = 0.f;
+#pragma unroll
+  for (int k = 0; k < kSpl; ++k) {
+    var_out += w[k] * (D - z[k]) * (D - z[k]);
+    const float ds = z[k] * scale - mean;
+    var_js += ds * ds * w[k];
+  }
+  var_out = warp_sum(var_out);
+  var_js = warp_sum(var_js) / (A + 1e-10f) + 1e-10f;
+  if (weights) store4(weights, w);
+  if (lane == 0) {
+    if (depth_out) depth_out[ray] = D;
+    if (opacity_out) opacity_out[ray] = A;
+    if (variance_out) variance_out[ray] = var_out;
+  }
+  if (MODE == 0) return;
+
+  // ---- loss (optimizer.py:460-591)
+  const bool opaque = fl & LONER_FLAG_OPAQUE;
+  const float G = depths[ray] * scale;
+  const float stdv = sqrtf(var_js);
+  const float s0 = cfg.eps_min / 3.0f;
+  const float mm = 0.5f * (G + mean);
+  const float sm = 0.5f * sqrtf(s0 * s0 + stdv * stdv);
+  float js = 0.5f * kl_gauss(G, s0, mm, sm) + 0.5f * kl_gauss(mean, stdv, mm, sm);
+  if (js < cfg.min_js) js = 0.f;
+  if (js > cfg.max_js) js = cfg.max_js;
+  const float eps = cfg.fixed_eps > 0.f ? cfg.fixed_eps : cfg.eps_min * (1.0f + cfg.alpha * js);
+  if (eps_out && lane == 0) eps_out[ray] = eps;
+  // target weights (losses.py:29-51)
+  const float sg = eps / 3.0f;
+  const float ca = __fdiv_rn(__fsub_rn(__fsub_rn(G, eps), G), sg);
+  const float cb = __fdiv_rn(__fsub_rn(__fadd_rn(G, eps), G), sg);
+  const float cdf_d = 0.5f * (1.0f + erff(cb * 0.70710678118654752f)) - 0.5f * (1.0f + erff(ca * 0.70710678118654752f));
+  const float lo_edge = __fsub_rn(G, eps), hi_edge = __fadd_rn(G, eps);
+  float t[kSpl];
+  float wn = 0.f;
+#pragma unroll
+  for (int k = 0; k < kSpl; ++k) {
+    const float s_m = z[k] * scale;
+    float v = 0.f;
+    if (opaque && (s_m > lo_edge) && (hi_edge > s_m)) {
+      const float x = (s_m - G) / sg;
+      v = 0.3989422804014327f * expf(-0.5f * (x * x)) / sg / cdf_d;
+    }
+    t[k] = v;
+    wn += v;
+  }
+  wn = warp_sum(wn) + 1e-6f;
+  const float n_valid = (float)counts[0], n_opaque = (float)counts[1];
+  const float k_los = cfg.los_lambda / (n_valid * (float)S);
+  const float derr = D * scale - G;
+  const float k_depth = opaque ? cfg.depth_lambda * 2.0f * derr * scale / n_opaque : 0.f;
+  const float k_opac = opaque ? ((A - 1.0f) > 0.f ? 1.f : ((A - 1.0f) < 0.f ? -1.f : 0.f)) / n_opaque : 0.f;
+  float l1 = 0.f;
+  float gsum = 0.f;                       // sum over the lane's samples of g_k w_k
+#pragma unroll
+  for (int k = 0; k < kSpl; ++k) {
+    const float df = w[k] - (opaque ? t[k] / wn : 0.f);
+    l1 += cfg.l2 ? df * df : fabsf(df);
+    const float sgn = cfg.l2 ? 2.0f * df : (df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f));
+    t[k] = k_los * sgn + k_depth * (z[k] - far) + k_opac;      // t now holds dL/dw_k
+    gsum += t[k] * w[k];
+  }
+  l1 = warp_sum(l1);
+  if (lane == 0) {
+    if (opaque) { atomicAdd(loss_acc + 0, derr * derr); atomicAdd(loss_acc + 2, fabsf(A - 1.0f)); }
+    atomicAdd(loss_acc + 1, l1);
+    atomicAdd(loss_acc + 3, eps);
+  }
+  // ---- backward: d_alpha_k = g_k T_k - (sum_{j>k} g_j w_j) / (1 - alpha_k + 1e-10)
+  float after = warp_incl_suffix_sum(gsum, lane) - gsum;       // samples of the lanes behind this one
+  float dnorm_acc = 0.f;
+#pragma unroll
+  for (int k = kSpl - 1; k >= 0; --k) {
+    const float alpha = 1.0f - e[k];
+    const float v = (1.0f - alpha) + 1e-10f;
+    const float d_alpha = t[k] * T[k] - after / v;
+    after += t[k] * w[k];
+    const float zn = (k + 1 < kSpl) ? z[k + 1] : z_next_lane;
+    const bool last = (lane == 31 && k == kSpl - 1);
+    const float dzk = last ? 1e10f : (zn - z[k]);
+    const float pos = r[k] > 0.f ? 1.f : 0.f;
+    dnorm_acc += d_alpha * dzk * r[k] * e[k];
+    T[k] = d_alpha * (dzk * dnorm) * e[k] * pos;               // T now holds d_sigma_k
+  }
+  store4(d_sigma, T);
+  const float g_norm = warp_sum(dnorm_acc);
+  if (d_rays && lane == 0) {
+    float* g = d_rays + ray * LONER_RAY_COLS;
+    const float kk = g_norm / dnorm;
+    g[3] += kk * dx; g[4] += kk * dy; g[5] += kk * dz;
+    g[12] += k_depth * (1.0f - A);   // depth = sum w z + (1 - A) * far   (rendering_tcnn.py:125-129)
+  }
+}
+
 // generic backward of raw2outputs given upstream gradients
 __global__ void __launch_bounds__(kRenderWarps * 32)
 render_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ z_vals, const float* __restrict__ rays,
@@ -282,6 +481,19 @@ render_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ z_v
 
 }  // namespace loner
 
+// S = 128 / 256 / 384 / 512 with 16-byte aligned rows run on the register variant
+template <int MODE, class... Args>
+static bool launch_render_reg(int S, unsigned blocks, cudaStream_t st, Args... args) {
+  switch (S) {
+    case 128: loner::render_reg_kernel<MODE, 4><<<blocks, loner::kRenderWarps * 32, 0, st>>>(args...); return true;
+    case 256: loner::render_reg_kernel<MODE, 8><<<blocks, loner::kRenderWarps * 32, 0, st>>>(args...); return true;
+    case 384: loner::render_reg_kernel<MODE, 12><<<blocks, loner::kRenderWarps * 32, 0, st>>>(args...); return true;
+    case 512: loner::render_reg_kernel<MODE, 16><<<blocks, loner::kRenderWarps * 32, 0, st>>>(args...); return true;
+    default: return false;
+  }
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 static int render_smem(int S, size_t* out) {
   *out = (size_t)loner::kRenderWarps * 4 * S * sizeof(float);
   return *out <= 200 * 1024;
@@ -298,6 +510,11 @@ extern "C" int loner_render_fwd(const float* sigma, const float* z_vals, const f
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const unsigned blocks = (unsigned)((n + loner::kRenderWarps - 1) / loner::kRenderWarps);
   loner::LossCfg cfg{1.f, 0.5f, 1.f, 10.f, 1.f, 0.f, 0.f, 0, 0.f};
+  const bool al = aligned16(sigma) && aligned16(z_vals) && aligned16(noise) && aligned16(weights);
+  if (!(al && launch_render_reg<0>(S, blocks, (cudaStream_t)stream, sigma, z_vals, rays, (const float*)nullptr,
+                                   (const uint8_t*)nullptr, n, noise, raw_noise_std, seed, (const int32_t*)nullptr, cfg,
+                                   (float*)nullptr, weights, depth, opacity, variance, (float*)nullptr, (float*)nullptr,
+                                   (float*)nullptr)))
   k<<<blocks, loner::kRenderWarps * 32, smem, (cudaStream_t)stream>>>(
       sigma, z_vals, rays, nullptr, nullptr, n, S, noise, raw_noise_std, seed, nullptr, cfg, nullptr, weights, depth,
       opacity, variance, nullptr, nullptr, nullptr);
@@ -321,6 +538,9 @@ extern "C" int loner_render_loss(const float* sigma, const float* z_vals, const 
   const unsigned blocks = (unsigned)((n + loner::kRenderWarps - 1) / loner::kRenderWarps);
   const float* c = loss_cfg9_host;
   loner::LossCfg cfg{c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7] != 0.f ? 1 : 0, c[8]};
+  const bool al = aligned16(sigma) && aligned16(z_vals) && aligned16(noise) && aligned16(weights) && aligned16(d_sigma);
+  if (!(al && launch_render_reg<1>(S, blocks, (cudaStream_t)stream, sigma, z_vals, rays, depths, flags, n, noise, raw_noise_std,
+                                   seed, counts, cfg, loss_acc, weights, depth, opacity, variance, eps_dyn, d_sigma, d_rays)))
   k<<<blocks, loner::kRenderWarps * 32, smem, (cudaStream_t)stream>>>(
       sigma, z_vals, rays, depths, flags, n, S, noise, raw_noise_std, seed, counts, cfg, loss_acc, weights, depth,
       opacity, variance, eps_dyn, d_sigma, d_rays);

@@ -509,11 +509,10 @@ class MappingEngine:
                               self._lr(cfg.lrate_sigma_mlp))
                 self._pack()
             self.launches += 2
-        cnt = counters.to(torch.float32)
-        los_lambda = cfg.los_lambda_at(self.global_step)
-        loss = (cfg.depthloss_lambda * loss_acc[0] / cnt[1] + los_lambda * loss_acc[1] / (cnt[0] * cfg.n_samples)
-                + loss_acc[2] / cnt[1])
-        self.last.update(loss_acc=loss_acc.clone(), counters=counters, depth_eps=loss_acc[3] / cnt[0])
+        fin = ops.loss_finalize(loss_acc, counters, cfg.depthloss_lambda, cfg.los_lambda_at(self.global_step), cfg.n_samples)
+        self.launches += 1
+        loss = fin[0]
+        self.last.update(loss_terms=fin, counters=counters, depth_eps=fin[1])
         return loss
 
     def _occupancy_update(self, rays, depths, flags=None):

@@ -57,6 +57,7 @@ _SIGS = {
     "loner_render_bwd": (_c.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _f32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "loner_render_loss": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _f32, _u64, _vp, _vp, _vp,
                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "loner_loss_finalize": (_c.c_int, [_vp, _vp, _f32, _f32, _i32, _vp, _vp]),
     "loner_points_bwd": (_c.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "loner_adam_step": (_c.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "loner_ogm_grad": (_c.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp]),

@@ -282,6 +282,15 @@ def render_loss(sigma, z, rays, depths, flags, counts, loss_cfg, noise=None, raw
     return out
 
 
+def loss_finalize(loss_acc, counts, depthloss_lambda, los_lambda, S, out=None):
+    """-> float[6] = loss, mean eps_dyn, depth loss, LOS loss, opacity loss, #valid rays (device, no sync)."""
+    if out is None:
+        out = torch.empty(6, device=loss_acc.device, dtype=torch.float32)
+    L.check(L.load().loner_loss_finalize(L.ptr(loss_acc), L.ptr(counts), float(depthloss_lambda), float(los_lambda), int(S),
+                                         L.ptr(out), L.stream_ptr()), "loner_loss_finalize")
+    return out
+
+
 def points_bwd(d_pos, z, d_rays):
     n, S = z.shape
     L.check(L.load().loner_points_bwd(L.ptr(_f32(d_pos)), L.ptr(_f32(z)), n, S, L.ptr(d_rays), L.stream_ptr()),
