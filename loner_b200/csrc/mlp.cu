@@ -123,7 +123,7 @@ __global__ void pack_kernel(Net net, const float* __restrict__ params, uint8_t* 
 //    reads 192 KB of operands (ncu: l1tex__data_pipe_tc_wavefronts), the epilogue stores 64 KB, the
 //    weight ring receives 128 KB and the stash copy reads 64 KB - 448 KB against 2048 tensor clocks.
 //    The next step is cta_group::2 (each SM holds half of B): -64 KB operands, -64 KB ring per tile-layer.
-constexpr int kPipeThreads = 352;   // warp 0 producer, 1 MMA issuer / relay, 2-9 epilogue, 10 stash copier
+constexpr int kPipeThreads = 320;
 constexpr int kGroupThreads = 256;
 constexpr int kRingBytes = 98304;                    // weight ring: 3 x 32 KB (one CTA) or 6 x 16 KB (CTA pair)
 constexpr int kPipeExtra = 2576;
@@ -153,9 +153,6 @@ struct PipeSmem {
   __device__ __forceinline__ uint32_t a_ready(int t) const { return bars() + 8u * (2 * kSlots + t); }
   __device__ __forceinline__ uint32_t acc_full(int t) const { return bars() + 8u * (2 * kSlots + 2 + t); }
   __device__ __forceinline__ uint32_t w_peer(uint32_t i) const { return bars() + 8u * (2 * kSlots + 4 + i); }
-  // stash hand-off: the epilogue warps have written (and fenced) tile t's image / the copy out of tile t has been read
-  __device__ __forceinline__ uint32_t img_ready(int t) const { return bars() + 8u * (3 * kSlots + 4 + t); }
-  __device__ __forceinline__ uint32_t buf_free(int t) const { return bars() + 8u * (3 * kSlots + 6 + t); }
   __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(base + kX + 2304); }
   // encoding table: feature pair p -> {kind, 2^f}; kind 0..2 = input dimension, 3 = padding ones, 4 = zeros
   __device__ __forceinline__ uint2* enc_tab() const { return reinterpret_cast<uint2*>(base + kX + 2320); }
@@ -183,10 +180,7 @@ __device__ __forceinline__ void pipe_init(const PipeSmem<kCtas>& sm, int tid, in
       if (kCtas == 2) mbar_init(sm.w_peer(i), 1);
     }
     // pair: one arrive per epilogue WARP of either CTA (8 + 8); single CTA: one per epilogue thread
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(sm.a_ready(t), kCtas == 2 ? 16 : kGroupThreads); mbar_init(sm.acc_full(t), 1);
-      mbar_init(sm.img_ready(t), 8); mbar_init(sm.buf_free(t), 1);       // one arrive per epilogue warp / by the copier
-    }
+    for (int t = 0; t < 2; ++t) { mbar_init(sm.a_ready(t), kCtas == 2 ? 16 : kGroupThreads); mbar_init(sm.acc_full(t), 1); }
     fence_mbar_init();
   }
   for (int j = tid; j < W; j += kPipeThreads) sm.wout()[j] = wout_src[j];
@@ -212,45 +206,6 @@ __device__ __forceinline__ void arrive_a(uint32_t a_ready_addr, int lane) {
   } else {
     mbar_arrive(a_ready_addr);
   }
-}
-
-// Stash copier (warp 10, lane 0).  The images the epilogue warps finish (activations in the forward, layer gradients
-// in dgrad) leave their tile buffer as ONE bulk copy each.  Round 1 issued them from an elected epilogue thread
-// behind a 256-thread barrier, after that thread had waited for the previous copy to drain: every step parked
-// all eight epilogue warps at the barrier behind the HBM write queue (ncu: 22 % of the kernel's stall samples).
-// Now the epilogue warps only ARRIVE on img_ready(t) and go on; this warp waits for the image, issues the copy, and
-// hands the buffer back (buf_free(t)) once the copy has been READ out of shared memory - one copy may stay in
-// flight while the next image is being produced.
-struct StashCopier {       // (scalars and a compile-time tile index: nothing may end up in local memory)
-  uint32_t img0, img1, fre0, fre1;
-  uint32_t par0 = 0u, par1 = 0u;
-  uint32_t prev_free = 0u;  // buf_free barrier of the previous step's buffer (0: none yet)
-  template <int t>
-  __device__ __forceinline__ void step(bool copy, void* dst, uint32_t src, uint32_t bytes) {
-    mbar_wait(t == 0 ? img0 : img1, t == 0 ? par0 : par1);
-    if (t == 0) par0 ^= 1u; else par1 ^= 1u;
-    if (copy) bulk_s2g(dst, src, bytes);
-    bulk_commit();                                     // an empty group keeps the group count = step count
-    if (prev_free) { bulk_wait_read<1>(); mbar_arrive(prev_free); }
-    prev_free = t == 0 ? fre0 : fre1;
-  }
-  __device__ __forceinline__ void finish() {
-    if (prev_free) { bulk_wait_read<0>(); mbar_arrive(prev_free); }
-    bulk_wait0();                                      // global writes complete before the kernel ends
-  }
-};
-// Epilogue side: the n-th write into tile buffer t waits for the copy issued after write n-1 to have been read out.
-struct StashGate {
-  uint32_t n0 = 0u, n1 = 0u;
-  __device__ __forceinline__ void before_write(uint32_t buf_free_bar, int t) {   // t is a constant after unrolling
-    const uint32_t n = t == 0 ? n0 : n1;
-    if (n > 0) mbar_wait(buf_free_bar, (n - 1u) & 1u);
-    if (t == 0) ++n0; else ++n1;
-  }
-};
-__device__ __forceinline__ void arrive_warp(uint32_t bar, int lane) {   // all lanes have written + fenced
-  __syncwarp();
-  if (lane == 0) mbar_arrive(bar);
 }
 
 template <int kCtas>
@@ -541,37 +496,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
         }
       }
     }
-  } else if (warp == 10) {
-    // ---------------- stash copier: A_0 .. A_L of every tile, in the epilogue's step order
-    if (kStash && lane == 0) {
-      StashCopier cp;
-      cp.img0 = sm.img_ready(0); cp.img1 = sm.img_ready(1); cp.fre0 = sm.buf_free(0); cp.fre1 = sm.buf_free(1);
-      for (int64_t u = units.first; u < units.count; u += units.stride) {
-        const int64_t tx = 2 * units.pair(u), ty = tx + 1;
-        uint8_t* gx = a.acts + tx * act_tile_bytes(net);
-        uint8_t* gy = a.acts + ty * act_tile_bytes(net);
-        cp.step<0>(tx < a.tiles, gx, sm.tileA(0), (uint32_t)kBlk);
-        cp.step<1>(ty < a.tiles, gy, sm.tileA(1), (uint32_t)kBlk);
-        for (int l = 0; l < net.L; ++l) {
-          const int64_t off = kBlk + (int64_t)l * kNb * kBlk;
-          cp.step<0>(tx < a.tiles, gx + off, sm.tileA(0), (uint32_t)(kNb * kBlk));
-          cp.step<1>(ty < a.tiles, gy + off, sm.tileA(1), (uint32_t)(kNb * kBlk));
-        }
-      }
-      cp.finish();
-    }
   } else {
     // ---------------- epilogue warps: thread = (sample row, column half); tile X, then tile Y.
-    // Stash mode: every finished image (A_0 .. A_L) is handed to the copier warp (img_ready), which sends it to
-    // HBM as ONE bulk copy and returns the tile buffer (buf_free) - see StashCopier.
+    // Stash mode: every finished image (A_0 .. A_L) leaves its tile buffer as ONE bulk copy issued by
+    // the elected thread after the step's barrier.  The elected thread waits for the reads of all
+    // earlier copies BEFORE that barrier, and the steps alternate X, Y, X, ... - so whenever a step
+    // starts writing a tile buffer, the copy issued from it two steps ago has been read out.
     const int e = warp - 2;
     const int h = e >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const bool elected = (e == 0) && lane == 0;
     const uint32_t xs = (uint32_t)(row & 7) << 4;
     constexpr int kCols = W / 2;                      // columns per thread
     const uint32_t acc_base = tmem + ((uint32_t)(q * 32) << 16) + h * kCols;
-    StashGate gate;
     uint32_t par_acc = 0;
     const bool pos_mode = a.pos != nullptr;
     const uint32_t a_rdy[2] = {kCtas == 2 ? mapa_u32(sm.a_ready(0), 0) : sm.a_ready(0),
@@ -590,18 +528,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
         const int64_t tile = 2 * pair + t;
         const bool active = tile < a.tiles;
         const uint32_t sA = sm.tileA(t);
-        if (kStash) gate.before_write(sm.buf_free(t), t);
         {
           float x[3];
           row_pos01(pos_mode, nxt[t], x);
           encode_row(sA, row, h, x, sm.enc_tab());
         }
         fence_async_smem();
+        if (kStash && elected) bulk_wait_read0();
         arrive_a<kCtas>(a_rdy[t], lane);
-        if (kStash) arrive_warp(sm.img_ready(t), lane);
         if (u + units.stride < units.count)
           nxt[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, row_index(units.pair(u + units.stride), t));
-        (void)active;
+        if (kStash) {
+          epi_bar();
+          if (elected && active) { bulk_s2g(a.acts + tile * act_tile_bytes(net), sA, (uint32_t)kBlk); bulk_commit(); }
+        }
       }
       for (int l = 0; l < net.L; ++l) {
         const bool last = (l == net.L - 1);
@@ -616,7 +556,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
           float* part = sm.part() + t * 128;
           mbar_wait(sm.acc_full(t), par_acc);
           tc_fence_after();
-          if (kStash) gate.before_write(sm.buf_free(t), t);
           float sig0 = 0.f, sig1 = 0.f;
           uint32_t mbits[kCols / 32];
           drain32<kCols>(acc_base + t * 256, [&](int i, uint32_t (&v)[32]) {
@@ -650,15 +589,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
             }
           }
           if (!last || kStash) fence_async_smem();     // the image becomes visible to the MMA / bulk-copy engines
+          if (kStash && elected) bulk_wait_read0();
           if (!last) arrive_a<kCtas>(a_rdy[t], lane);
           else if (h == 1) part[row] = sig;
-          if (kStash) arrive_warp(sm.img_ready(t), lane);
-          if (last) epi_bar();                         // the two column halves of a row exchange their partial sigma
+          if (kStash || last) epi_bar();
           if (last && h == 0 && in) a.sigma[gs] = sig + part[row];
+          if (kStash && elected && active) {
+            bulk_s2g(a.acts + tile * act_tile_bytes(net) + kBlk + (int64_t)l * kNb * kBlk, sA, (uint32_t)(kNb * kBlk));
+            bulk_commit();
+          }
         }
         par_acc ^= 1u;
       }
     }
+    if (kStash && elected) bulk_wait0();
   }
   pipe_teardown<kCtas>(tmem, warp);
 }
@@ -758,37 +702,17 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
         }
       }
     }
-  } else if (warp == 10) {
-    // ---------------- stash copier: dZ_L (unless wgrad rebuilds it) .. dZ_1 of every tile, in the epilogue's step order
-    if (lane == 0) {
-      StashCopier cp;
-      cp.img0 = sm.img_ready(0); cp.img1 = sm.img_ready(1); cp.fre0 = sm.buf_free(0); cp.fre1 = sm.buf_free(1);
-      for (int64_t u = units.first; u < units.count; u += units.stride) {
-        const int64_t tx = 2 * units.pair(u), ty = tx + 1;
-        uint8_t* gx = a.dz + tx * dz_tile_bytes(net);
-        uint8_t* gy = a.dz + ty * dz_tile_bytes(net);
-        const int64_t off_last = (int64_t)(net.L - 1) * kNb * kBlk;
-        cp.step<0>(a.stash_last && tx < a.tiles, gx + off_last, sm.tileA(0), (uint32_t)(kNb * kBlk));
-        cp.step<1>(a.stash_last && ty < a.tiles, gy + off_last, sm.tileA(1), (uint32_t)(kNb * kBlk));
-        for (int l = net.L - 1; l >= 1; --l) {
-          const int64_t off = (int64_t)(l - 1) * kNb * kBlk;
-          cp.step<0>(tx < a.tiles, gx + off, sm.tileA(0), (uint32_t)(kNb * kBlk));
-          cp.step<1>(ty < a.tiles, gy + off, sm.tileA(1), (uint32_t)(kNb * kBlk));
-        }
-      }
-      cp.finish();
-    }
   } else {
     // ---------------- epilogue warps: thread = (sample row, column half); tile X, then tile Y
-    // (same step / hand-off protocol as the forward kernel: img_ready -> copier warp -> buf_free).
+    // (same step / barrier / bulk-copy protocol as the forward kernel).
     const int e = warp - 2;
     const int h = e >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const bool elected = (e == 0) && lane == 0;
     const uint32_t xs = (uint32_t)(row & 7) << 4;
     constexpr int kCols = W / 2;
     constexpr int kWords = W / 32;
-    StashGate gate;
     constexpr int kMw = kCols / 32;
     const uint32_t acc_row = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t par_acc = 0;
@@ -826,7 +750,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
         const uint32_t stile = sm.tileA(t);
         const uint32_t srow = stile + row * 128;
         if (want_dx && h == 0) rin[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, in ? gs : a.P - 1);
-        gate.before_write(sm.buf_free(t), t);
         // dZ_L = d_sigma * w_out * relu'(Z_L)
 #pragma unroll
         for (int it = 0; it < kMw; ++it) {
@@ -850,9 +773,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
           ds[t] = load_ds(tile + next_tile);
         }
         fence_async_smem();
+        if (elected) bulk_wait_read0();
         arrive_a<kCtas>(a_rdy[t], lane);
-        arrive_warp(sm.img_ready(t), lane);
-        (void)active;
+        epi_bar();
+        if (a.stash_last && elected && active) {
+          bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(net.L - 1) * kNb * kBlk, stile, (uint32_t)(kNb * kBlk));
+          bulk_commit();
+        }
       }
       for (int l = net.L - 1; l >= l_lo; --l) {
 #pragma unroll
@@ -868,7 +795,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
           if (l >= 1) {
             // dZ_l = dA_l * relu'(Z_l)  -> fp16 image (next GEMM's A operand in smem, wgrad's B operand in HBM)
             const bool feeds_gemm = (l - 1 >= l_lo);
-            gate.before_write(sm.buf_free(t), t);
             drain32<kCols>(acc_row + t * 256 + h * kCols, [&](int i, uint32_t (&v)[32]) {
               const uint32_t bits = mw[t][i];
 #define LONER_DZ(P) v[P] = cvt_sat_h2(__uint_as_float(v[2 * P]), __uint_as_float(v[2 * P + 1])) & half2_mask<P>(bits);
@@ -886,8 +812,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
               ds[t] = load_ds(tile + next_tile);
             }
             fence_async_smem();
+            if (elected) bulk_wait_read0();
             if (feeds_gemm) arrive_a<kCtas>(a_rdy[t], lane);
-            arrive_warp(sm.img_ready(t), lane);
+            epi_bar();
+            if (elected && active) {
+              bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(l - 1) * kNb * kBlk, stile, (uint32_t)(kNb * kBlk));
+              bulk_commit();
+            }
           } else {
             // l == 0: dEnc [128 x Epad] -> d_pos through the sin/cos encoding (lower-half warps only)
             if (h == 0) {
@@ -929,6 +860,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
         par_acc ^= 1u;
       }
     }
+    if (elected) bulk_wait0();
   }
   pipe_teardown<kCtas>(tmem, warp);
 }
