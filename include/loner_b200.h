@@ -137,8 +137,10 @@ typedef struct {
   float per_level_scale;         /* <= 0: tcnn's default 2.0 */
   int32_t n_neurons;             /* 64 */
   int32_t n_hidden_layers;       /* 1 */
-  int32_t reserved;
+  int32_t flags;                 /* 0 = production kernels (warp-level tensor-core head); LONER_HASH_* A/B variants */
 } loner_hashnet_t;
+/* the head (32 -> 64 -> 1) on scalar CUDA-core code instead of mma.sync tiles (round 1's kernels) */
+#define LONER_HASH_SCALAR 1
 
 int64_t loner_hash_param_count(const loner_hashnet_t* net);
 int64_t loner_hash_table_entries(const loner_hashnet_t* net);

@@ -53,10 +53,11 @@ def build(force=False, verbose=False):
 
 def build_probe():
     """Hardware probes used while sizing the kernels (tests/gpu_probe.py); NOT part of the product library."""
-    src = os.path.join(HERE, "..", "tests", "probes", "probe_tmem.cu")
-    out = os.path.join(HERE, "..", "tests", "probes", "libloner_probe.so")
-    if not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out):
-        subprocess.check_call([NVCC] + FLAGS + ["-I", CSRC, "-shared", src, "-o", out, "-lcudart"])
+    d = os.path.join(HERE, "..", "tests", "probes")
+    srcs = [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(".cu")]
+    out = os.path.join(d, "libloner_probe.so")
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        subprocess.check_call([NVCC] + FLAGS + ["-I", CSRC, "-shared"] + srcs + ["-o", out, "-lcudart"])
     return out
 
 

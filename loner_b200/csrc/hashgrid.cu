@@ -25,6 +25,7 @@ constexpr int kW = 64;             // hidden width
 constexpr int kThreads = 256;
 
 struct HashNet {
+  int flags;                       // LONER_HASH_* (kernel variants)
   int n_levels, E, Epad;           // E = 2 * n_levels encoded features, padded to 16 with 1.0
   float scale[kMaxLevels];
   uint32_t res[kMaxLevels];
@@ -40,6 +41,7 @@ __host__ inline bool net_from(const loner_hashnet_t* n, HashNet& o) {
   if (n->n_neurons != kW || n->n_hidden_layers != 1) return false;
   const float pls = n->per_level_scale > 0.f ? n->per_level_scale : 2.0f;
   o.n_levels = n->n_levels;
+  o.flags = n->flags;
   o.E = 2 * n->n_levels;
   o.Epad = (o.E + 15) / 16 * 16;
   uint32_t off = 0;
@@ -366,6 +368,292 @@ __global__ void __launch_bounds__(kThreads) hash_bwd_kernel(const Args a) {
   if (tid < kW) part[w1_floats(net) + tid] = accWout;
 }
 
+// ------------------------------------------------------------------------------------------
+// Warp-level tensor-core variant (round 2).  ncu of the scalar kernels above: hash_bwd executed 26.7 K
+// instructions per sample - 3.5 G warp instructions per C2 step, 46 % issue-slot utilisation, 31 % of the
+// stall samples "no instruction" (instruction-cache misses of the fully unrolled body) - i.e. the kernel was
+// bound by the SCALAR code of the 32 -> 64 -> 1 head (an LDS + two converts per two FMAs), not by the
+// gathers / atomics it exists for.  Here the three small GEMMs of a 32-sample warp tile
+//     H [32 x 64]  = Enc [32 x 32] W1^T          (forward, recomputed in the backward)
+//     dEnc [32 x 32] = dH [32 x 64] W1           (input gradient of the head)
+//     dW1 [64 x 32] += dH^T [64 x 256] Enc [256 x 32]   (per CTA tile of 256 samples, M x N split over the warps)
+// run on mma.sync.m16n8k16 (fp16 operands, fp32 accumulation), fed by ldmatrix from small per-warp tiles in
+// shared memory.  tcgen05 is the wrong tool for a 12 KFLOP-per-sample contraction inside a gather kernel:
+// it would need the operands staged as 128-row tiles and TMEM round trips for 64 columns of output.
+constexpr int kEncLd = 40;          // halves per row of the per-warp encoding tile (32 + 8: conflict-free ldmatrix)
+constexpr int kDhLd = 72;           // halves per row of the per-warp dH tile (64 + 8)
+constexpr int kDencLd = 33;         // floats per row of the per-warp dEnc tile
+constexpr int kW1Ld = 40;           // halves per row of W1 [64][32 + 8]
+struct WarpTiles {
+  __align__(16) __half enc[32][kEncLd];      // 2560 B
+  __align__(16) __half dh[32][kDhLd];        // 4608 B
+  float denc[32][kDencLd];                   // 4224 B
+};
+struct MmaSmem {
+  __align__(16) __half w1[kW][kW1Ld];        // 5120 B, zero beyond Epad
+  float wout[kW];
+  float red[8][kW];                          // dW_out partials of the warps
+  WarpTiles wt[8];
+};
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
+__device__ __forceinline__ void load_weights_mma(const Args& a, MmaSmem& sm, int tid) {
+  const __half* w1 = reinterpret_cast<const __half*>(a.packed);
+  const int E = a.net.Epad;
+  for (int i = tid; i < kW * kW1Ld; i += kThreads) {
+    const int j = i / kW1Ld, k = i % kW1Ld;
+    sm.w1[j][k] = k < E ? w1[j * E + k] : __float2half_rn(0.f);
+  }
+  const float* wo = reinterpret_cast<const float*>(a.packed + packed_wout_off(a.net));
+  for (int j = tid; j < kW; j += kThreads) sm.wout[j] = wo[j];
+}
+
+// this thread's encoded sample -> row `lane` of the warp's fp16 tile (features >= Epad are zero)
+__device__ __forceinline__ void stash_enc(WarpTiles& wt, int lane, const float (&enc)[2 * kMaxLevels]) {
+#pragma unroll
+  for (int i = 0; i < 2 * kMaxLevels; i += 8)
+    *reinterpret_cast<uint4*>(&wt.enc[lane][i]) = make_uint4(pack_h2(enc[i], enc[i + 1]), pack_h2(enc[i + 2], enc[i + 3]),
+                                                             pack_h2(enc[i + 4], enc[i + 5]), pack_h2(enc[i + 6], enc[i + 7]));
+}
+
+// hidden pre-activations of 16 samples (m-tile mt of the warp tile): c[nt][.] = C fragment of hidden columns 8 nt .. 8 nt + 7
+__device__ __forceinline__ void hidden_gemm(const MmaSmem& sm, const WarpTiles& wt, int mt, int lane, float (&c)[8][4]) {
+  uint32_t a0[4], a1[4];
+  ldsm4(a0, &wt.enc[mt * 16 + (lane & 15)][(lane >> 4) * 8]);
+  ldsm4(a1, &wt.enc[mt * 16 + (lane & 15)][16 + (lane >> 4) * 8]);
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    uint32_t b[4];                   // W1[n][k], k contiguous = the "col" operand as stored: k 0-7 | 8-15 | 16-23 | 24-31
+    ldsm4(b, &sm.w1[nt * 8 + (lane & 7)][(lane >> 3) * 8]);
+    c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+    mma16816(c[nt], a0, b[0], b[1]);
+    mma16816(c[nt], a1, b[2], b[3]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) hash_fwd_mma_kernel(const Args a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  MmaSmem& sm = *reinterpret_cast<MmaSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  load_weights_mma(a, sm, tid);
+  __syncthreads();
+  WarpTiles& wt = sm.wt[warp];
+  const __half2* table = reinterpret_cast<const __half2*>(a.packed + packed_table_off(a.net));
+  const int64_t n_tiles = (a.P + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t s = tile * kThreads + tid;
+    float x[3] = {0.f, 0.f, 0.f}, enc[2 * kMaxLevels];
+    if (s < a.P) position01(a, s, x);
+    encode(a.net, table, x, enc);
+    __syncwarp();
+    stash_enc(wt, lane, enc);
+    __syncwarp();
+    const int64_t row0 = tile * kThreads + warp * 32;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float c[8][4];
+      hidden_gemm(sm, wt, mt, lane, c);
+      float s_lo = 0.f, s_hi = 0.f;          // rows 16 mt + g and 16 mt + g + 8
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float w0 = sm.wout[nt * 8 + 2 * t], w1 = sm.wout[nt * 8 + 2 * t + 1];
+        s_lo = fmaf(round_h(fmaxf(c[nt][0], 0.f)), w0, s_lo);
+        s_lo = fmaf(round_h(fmaxf(c[nt][1], 0.f)), w1, s_lo);
+        s_hi = fmaf(round_h(fmaxf(c[nt][2], 0.f)), w0, s_hi);
+        s_hi = fmaf(round_h(fmaxf(c[nt][3], 0.f)), w1, s_hi);
+      }
+      s_lo += __shfl_xor_sync(kFull, s_lo, 1); s_lo += __shfl_xor_sync(kFull, s_lo, 2);
+      s_hi += __shfl_xor_sync(kFull, s_hi, 1); s_hi += __shfl_xor_sync(kFull, s_hi, 2);
+      if (t == 0) {
+        const int64_t r_lo = row0 + mt * 16 + g, r_hi = r_lo + 8;
+        if (r_lo < a.P) a.sigma[r_lo] = s_lo;
+        if (r_hi < a.P) a.sigma[r_hi] = s_hi;
+      }
+    }
+  }
+}
+
+template <bool kDx>
+__global__ void __launch_bounds__(kThreads, 2) hash_bwd_mma_kernel(const Args a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  MmaSmem& sm = *reinterpret_cast<MmaSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  load_weights_mma(a, sm, tid);
+  __syncthreads();
+  WarpTiles& wt = sm.wt[warp];
+  const HashNet& net = a.net;
+  const __half2* table = reinterpret_cast<const __half2*>(a.packed + packed_table_off(net));
+  // dW1 [64 hidden x 32 features] = 4 x 4 C tiles of 16 x 8; warp w owns tiles (m = w >> 1, n = 2 (w & 1) + {0, 1})
+  float accW[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) accW[i][0] = accW[i][1] = accW[i][2] = accW[i][3] = 0.f;
+  float accOut[8][2];                      // dW_out partial: hidden columns 8 nt + 2 t + {0, 1}, summed over this thread's rows
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) accOut[nt][0] = accOut[nt][1] = 0.f;
+  const float inv_g = 1.0f / a.gscale;
+  const int64_t n_tiles = (a.P + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t s = tile * kThreads + tid;
+    const bool in = s < a.P;
+    float x[3] = {0.f, 0.f, 0.f};
+    {
+      float enc[2 * kMaxLevels];
+      if (in) position01(a, s, x);
+      encode(net, table, x, enc);
+      stash_enc(wt, lane, enc);
+    }
+    const float ds = in ? __ldg(a.d_sigma + s) : 0.f;
+    __syncwarp();
+    // ---- forward recompute + dH + dEnc, 16 samples at a time
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float c[8][4];
+      hidden_gemm(sm, wt, mt, lane, c);
+      const float ds_lo = __shfl_sync(kFull, ds, mt * 16 + g), ds_hi = __shfl_sync(kFull, ds, mt * 16 + g + 8);
+      uint32_t dhp[8][2];                  // dH as packed half2 in C layout = A fragments of the dEnc GEMM
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float w0 = sm.wout[nt * 8 + 2 * t], w1 = sm.wout[nt * 8 + 2 * t + 1];
+        const float h00 = round_h(fmaxf(c[nt][0], 0.f)), h01 = round_h(fmaxf(c[nt][1], 0.f));
+        const float h10 = round_h(fmaxf(c[nt][2], 0.f)), h11 = round_h(fmaxf(c[nt][3], 0.f));
+        accOut[nt][0] += ds_lo * h00 + ds_hi * h10;
+        accOut[nt][1] += ds_lo * h01 + ds_hi * h11;
+        const float k = a.gscale;
+        const float d00 = h00 > 0.f ? fminf(fmaxf(ds_lo * w0 * k, -65504.f), 65504.f) : 0.f;
+        const float d01 = h01 > 0.f ? fminf(fmaxf(ds_lo * w1 * k, -65504.f), 65504.f) : 0.f;
+        const float d10 = h10 > 0.f ? fminf(fmaxf(ds_hi * w0 * k, -65504.f), 65504.f) : 0.f;
+        const float d11 = h11 > 0.f ? fminf(fmaxf(ds_hi * w1 * k, -65504.f), 65504.f) : 0.f;
+        dhp[nt][0] = pack_h2(d00, d01);
+        dhp[nt][1] = pack_h2(d10, d11);
+        *reinterpret_cast<uint32_t*>(&wt.dh[mt * 16 + g][nt * 8 + 2 * t]) = dhp[nt][0];
+        *reinterpret_cast<uint32_t*>(&wt.dh[mt * 16 + g + 8][nt * 8 + 2 * t]) = dhp[nt][1];
+      }
+      // dEnc [16 x 32] = dH [16 x 64] W1 [64 x 32]: B from W1[k = hidden][n = feature] (n contiguous) through ldmatrix.trans
+      float d[4][4];
+#pragma unroll
+      for (int nf = 0; nf < 4; ++nf) d[nf][0] = d[nf][1] = d[nf][2] = d[nf][3] = 0.f;
+#pragma unroll
+      for (int kp = 0; kp < 2; ++kp) {     // pairs of 16-deep k tiles: hidden 32 kp .. 32 kp + 31
+        const uint32_t a0[4] = {dhp[4 * kp][0], dhp[4 * kp][1], dhp[4 * kp + 1][0], dhp[4 * kp + 1][1]};
+        const uint32_t a1[4] = {dhp[4 * kp + 2][0], dhp[4 * kp + 2][1], dhp[4 * kp + 3][0], dhp[4 * kp + 3][1]};
+#pragma unroll
+        for (int nf = 0; nf < 4; ++nf) {
+          uint32_t b[4];                   // rows k: 32 kp + {0-7, 8-15, 16-23, 24-31}, columns n = 8 nf ..
+          ldsm4t(b, &sm.w1[32 * kp + lane][nf * 8]);
+          mma16816(d[nf], a0, b[0], b[1]);
+          mma16816(d[nf], a1, b[2], b[3]);
+        }
+      }
+#pragma unroll
+      for (int nf = 0; nf < 4; ++nf) {
+        wt.denc[mt * 16 + g][nf * 8 + 2 * t] = d[nf][0] * inv_g;
+        wt.denc[mt * 16 + g][nf * 8 + 2 * t + 1] = d[nf][1] * inv_g;
+        wt.denc[mt * 16 + g + 8][nf * 8 + 2 * t] = d[nf][2] * inv_g;
+        wt.denc[mt * 16 + g + 8][nf * 8 + 2 * t + 1] = d[nf][3] * inv_g;
+      }
+    }
+    __syncwarp();
+    // ---- scatter into the gradient table, and d_pos through the interpolation weights (per sample, as before)
+    float dx[3] = {0.f, 0.f, 0.f};
+    if (in && ds != 0.f) {
+#pragma unroll
+      for (int l = 0; l < kMaxLevels; ++l) {
+        if (l < net.n_levels) {
+          const Cell q = locate(net.scale[l], x);
+          const uint32_t res = net.res[l], ent = net.entries[l];
+          const bool dense = net.dense[l] != 0u;
+          float2* gt = reinterpret_cast<float2*>(a.d_table) + net.offset[l];
+          const float gx = wt.denc[lane][2 * l], gy = wt.denc[lane][2 * l + 1];
+          float lx[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t idx = entry_index(q.c[0] + (c & 1), q.c[1] + ((c >> 1) & 1), q.c[2] + (c >> 2), res, ent, dense);
+            const float w = corner_weight(q, c);
+            atomicAdd(gt + idx, make_float2(w * gx, w * gy));
+            if (kDx) {
+              const float2 v = __half22float2(__ldg(table + net.offset[l] + idx));
+              const float dot = v.x * gx + v.y * gy;
+              const float w0 = (c & 1) ? q.f[0] : 1.0f - q.f[0], w1 = (c & 2) ? q.f[1] : 1.0f - q.f[1],
+                          w2 = (c & 4) ? q.f[2] : 1.0f - q.f[2];
+              lx[0] += ((c & 1) ? 1.0f : -1.0f) * w1 * w2 * dot;
+              lx[1] += ((c & 2) ? 1.0f : -1.0f) * w0 * w2 * dot;
+              lx[2] += ((c & 4) ? 1.0f : -1.0f) * w0 * w1 * dot;
+            }
+          }
+          if (kDx) {
+#pragma unroll
+            for (int dd = 0; dd < 3; ++dd) dx[dd] = fmaf(net.scale[l], lx[dd], dx[dd]);
+          }
+        }
+      }
+    }
+    if (kDx && in) {
+#pragma unroll
+      for (int dd = 0; dd < 3; ++dd) a.d_pos[s * 3 + dd] = 0.5f * dx[dd];     // x = (pos + 1) / 2
+    }
+    __syncthreads();
+    // ---- dW1 [64 x 32] += dH^T [64 x 256] Enc [256 x 32] over the CTA tile: warp w owns C tiles (m = w >> 1, n = 2 (w & 1) + {0, 1})
+    {
+      const int mtile = warp >> 1, npair = warp & 1;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) {           // the 32-sample tiles of the eight warps
+        const WarpTiles& o = sm.wt[w8];
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+          uint32_t af[4], bf[4];
+          // A = dH^T: stored [k = sample][m = hidden] -> transposed load; tiles (m lo, k lo) (m hi, k lo) (m lo, k hi) (m hi, k hi)
+          ldsm4t(af, &o.dh[kt * 16 + (lane & 7) + ((lane >> 4) & 1) * 8][mtile * 16 + ((lane >> 3) & 1) * 8]);
+          // B = Enc: stored [k = sample][n = feature] -> transposed load; (k lo, n0) (k hi, n0) (k lo, n1) (k hi, n1)
+          ldsm4t(bf, &o.enc[kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][npair * 16 + ((lane >> 4) & 1) * 8]);
+          mma16816(accW[0], af, bf[0], bf[1]);
+          mma16816(accW[1], af, bf[2], bf[3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- per-CTA partials: dW1 (loss-scaled) in [hidden j][feature i] order with row stride Epad, then dW_out
+  float* part = a.partials + (int64_t)blockIdx.x * (w1_floats(net) + kW);
+  {
+    const int mtile = warp >> 1, npair = warp & 1;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int col = npair * 16 + i * 8 + 2 * t;
+      const int r0 = mtile * 16 + g;
+      if (col < net.Epad) { part[r0 * net.Epad + col] = accW[i][0]; part[(r0 + 8) * net.Epad + col] = accW[i][2]; }
+      if (col + 1 < net.Epad) { part[r0 * net.Epad + col + 1] = accW[i][1]; part[(r0 + 8) * net.Epad + col + 1] = accW[i][3]; }
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float v = accOut[nt][j];
+      v += __shfl_xor_sync(kFull, v, 4); v += __shfl_xor_sync(kFull, v, 8); v += __shfl_xor_sync(kFull, v, 16);
+      if (g == 0) sm.red[warp][nt * 8 + 2 * t + j] = v;
+    }
+  __syncthreads();
+  if (tid < kW) {
+    float v = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) v += sm.red[w8][tid];
+    part[w1_floats(net) + tid] = v;
+  }
+}
+
 // d_params[W1] += sum_b partials[b][W1] / gscale;  d_params[W_out row 0] += sum_b partials[b][W_out]
 __global__ void __launch_bounds__(256) hash_reduce_kernel(HashNet net, const float* __restrict__ partials, int n_blocks,
                                                          float inv_gscale, float* __restrict__ d_params) {
@@ -442,8 +730,15 @@ extern "C" int loner_hash_fwd(const loner_hashnet_t* n, const void* packed, cons
   if (!sigma) return LONER_E_BAD_ARG;
   a.sigma = sigma;
   const int64_t want = (P + kThreads - 1) / kThreads;
-  const int64_t cap = (int64_t)sm_count() * 8;
-  hash_fwd_kernel<<<(unsigned)(want < cap ? want : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+  if (a.net.flags & LONER_HASH_SCALAR) {
+    const int64_t cap = (int64_t)sm_count() * 8;
+    hash_fwd_kernel<<<(unsigned)(want < cap ? want : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
+  } else {
+    const int64_t cap = (int64_t)sm_count() * 2;
+    const int smem = (int)sizeof(MmaSmem);
+    cudaFuncSetAttribute(hash_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    hash_fwd_mma_kernel<<<(unsigned)(want < cap ? want : cap), kThreads, smem, (cudaStream_t)stream>>>(a);
+  }
   LONER_CHECK_LAUNCH();
   return LONER_OK;
 }
@@ -461,14 +756,16 @@ extern "C" int loner_hash_bwd(const loner_hashnet_t* n, const void* packed, cons
   const int64_t tiles = (P + kThreads - 1) / kThreads;
   const int blocks = (int)(tiles < bwd_blocks() ? tiles : bwd_blocks());
   cudaStream_t st = (cudaStream_t)stream;
-  const int smem = (int)sizeof(BwdSmem);
-  if (d_pos) {
-    cudaFuncSetAttribute(hash_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    hash_bwd_kernel<true><<<blocks, kThreads, smem, st>>>(a);
-  } else {
-    cudaFuncSetAttribute(hash_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    hash_bwd_kernel<false><<<blocks, kThreads, smem, st>>>(a);
-  }
+  const bool scalar = (a.net.flags & LONER_HASH_SCALAR) != 0;
+  const int smem = scalar ? (int)sizeof(BwdSmem) : (int)sizeof(MmaSmem);
+#define LONER_HASH_BWD(K)                                                                        \
+  do {                                                                                           \
+    cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                  \
+    K<<<blocks, kThreads, smem, st>>>(a);                                                        \
+  } while (0)
+  if (scalar) { if (d_pos) LONER_HASH_BWD(hash_bwd_kernel<true>); else LONER_HASH_BWD(hash_bwd_kernel<false>); }
+  else        { if (d_pos) LONER_HASH_BWD(hash_bwd_mma_kernel<true>); else LONER_HASH_BWD(hash_bwd_mma_kernel<false>); }
+#undef LONER_HASH_BWD
   LONER_CHECK_LAUNCH();
   hash_reduce_kernel<<<16, 256, 0, st>>>(a.net, a.partials, blocks, 1.0f / grad_scale, d_params);
   LONER_CHECK_LAUNCH();

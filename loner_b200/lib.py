@@ -25,7 +25,7 @@ class PickSegT(_c.Structure):
 class HashNetT(_c.Structure):
     _fields_ = [("n_levels", _i32), ("n_features_per_level", _i32), ("log2_hashmap_size", _i32),
                 ("base_resolution", _i32), ("per_level_scale", _f32), ("n_neurons", _i32),
-                ("n_hidden_layers", _i32), ("reserved", _i32)]
+                ("n_hidden_layers", _i32), ("flags", _i32)]
 
 
 _SIGS = {

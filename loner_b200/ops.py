@@ -17,6 +17,7 @@ def _f32(t):
 
 
 NET_SINGLE_CTA, NET_STASH_DZL = 1, 2      # LONER_NET_* (include/loner_b200.h)
+HASH_SCALAR = 1                            # LONER_HASH_*
 DEFAULT_NET_FLAGS = 0                       # production: CTA pairs, dZ_L rebuilt inside wgrad
 
 
@@ -59,9 +60,11 @@ class HashNet:
     Flat fp32 params in tcnn's order: W1 [64, e_pad] | W_out [16, 64] | table [entries, 2]."""
 
     def __init__(self, n_levels=16, n_features_per_level=2, log2_hashmap_size=18, base_resolution=16,
-                 per_level_scale=2.0, n_neurons=64, n_hidden_layers=1):
+                 per_level_scale=2.0, n_neurons=64, n_hidden_layers=1, flags=0):
+        """flags: LONER_HASH_* bits (HASH_SCALAR = round 1's CUDA-core head, kept for A/B)."""
+        self.flags = int(flags)
         self.c = L.HashNetT(int(n_levels), int(n_features_per_level), int(log2_hashmap_size), int(base_resolution),
-                            float(per_level_scale), int(n_neurons), int(n_hidden_layers), 0)
+                            float(per_level_scale), int(n_neurons), int(n_hidden_layers), self.flags)
         lib = L.load()
         self.param_count = lib.loner_hash_param_count(ctypes.byref(self.c))
         if self.param_count < 0:

@@ -6,7 +6,7 @@ from loner_b200 import ops, synth
 
 N, S = int(os.environ.get("MB_N", 8192)), 512
 dev = "cuda"
-net = ops.HashNet()
+net = ops.HashNet(flags=int(os.environ.get("MB_HASH_FLAGS", 0)))
 g = torch.Generator().manual_seed(0)
 params = torch.cat([(torch.rand(net.n_network_params, generator=g) - 0.5) * 0.4, (torch.rand(2 * net.table_entries, generator=g) - 0.5)]).to(dev)
 packed = ops.hash_pack(net, params)

@@ -21,11 +21,14 @@ CONFIGS = {
 }
 
 
-def _setup(cfg, P, seed=0):
+FLAGS = [0, ops.HASH_SCALAR]        # production (warp-level tensor-core head) and round 1's scalar kernels
+
+
+def _setup(cfg, P, seed=0, flags=0):
     hs = H.HashGridSpec(**cfg)
     spec = orc.NetSpec(n_neurons=64, n_hidden_layers=1, precision="fp16", hash=hs)
     net = ops.HashNet(n_levels=hs.n_levels, log2_hashmap_size=hs.log2_hashmap_size, base_resolution=hs.base_resolution,
-                      per_level_scale=hs.per_level_scale)
+                      per_level_scale=hs.per_level_scale, flags=flags)
     g = torch.Generator().manual_seed(seed)
     w = tcnn_standin.xavier_uniform_flat(spec.shapes, 1337)
     table = (torch.rand(hs.n_params, generator=g) - 0.5)          # O(1) features so that sigma is not noise
@@ -34,9 +37,10 @@ def _setup(cfg, P, seed=0):
     return hs, spec, net, params, pos
 
 
+@pytest.mark.parametrize("flags", FLAGS)
 @pytest.mark.parametrize("name", sorted(CONFIGS))
-def test_hash_forward_matches_oracle(name):
-    hs, spec, net, params, pos = _setup(CONFIGS[name], 3001)
+def test_hash_forward_matches_oracle(name, flags):
+    hs, spec, net, params, pos = _setup(CONFIGS[name], 3001, flags=flags)
     ref = orc.sigma_net(pos, params, spec)
     packed = ops.hash_pack(net, params.to(DEV))
     sigma = ops.hash_fwd(net, packed, pos.shape[0], pos=pos.to(DEV).contiguous())
@@ -63,9 +67,10 @@ def test_hash_forward_from_rays_equals_from_positions():
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("flags", FLAGS)
 @pytest.mark.parametrize("name", sorted(CONFIGS))
-def test_hash_backward_matches_autograd(name):
-    hs, spec, net, params, pos = _setup(CONFIGS[name], 2000, seed=5)
+def test_hash_backward_matches_autograd(name, flags):
+    hs, spec, net, params, pos = _setup(CONFIGS[name], 2000, seed=5, flags=flags)
     g = torch.Generator().manual_seed(9)
     d_sigma = torch.randn(pos.shape[0], generator=g) * 1e-3
     p_ref = params.clone().requires_grad_(True)
@@ -80,7 +85,7 @@ def test_hash_backward_matches_autograd(name):
     parts = {"dW1": (0, nw1), "dW_out": (nw1, nw1 + 64), "d_table": (net.n_network_params, net.param_count)}
     for k, (a, b) in parts.items():
         e = norm_relerr(d_params[a:b], p_ref.grad[a:b])
-        print(f"[hash bwd {name}] {k} norm-rel err {e:.2e} (|ref| {float(p_ref.grad[a:b].norm()):.3e})")
+        print(f"[hash bwd {name} flags={flags}] {k} norm-rel err {e:.2e} (|ref| {float(p_ref.grad[a:b].norm()):.3e})")
         assert e < 3e-3                      # measured (B200): dW1 2-5e-4, dW_out 2e-5, d_table 1e-7
     assert float(d_params[nw1 + 64:net.n_network_params].abs().max()) == 0.0      # rows 1..15 of the padded output matrix
     e = norm_relerr(d_pos, pos_ref.grad)
