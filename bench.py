@@ -179,6 +179,14 @@ def ncu_traffic_bytes(kernel_substr, stash=True):
     return None, None
 
 
+def l2_probe_peaks():
+    p = os.path.join(REPO, "profiles", "r2_probe_l2.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
 def build_engine(wl, device, seed, world=1):
     from loner_b200 import engine as eng
     from loner_b200 import synth
@@ -504,8 +512,22 @@ def main():
         hs = {}
         for name in ("c2hash", "refdefault"):
             r = run_workload(WORKLOADS[name], tm, rank, max(5, min(args.steps, 10)), 3, sections=True)
+            Ph = min(r["N"], 16384) * WORKLOADS[name]["S"]
+            sec = {k: v[0] for k, v in r["sections"].items()}
+            l2 = l2_probe_peaks()
             hs[name] = {"rays_per_s": r["value"], "ms_per_step": r["ms_per_step"], "config": describe(WORKLOADS[name], world),
-                        "sections_ms": {k: round(v[0], 4) for k, v in r["sections"].items()}}
+                        "sections_ms": {k: round(v, 4) for k, v in sec.items()},
+                        # algorithmic L2 operations: 128 four-byte gathers per sample (forward; the backward re-gathers them)
+                        # and 128 eight-byte vector reductions per sample (backward), against the rates measured for
+                        # uniformly random addresses into tables of the same size (tests/gpu_probe_l2.py)
+                        "roofline": {"bound": "l2 request rate",
+                                     "fwd_gathers_G_per_s": round(128 * Ph / (sec["mlp_fwd"] * 1e-3) / 1e9, 1),
+                                     "bwd_gathers_plus_reductions_G_per_s": round(256 * Ph / (sec["mlp_dgrad"] * 1e-3) / 1e9, 1),
+                                     "peak_random_gathers_G_per_s": l2.get("random_4B_gathers_G_per_s"),
+                                     "peak_random_reductions_G_per_s": l2.get("random_v2f32_reductions_G_per_s"),
+                                     "peak_source": "profiles/r2_probe_l2.json (tests/gpu_probe_l2.py on a B200 of this pool)",
+                                     "note": "ray-ordered samples share cells: gathers hit L1 and the coarse-level reductions are "
+                                             "aggregated per warp run, so the achieved algorithmic rates may exceed the random-address peaks"}}
             r["engine"] = None
             torch.cuda.empty_cache()
         extras["hash"] = hs

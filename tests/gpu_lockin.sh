@@ -8,12 +8,19 @@ mkdir -p gpurun_out
 tail -3 gpurun_out/${tag}_pytest.log
 (timeout 900 python bench.py --steps 40 --warmup 5 > gpurun_out/${tag}_bench_c2.json 2> gpurun_out/${tag}_bench_c2.err)
 (timeout 300 python tests/gpu_ab.py > gpurun_out/${tag}_ab.jsonl 2>&1)
+(timeout 300 python bench.py --workload c5 --steps 8 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${tag}_bench_c5.json 2> gpurun_out/${tag}_bench_c5.err)
+(timeout 300 python bench.py --workload c3 --steps 10 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${tag}_bench_c3.json 2> gpurun_out/${tag}_bench_c3.err)
+(timeout 300 python bench.py --workload c1 --steps 20 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/${tag}_bench_c1.json 2> gpurun_out/${tag}_bench_c1.err)
+(timeout 200 python tests/gpu_probe_l2.py > gpurun_out/${tag}_probe_l2.json 2>&1; timeout 200 python tests/gpu_probe_store.py > gpurun_out/${tag}_probe_bulk_store.txt 2>&1; timeout 200 python tests/gpu_hash_hotspot.py > gpurun_out/${tag}_hash_hotspot.json 2>&1)
 # launch list of a short bench run (every launch with its device time; shares, not absolutes)
 (timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv --log-file gpurun_out/${tag}_launches_raw.csv \
    python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${tag}_launches_bench.log 2>&1)
-# full counters + source of every own kernel, one launch each, C2 size
-(MB_N=8192 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'^(adam|mlp_|ogm_|pack|ray_|render|sample_|wgrad_|hash_|points_)' -s 14 -c 13 \
+# full counters + source of every own kernel (one joint iteration, one map-only iteration, one render, one hash iteration), C2 size
+(MB_N=8192 timeout 1500 ncu --set full --clock-control none --profile-from-start off \
+   -k regex:'^(adam|sgd|mlp_|ogm_|pack|ray_|render|sample_|wgrad_|hash_|points_|loss_)' \
    -o gpurun_out/${tag}_prof python tests/gpu_profile_target.py > gpurun_out/${tag}_ncu.log 2>&1)
 ncu -i gpurun_out/${tag}_prof.ncu-rep --page raw --csv 2>/dev/null | python profiles/summarize_ncu.py > gpurun_out/${tag}_ncu_summary.csv
+# gpurun merges at most 64 MiB back: the compact summary is what gets committed, the raw report only if it is small
+[ $(stat -c %s gpurun_out/${tag}_prof.ncu-rep) -gt 40000000 ] && rm -f gpurun_out/${tag}_prof.ncu-rep
 cuobjdump -sass loner_b200/libloner_b200.so | grep -oE "UTCHMMA[.A-Z0-9]*|UTCBAR[.A-Z0-9]*|LDTM[.A-Z0-9x]*|UBLKCP[.A-Z0-9]*|UCGABAR[_A-Z]*|F2FP[.A-Z0-9_]*|HSET2[.A-Z0-9]*" | sort | uniq -c > gpurun_out/${tag}_sass_mnemonics.txt
 ls -la gpurun_out | tail -20

@@ -1,52 +1,45 @@
-"""ncu target (not a test): every kernel of the step once after one warm-up pass, at MB_N rays x 512 samples, 4x256.
-    ncu --set full --import-source on -k regex:mlp_ --launch-skip <n> -c <m> python tests/gpu_profile_target.py
-MB_FLAGS selects the kernel variants (loner_net_t.flags), MB_ONLY=wgrad runs only forward + backward."""
+"""ncu target (not a test): every kernel of the library once, at the C2 size (MB_N rays x 512 samples), after warm-up.
+One joint pose+map iteration of the Frequency 4x256 engine (occupancy update included), one test-mode render, and one
+iteration of the shipped HashGrid + 1x64 engine run between cudaProfilerStart/Stop:
+
+    ncu --set full --import-source on --profile-from-start off -k regex:'^(?!.*(at::|elementwise|vectorized|reduce_kernel<|cub::))' \
+        -o gpurun_out/prof python tests/gpu_profile_target.py
+MB_FLAGS selects the MLP kernel variants (loner_net_t.flags)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from loner_b200 import ops, synth, engine as eng
 
-N, S, W, L = int(os.environ.get("MB_N", 2048)), 512, 256, 4
-FLAGS = int(os.environ.get("MB_FLAGS", ops.DEFAULT_NET_FLAGS))
-dev = "cuda"
-net = ops.Net(10, W, L, flags=FLAGS)
-params = eng.xavier_uniform_flat(net.layer_shapes(), 1337).to(dev)
-packed = ops.mlp_pack(net, params)
+N, S = int(os.environ.get("MB_N", 8192)), 512
+flags = os.environ.get("MB_FLAGS")
 wc = synth.world_cube("canteen")
-scans, poses = synth.make_window("canteen", 1, seed=0)
-points = ops.pack_points(scans[0].ray_directions, scans[0].distances).to(dev)
-g = torch.Generator().manual_seed(0)
-ray_point = torch.randint(0, points.shape[0], (N,), generator=g).to(dev)
-ray_kf = torch.zeros(N, dtype=torch.int32, device=dev)
-P6 = synth.axis_angle_from_yaw_pose(poses[0])
-poses12 = eng.poses6_to_poses12(P6[None]).to(dev)
-grid = synth.trained_occupancy_grid("canteen")[0, 0].to(dev)
-P = N * S
-acts = torch.empty(net.act_bytes(P), device=dev, dtype=torch.uint8)
-sigma = torch.empty(P, device=dev)
-cfg7 = [wc.scale_factor, 0.5, 1.0, 10.0, 1.0, 1000.0, 0.005]
-scratch = torch.empty(net.bwd_scratch_bytes(P), device=dev, dtype=torch.uint8)
-gs = ops.default_grad_scale(N, S)
-dp = torch.zeros(net.param_count, device=dev)
-m, v = torch.zeros_like(dp), torch.zeros_like(dp)
-params2 = params.clone()
-only = os.environ.get("MB_ONLY", "")
-for rep in range(2):      # rep 0 = warm-up
-    counters = torch.zeros(2, dtype=torch.int32, device=dev)
-    rays, depths, flags = ops.ray_build(points, ray_kf, ray_point, poses12, wc.shift, wc.scale_factor, (1.0, 50.0), counters)
-    z = ops.sample_ogm(rays, grid, S, 1.0, None, None, seed=1)
-    if not only:
-        ops.mlp_fwd(net, packed, P, rays=rays, z=z, stash=False, sigma=sigma)
-    ops.mlp_fwd(net, packed, P, rays=rays, z=z, stash=True, sigma=sigma, acts=acts)
-    rl = ops.render_loss(sigma, z, rays, depths, flags, counters, cfg7, want_outputs=False)
-    if not only:
-        ops.mlp_dgrad(net, packed, P, rl["d_sigma"], acts, gs, scratch, rays=rays, z=z, want_dpos=True)
-    ops.mlp_dgrad(net, packed, P, rl["d_sigma"], acts, gs, scratch, rays=rays, z=z)
-    ops.mlp_wgrad(net, packed, P, rl["d_sigma"], acts, gs, dp, scratch)
-    if not only:
-        ops.adam_step(params2, dp, m, v, 1, 0.01)
-        ops.mlp_pack(net, params)
-        ops.ogm_grad(rays, z, depths, wc.scale_factor, 100, flags=flags)
-        ops.render_fwd(sigma.view(N, S), z, rays, raw_noise_std=1.0, seed=3)
-    torch.cuda.synchronize()
+scans, poses = synth.make_window("canteen", 2, seed=0)
+
+
+def engine(**kw):
+    cfg = eng.EngineConfig(scale=wc.scale_factor, shift=wc.shift, ray_range=(1.0, 50.0), n_samples=S,
+                           net_flags=None if flags is None else int(flags), **kw)
+    e = eng.MappingEngine(cfg)
+    for k in range(2):
+        e.add_keyframe(scans[k].ray_directions, scans[k].distances, synth.axis_angle_from_yaw_pose(poses[k]))
+    e.grid.copy_(synth.trained_occupancy_grid("canteen")[0, 0])
+    e.new_phase(optimize_poses=True)
+    return e
+
+
+ef = engine()
+eh = engine(encoding="HashGrid", n_neurons=64, n_hidden_layers=1)
+for e in (ef, eh):
+    for _ in range(10):                       # global_step 10 -> the profiled step runs the occupancy update too
+        e.step([0, 1], N // 2, optimize_poses=True)
+rays = ef.last["rays"]
+ef.render(rays, seed=1)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+ef.step([0, 1], N // 2, optimize_poses=True)
+ef.step([0, 1], N // 2, optimize_poses=False)      # the map-only dgrad variant (no d_pos)
+ef.render(rays, seed=2)
+eh.step([0, 1], N // 2, optimize_poses=True)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done")
