@@ -6,6 +6,7 @@ tag=${1:-r2}
 mkdir -p gpurun_out
 (timeout 1500 python -m pytest tests -m gpu -q -s > gpurun_out/${tag}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_pytest.log)
 tail -3 gpurun_out/${tag}_pytest.log
+(timeout 300 python __graft_entry__.py --smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_smoke.log); tail -2 gpurun_out/${tag}_smoke.log
 (timeout 900 python bench.py --steps 40 --warmup 5 > gpurun_out/${tag}_bench_c2.json 2> gpurun_out/${tag}_bench_c2.err)
 (timeout 300 python tests/gpu_ab.py > gpurun_out/${tag}_ab.jsonl 2>&1)
 (timeout 300 python bench.py --workload c5 --steps 8 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${tag}_bench_c5.json 2> gpurun_out/${tag}_bench_c5.err)
