@@ -110,7 +110,7 @@ int loner_mlp_fwd(const loner_net_t* net, const void* packed, const float* pos, 
                   const float* z_vals, int32_t S, int64_t P, float* sigma, void* acts, void* stream);
 
 /* backward.  d_sigma [P] (16-byte aligned) -> d_params [param_count] (+=, caller zeroes) and, if d_pos != NULL,
- * d_pos [P,3] (gradient w.r.t. the [-1,1] positions; +=, caller zeroes).  grad_scale: power-of-two loss scale
+ * d_pos [P,3] (gradient w.r.t. the [-1,1] positions).  grad_scale: power-of-two loss scale
  * applied to the fp16 intermediate gradients (undone before d_params / d_pos are written). */
 int loner_mlp_bwd(const loner_net_t* net, const void* packed, const float* pos, const float* rays,
                   const float* z_vals, int32_t S, int64_t P, const float* d_sigma, const void* acts,

@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
         const bool in = active && gs < a.P;
         const uint32_t stile = sm.tileA(t);
         const uint32_t srow = stile + row * 128;
-        if (want_dx) rin[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, in ? gs : a.P - 1);
+        if (want_dx && h == 0) rin[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, in ? gs : a.P - 1);
         // dZ_L = d_sigma * w_out * relu'(Z_L)
 #pragma unroll
         for (int it = 0; it < kMw; ++it) {
@@ -820,15 +820,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
               bulk_commit();
             }
           } else {
-            // l == 0: dEnc [128 x Epad] -> d_pos through the sin/cos encoding.  The two warps of a lane quarter split the
-            // encoded columns (32 each) and BOTH add their part to d_pos (caller-zeroed): with only the lower-half warps
-            // working, one warp per scheduler ran this SFU-heavy chain alone (+0.5 ms per C2-sized launch).
-            {
+            // l == 0: dEnc [128 x Epad] -> d_pos through the sin/cos encoding (lower-half warps only)
+            if (h == 0) {
               float x[3];
               row_pos01(pos_mode, rin[t], x);
               float dx[3] = {0.f, 0.f, 0.f};
               const uint2* tab = sm.enc_tab();
-              for (int it = h; it * 32 < net.Epad; it += 2) {
+              for (int it = 0; it * 32 < net.Epad; ++it) {
                 uint32_t v[32];
                 tmem_ld32(acc_row + t * 256 + it * 32, v);
                 tmem_ld_wait();
@@ -847,11 +845,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
                   }
                 }
               }
-              if (in && h * 32 < net.Epad) {
+              if (in) {
                 const float inv = 0.5f / a.gscale;      // x = (pos + 1) / 2
-                atomicAdd(a.d_pos + gs * 3 + 0, dx[0] * inv);
-                atomicAdd(a.d_pos + gs * 3 + 1, dx[1] * inv);
-                atomicAdd(a.d_pos + gs * 3 + 2, dx[2] * inv);
+                a.d_pos[gs * 3 + 0] = dx[0] * inv;
+                a.d_pos[gs * 3 + 1] = dx[1] * inv;
+                a.d_pos[gs * 3 + 2] = dx[2] * inv;
               }
             }
             tc_fence_before();

@@ -211,7 +211,7 @@ def mlp_bwd(net: Net, packed, P, d_sigma, acts, grad_scale, d_params, pos=None, 
     dev = packed.device
     if scratch is None:
         scratch = torch.empty(net.bwd_scratch_bytes(P), device=dev, dtype=torch.uint8)
-    d_pos = torch.zeros(P, 3, device=dev, dtype=torch.float32) if want_dpos else None      # the kernel accumulates
+    d_pos = torch.empty(P, 3, device=dev, dtype=torch.float32) if want_dpos else None
     S = z.shape[1] if z is not None else 1
     L.check(L.load().loner_mlp_bwd(net.ref(), L.ptr(packed), L.ptr(pos), L.ptr(rays), L.ptr(z), S, P,
                                    L.ptr(_f32(d_sigma)), L.ptr(acts), float(grad_scale), L.ptr(d_params),
@@ -220,7 +220,7 @@ def mlp_bwd(net: Net, packed, P, d_sigma, acts, grad_scale, d_params, pos=None, 
 
 
 def mlp_dgrad(net: Net, packed, P, d_sigma, acts, grad_scale, scratch, pos=None, rays=None, z=None, want_dpos=False):
-    d_pos = torch.zeros(P, 3, device=packed.device, dtype=torch.float32) if want_dpos else None   # the kernel accumulates
+    d_pos = torch.empty(P, 3, device=packed.device, dtype=torch.float32) if want_dpos else None
     S = z.shape[1] if z is not None else 1
     L.check(L.load().loner_mlp_dgrad(net.ref(), L.ptr(packed), L.ptr(pos), L.ptr(rays), L.ptr(z), S, P,
                                      L.ptr(_f32(d_sigma)), L.ptr(acts), float(grad_scale), L.ptr(d_pos),
