@@ -195,6 +195,18 @@ int loner_loss_finalize(const float* loss_acc, const int32_t* counts, float dept
 int loner_points_bwd(const float* d_pos, const float* z_vals, int64_t n, int32_t S, float* d_rays,
                      void* stream);
 
+/* ---- a5  pose 6-vectors [t | axis-angle] -> [K,12] = R row-major | t (common/pose_utils.py:288-302
+ * tensor_to_transform, i.e. pytorch3d.transforms.axis_angle_to_matrix through the unit quaternion).
+ * poses6: the keyframe pose store [n_keyframes,6]; rows [K]: store rows of the window's keyframes. */
+int loner_pose_matrices(const float* poses6, const int32_t* rows, int32_t K, float* poses12, void* stream);
+
+/* chain rule of the above + the pose half of the optimiser (mapping/optimizer.py:249-267,:376): d_poses12 [K,12] ->
+ * grad6 [n_keyframes,6] (rows of the window; zero for rows with free_rows[row] == 0), and, if apply != 0, one
+ * torch.optim.Adam step on the free rows (per-row step counts in steps [n_keyframes], moments [n_keyframes,6]). */
+int loner_pose_step(float* poses6, const int32_t* rows, const uint8_t* free_rows, int32_t K, const float* d_poses12,
+                    float* grad6, float* exp_avg, float* exp_avg_sq, int32_t* steps, float lr, float beta1,
+                    float beta2, float eps, int32_t apply, void* stream);
+
 /* ---- a18  torch.optim.Adam step on the flat fp32 params (mapping/optimizer.py:257-267,:376)
  * fused with the fp16 repack.  step >= 1. */
 int loner_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,

@@ -29,6 +29,95 @@ sgd_kernel(float* __restrict__ x, const float* __restrict__ g, int64_t n, float 
     x[i] = x[i] - lr * g[i];
 }
 
+// ---- poses: 6-vector [t | axis-angle] -> R | t through the unit quaternion (pytorch3d.transforms.axis_angle_to_matrix,
+// which tensor_to_transform calls), and its chain rule by forward-mode differentiation over the three rotation
+// parameters: a value with three tangents per intermediate, so the derivative follows the forward arithmetic line by line.
+struct D3 {
+  float v, d[3];
+};
+__device__ __forceinline__ D3 d3c(float c) { return D3{c, {0.f, 0.f, 0.f}}; }
+__device__ __forceinline__ D3 operator+(const D3& a, const D3& b) { return D3{a.v + b.v, {a.d[0] + b.d[0], a.d[1] + b.d[1], a.d[2] + b.d[2]}}; }
+__device__ __forceinline__ D3 operator-(const D3& a, const D3& b) { return D3{a.v - b.v, {a.d[0] - b.d[0], a.d[1] - b.d[1], a.d[2] - b.d[2]}}; }
+__device__ __forceinline__ D3 operator*(const D3& a, const D3& b) {
+  return D3{a.v * b.v, {a.d[0] * b.v + a.v * b.d[0], a.d[1] * b.v + a.v * b.d[1], a.d[2] * b.v + a.v * b.d[2]}};
+}
+__device__ __forceinline__ D3 operator/(const D3& a, const D3& b) {
+  const float q = a.v / b.v, ib = 1.f / b.v;
+  return D3{q, {(a.d[0] - q * b.d[0]) * ib, (a.d[1] - q * b.d[1]) * ib, (a.d[2] - q * b.d[2]) * ib}};
+}
+__device__ __forceinline__ D3 d3f(float v, float dv, const D3& x) {      // f(x) with f'(x) = dv
+  return D3{v, {dv * x.d[0], dv * x.d[1], dv * x.d[2]}};
+}
+// R (row-major, 9 values with tangents) of the axis-angle vector aa
+__device__ __forceinline__ void axis_angle_rotation(const float aa[3], D3 R[9]) {
+  D3 x[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { x[i] = d3c(aa[i]); x[i].d[i] = 1.f; }
+  const float n2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];
+  const float an = sqrtf(n2);
+  D3 angle = d3c(an);                                   // d|aa| / d aa = aa / |aa| (0 at the origin, like torch.norm)
+  if (an > 0.f) { angle.d[0] = aa[0] / an; angle.d[1] = aa[1] / an; angle.d[2] = aa[2] / an; }
+  const D3 half = angle * d3c(0.5f);
+  D3 s_over_a;                                          // sin(angle / 2) / angle, Taylor below 1e-6
+  if (fabsf(an) < 1e-6f) s_over_a = d3c(0.5f) - angle * angle * d3c(1.f / 48.f);
+  else s_over_a = d3f(sinf(half.v), cosf(half.v), half) / angle;
+  const D3 r = d3f(cosf(half.v), -sinf(half.v), half);
+  const D3 i = x[0] * s_over_a, j = x[1] * s_over_a, k = x[2] * s_over_a;
+  const D3 two_s = d3c(2.f) / (r * r + i * i + j * j + k * k);
+  const D3 one = d3c(1.f);
+  R[0] = one - two_s * (j * j + k * k); R[1] = two_s * (i * j - k * r);       R[2] = two_s * (i * k + j * r);
+  R[3] = two_s * (i * j + k * r);       R[4] = one - two_s * (i * i + k * k); R[5] = two_s * (j * k - i * r);
+  R[6] = two_s * (i * k - j * r);       R[7] = two_s * (j * k + i * r);       R[8] = one - two_s * (i * i + j * j);
+}
+
+__global__ void pose_matrices_kernel(const float* __restrict__ store, const int32_t* __restrict__ rows, int K,
+                                     float* __restrict__ poses12) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const float* p = store + (int64_t)rows[k] * 6;
+  const float aa[3] = {p[3], p[4], p[5]};
+  D3 R[9];
+  axis_angle_rotation(aa, R);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) poses12[k * 12 + e] = R[e].v;
+#pragma unroll
+  for (int e = 0; e < 3; ++e) poses12[k * 12 + 9 + e] = p[e];
+}
+
+// d_poses12 -> the gradient of the 6-vector; rows flagged free take one torch.optim.Adam step with their own step count
+__global__ void pose_step_kernel(float* __restrict__ store, const int32_t* __restrict__ rows, const uint8_t* __restrict__ free_rows,
+                                 int K, const float* __restrict__ d_poses12, float* __restrict__ grad6,
+                                 float* __restrict__ m, float* __restrict__ v, int32_t* __restrict__ steps, float lr,
+                                 float b1, float b2, float eps, int apply) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int64_t row = rows[k];
+  float* p = store + row * 6;
+  const float aa[3] = {p[3], p[4], p[5]};
+  D3 R[9];
+  axis_angle_rotation(aa, R);
+  const float* g12 = d_poses12 + k * 12;
+  float g[6] = {g12[9], g12[10], g12[11], 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int e = 0; e < 9; ++e) {
+    g[3] += g12[e] * R[e].d[0]; g[4] += g12[e] * R[e].d[1]; g[5] += g12[e] * R[e].d[2];
+  }
+  const bool is_free = free_rows[row] != 0;
+#pragma unroll
+  for (int e = 0; e < 6; ++e) grad6[row * 6 + e] = is_free ? g[e] : 0.f;
+  if (!apply || !is_free) return;
+  const int t = steps[row] + 1;
+  steps[row] = t;
+  const float bc1 = 1.f - powf(b1, (float)t), bc2_sqrt = sqrtf(1.f - powf(b2, (float)t));
+#pragma unroll
+  for (int e = 0; e < 6; ++e) {
+    const float mi = b1 * m[row * 6 + e] + (1.f - b1) * g[e];
+    const float vi = b2 * v[row * 6 + e] + (1.f - b2) * g[e] * g[e];
+    m[row * 6 + e] = mi; v[row * 6 + e] = vi;
+    p[e] = p[e] - (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+
 // One warp per ray.  The samples of a ray are sorted, so consecutive samples fall into the same voxel
 // cell for long runs (a cell is 2/V of the cube; S samples cover at most ~sqrt(3) V cells): every lane
 // walks a contiguous run of ceil(S/32) samples and keeps the 8 corner sums of its current cell in
@@ -125,6 +214,27 @@ extern "C" int loner_adam_step(float* params, const float* grads, float* exp_avg
   if (blocks > 1184) blocks = 1184;
   loner::adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, count, lr, beta1,
                                                               beta2, eps, (float)bc1, (float)sqrt(bc2), grad_unscale);
+  LONER_CHECK_LAUNCH();
+  return LONER_OK;
+}
+
+extern "C" int loner_pose_matrices(const float* poses6, const int32_t* rows, int32_t K, float* poses12, void* stream) {
+  if (K == 0) return LONER_OK;
+  if (!poses6 || !rows || !poses12 || K < 0) return LONER_E_BAD_ARG;
+  loner::pose_matrices_kernel<<<(K + 63) / 64, 64, 0, (cudaStream_t)stream>>>(poses6, rows, K, poses12);
+  LONER_CHECK_LAUNCH();
+  return LONER_OK;
+}
+
+extern "C" int loner_pose_step(float* poses6, const int32_t* rows, const uint8_t* free_rows, int32_t K,
+                               const float* d_poses12, float* grad6, float* exp_avg, float* exp_avg_sq, int32_t* steps,
+                               float lr, float beta1, float beta2, float eps, int32_t apply, void* stream) {
+  if (K == 0) return LONER_OK;
+  if (!poses6 || !rows || !free_rows || !d_poses12 || !grad6 || K < 0) return LONER_E_BAD_ARG;
+  if (apply && (!exp_avg || !exp_avg_sq || !steps)) return LONER_E_BAD_ARG;
+  loner::pose_step_kernel<<<(K + 63) / 64, 64, 0, (cudaStream_t)stream>>>(poses6, rows, free_rows, K, d_poses12, grad6,
+                                                                          exp_avg, exp_avg_sq, steps, lr, beta1, beta2, eps,
+                                                                          apply);
   LONER_CHECK_LAUNCH();
   return LONER_OK;
 }

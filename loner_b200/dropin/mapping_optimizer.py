@@ -76,8 +76,8 @@ class _AdamState:
         state = {0: {"step": torch.tensor(float(e.adam_t)), "exp_avg": e.exp_avg.detach().clone(),
                      "exp_avg_sq": e.exp_avg_sq.detach().clone()}}
         groups = [dict(base, lr=e.cfg.lrate_sigma_mlp, params=[0])]
-        if e.pose_opt is not None:
-            sd = e.pose_opt.state_dict()
+        if e.pose_phase:
+            sd = e.pose_state_dict()
             ids = sd["param_groups"][0]["params"]
             for i in ids:
                 if i in sd["state"]:

@@ -24,29 +24,6 @@ import torch.distributed as dist
 from . import ops, parallel
 
 
-def axis_angle_to_matrix(aa: torch.Tensor) -> torch.Tensor:
-    """[...,3] -> [...,3,3] via the unit quaternion, as pytorch3d.transforms does for the reference
-    (common/pose_utils.py:294); stays in PyTorch so pose 6-vectors remain autograd leaves."""
-    angles = torch.norm(aa, p=2, dim=-1, keepdim=True)
-    half = 0.5 * angles
-    small = angles.abs() < 1e-6
-    safe = torch.where(small, torch.ones_like(angles), angles)
-    s_over_a = torch.where(small, 0.5 - (angles * angles) / 48, torch.sin(half) / safe)
-    q = torch.cat([torch.cos(half), aa * s_over_a], dim=-1)
-    r, i, j, k = torch.unbind(q, -1)
-    two_s = 2.0 / (q * q).sum(-1)
-    o = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
-                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
-                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
-    return o.reshape(q.shape[:-1] + (3, 3))
-
-
-def poses6_to_poses12(poses6: torch.Tensor) -> torch.Tensor:
-    """[K,6] = [t, axis-angle] -> [K,12] = R row-major | t  (common/pose_utils.py:288-302)."""
-    R = axis_angle_to_matrix(poses6[:, 3:])
-    return torch.cat([R.reshape(-1, 9), poses6[:, :3]], dim=1)
-
-
 @dataclass
 class EngineConfig:
     # geometry (WorldCube + ray_range of the sequence file)
@@ -158,8 +135,15 @@ class MappingEngine:
         self.kf_sky_offsets = []
         self.kf_sky_sizes = []
         self.kf_masks = []
-        self.poses6 = []            # list of [6] leaf tensors on device
-        self.pose_opt = None
+        # pose store [capacity,6] = [t | axis-angle] per keyframe, with its gradient, Adam moments and step counts;
+        # poses6[k] is a VIEW of row k (whose .grad is set after a step that optimised poses)
+        self._pose_cap = 0
+        self.poses6 = []
+        self._grow_pose_store(256)
+        self._pose_free_host = []   # per keyframe: its pose is optimised in the current phase
+        self.pose_phase = False     # a pose-optimising phase is open (new_phase(optimize_poses=True))
+        self._pose_rows = None      # (window, int32 device rows)
+        self._grad_rows = []        # keyframes whose poses6[k].grad is currently set
         self.world = dist.get_world_size() if distributed and dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
         # every rank draws its own rays and noise: the streams are keyed by (cfg.seed, rank)
@@ -179,6 +163,31 @@ class MappingEngine:
         self._last_d_poses12 = None
         self._counters = torch.zeros(2, device=self.dev, dtype=torch.int32)
         self._side = None           # side stream of the loss-normaliser all-reduce (multi-GPU)
+
+    def _grow_pose_store(self, cap):
+        n = len(self.poses6)
+        new = lambda *shape, dt=torch.float32: torch.zeros(*shape, device=self.dev, dtype=dt)
+        store, grad, m, v = new(cap, 6), new(cap, 6), new(cap, 6), new(cap, 6)
+        steps, free = new(cap, dt=torch.int32), new(cap, dt=torch.uint8)
+        if n:
+            for dst, src in ((store, self.pose_store), (grad, self.pose_grad), (m, self.pose_m), (v, self.pose_v),
+                             (steps, self.pose_steps), (free, self.pose_free)):
+                dst[:n] = src[:n]
+        self.pose_store, self.pose_grad, self.pose_m, self.pose_v = store, grad, m, v
+        self.pose_steps, self.pose_free = steps, free
+        self._pose_cap = cap
+        self.poses6 = [store[k] for k in range(n)]
+        self._pose_rows = None
+        self._grad_rows = []
+
+    def pose_state_dict(self):
+        """The pose group of the current phase in torch.optim.Adam's state_dict format (checkpoint surface)."""
+        ids = [k for k, f in enumerate(self._pose_free_host) if f]
+        steps = self.pose_steps[:len(self.poses6)].cpu()
+        state = {i: {"step": torch.tensor(float(steps[k])), "exp_avg": self.pose_m[k].detach().clone(),
+                     "exp_avg_sq": self.pose_v[k].detach().clone()}
+                 for i, k in enumerate(ids) if int(steps[k]) > 0}
+        return {"state": state, "param_groups": [dict(lr=self.cfg.lrate_pose, params=list(range(len(ids))))]}
 
     def _views(self, K):
         """The flat exchange buffer for a K-keyframe window and its three views.  The kernels write the
@@ -228,7 +237,12 @@ class MappingEngine:
         self.kf_sky_offsets.append(self.n_points + n_l)
         self.kf_sky_sizes.append(n_s)
         self.n_points = need
-        self.poses6.append(pose6.detach().to(self.dev, torch.float32).clone())
+        k = len(self.poses6)
+        if k >= self._pose_cap:
+            self._grow_pose_store(2 * self._pose_cap)
+        self.pose_store[k] = pose6.detach().to(self.dev, torch.float32)
+        self.poses6.append(self.pose_store[k])
+        self._pose_free_host.append(False)
         self._pose_cache = None
         self._wcache = {}
         return len(self.poses6) - 1
@@ -241,15 +255,14 @@ class MappingEngine:
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
         self.adam_t = 0
-        self.pose_opt = None
         self._pose_cache = None
-        for k, p in enumerate(self.poses6):
-            free = (k > 0) if pose_ids is None else (k in pose_ids)     # keyframe 0 is anchored by default
-            p.requires_grad_(bool(optimize_poses and free))
-        if optimize_poses:
-            leaves = [p for p in self.poses6 if p.requires_grad]
-            if leaves:
-                self.pose_opt = torch.optim.Adam([{"params": leaves, "lr": self.cfg.lrate_pose}])
+        n = len(self.poses6)
+        # keyframe 0 is anchored by default
+        self._pose_free_host = [bool(optimize_poses and ((k > 0) if pose_ids is None else (k in pose_ids))) for k in range(n)]
+        self.pose_phase = bool(optimize_poses) and any(self._pose_free_host)
+        self.pose_m.zero_(); self.pose_v.zero_(); self.pose_steps.zero_()
+        if n:
+            self.pose_free[:n] = torch.tensor(self._pose_free_host, dtype=torch.uint8).to(self.dev)
 
     # ---------------------------------------------------------------- helpers
     @contextlib.contextmanager
@@ -346,12 +359,15 @@ class MappingEngine:
         return ray_kf, ray_point.contiguous()
 
     def _poses12(self, window, optimize_poses):
-        """[K,12] pose matrices; recomputed through autograd only while poses are being optimised."""
+        """[K,12] pose matrices of the window (loner_pose_matrices); recomputed every step only while poses move."""
         key = tuple(window)
         if not optimize_poses and self._pose_cache is not None and self._pose_cache[0] == key:
             return self._pose_cache[1]
-        p12 = poses6_to_poses12(torch.stack([self.poses6[k] for k in window]))
-        self._pose_cache = None if optimize_poses else (key, p12.detach().contiguous())
+        if self._pose_rows is None or self._pose_rows[0] != key:
+            self._pose_rows = (key, torch.tensor(list(window), dtype=torch.int32).to(self.dev))
+        p12 = ops.pose_matrices(self.pose_store, self._pose_rows[1])
+        self.launches += 1
+        self._pose_cache = None if optimize_poses else (key, p12)
         return p12
 
     def _lr(self, base):
@@ -386,8 +402,7 @@ class MappingEngine:
             ray_kf, ray_point = self._injected_rays(window, n_per_kf, injected["ray_point"], injected.get("ray_kf"))
         else:
             ray_kf, ray_point = self._pick_rays(window, n_per_kf)
-        poses12 = self._poses12(window, optimize_poses)
-        p12 = poses12.detach().contiguous()
+        p12 = self._poses12(window, optimize_poses)
         self._flat.zero_()                 # d_params, d_poses12, loss sums: one memset
         counters = self._counters.zero_()
         rays, depths, flags = ops.ray_build(self.points, ray_kf, ray_point, p12, cfg.shift, cfg.scale,
@@ -403,13 +418,15 @@ class MappingEngine:
             self.launches += 1
         loss = self._exchange_and_update(loss_acc, counters, d_poses12)
         if d_poses12 is not None:
-            for p in self.poses6:
-                p.grad = None
-            poses12.backward(self._last_d_poses12)
-            if self.pose_opt is not None:
-                for g in self.pose_opt.param_groups:
-                    g["lr"] = self._lr(cfg.lrate_pose)
-                self.pose_opt.step()
+            # chain rule to the 6-vectors + the pose group's Adam step (optimizer.py:249-267,:376): one kernel
+            ops.pose_step(self.pose_store, self._pose_rows[1], self.pose_free, self._last_d_poses12, self.pose_grad,
+                          self.pose_m, self.pose_v, self.pose_steps, self._lr(cfg.lrate_pose), apply=self.pose_phase)
+            self.launches += 1
+            for k in self._grad_rows:
+                self.poses6[k].grad = None
+            self._grad_rows = [k for k in window if self._pose_free_host[k]]
+            for k in self._grad_rows:
+                self.poses6[k].grad = self.pose_grad[k]
         self._occupancy_update(rays, depths, flags)
         return loss
 

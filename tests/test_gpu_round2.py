@@ -478,3 +478,47 @@ def test_two_rank_nccl_step_equals_single_gpu_step():
     print("2-rank NCCL grad check:", r)
     assert r["world"] == 2
     assert r["loss_rel"] < 1e-5 and r["d_params_rel"] < 1e-5 and r["pose_grad_rel"] < 1e-4
+
+
+def test_pose_kernels_match_autograd_and_torch_adam():
+    """loner_pose_matrices / loner_pose_step (a5 + the pose group of optimizer.py:249-267) against the PyTorch
+    restatement of tensor_to_transform with autograd and torch.optim.Adam: matrices 1e-6, gradients 1e-5 of the
+    largest entry, three Adam steps on the free rows 1e-6; anchored rows do not move and get a zero gradient."""
+    from gpu_util import poses6_to_poses12
+    g = torch.Generator().manual_seed(3)
+    n = 7
+    store = torch.randn(n, 6, generator=g)
+    store[1, 3:] = 0.0                         # identity rotation (norm gradient 0 at the origin)
+    store[2, 3:] = torch.tensor([3e-7, -2e-7, 1e-7])      # Taylor branch
+    store[3, 3:] *= 2.5                        # angle > pi
+    rows = torch.tensor([5, 0, 3, 2, 1], dtype=torch.int32)
+    free = torch.tensor([0, 1, 1, 1, 0, 1, 1], dtype=torch.uint8)
+    d12 = torch.randn(3, rows.numel(), 12, generator=g)
+    # reference: autograd + torch.optim.Adam over the free rows
+    leaves = [store[k].clone().requires_grad_(bool(free[k])) for k in range(n)]
+    opt = torch.optim.Adam([p for p in leaves if p.requires_grad], lr=1e-2)
+    ref_mats, ref_grads = [], []
+    for it in range(3):
+        opt.zero_grad(set_to_none=True)
+        p12 = poses6_to_poses12(torch.stack([leaves[int(k)] for k in rows]))
+        ref_mats.append(p12.detach().clone())
+        p12.backward(d12[it])
+        ref_grads.append(torch.stack([p.grad.clone() if p.grad is not None else torch.zeros(6) for p in leaves]))
+        opt.step()
+    # kernels
+    st = store.to(DEV).contiguous()
+    rows_d, free_d = rows.to(DEV), free.to(DEV)
+    grad6 = torch.zeros(n, 6, device=DEV)
+    m, v = torch.zeros(n, 6, device=DEV), torch.zeros(n, 6, device=DEV)
+    steps = torch.zeros(n, dtype=torch.int32, device=DEV)
+    for it in range(3):
+        mats = ops.pose_matrices(st, rows_d)
+        assert (mats.cpu() - ref_mats[it]).abs().max() < 2e-6
+        grad6.zero_()
+        ops.pose_step(st, rows_d, free_d, d12[it].to(DEV).contiguous(), grad6, m, v, steps, 1e-2)
+        err = (grad6.cpu() - ref_grads[it]).abs().max() / ref_grads[it].abs().max()
+        assert err < 1e-5, err
+    want = torch.stack([p.detach() for p in leaves])
+    assert (st.cpu() - want).abs().max() < 2e-6
+    assert torch.equal(st.cpu()[[0, 4]], store[[0, 4]])                 # anchored rows untouched
+    assert steps.cpu().tolist() == [0, 3, 3, 3, 0, 3, 0]                # row 6 is free but outside the window
