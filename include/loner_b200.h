@@ -198,14 +198,22 @@ int loner_points_bwd(const float* d_pos, const float* z_vals, int64_t n, int32_t
 /* ---- a5  pose 6-vectors [t | axis-angle] -> [K,12] = R row-major | t (common/pose_utils.py:288-302
  * tensor_to_transform, i.e. pytorch3d.transforms.axis_angle_to_matrix through the unit quaternion).
  * poses6: the keyframe pose store [n_keyframes,6]; rows [K]: store rows of the window's keyframes. */
-int loner_pose_matrices(const float* poses6, const int32_t* rows, int32_t K, float* poses12, void* stream);
+int loner_pose_matrices(const float* poses6, const int32_t* rows, int32_t K, const float* shift, float scale,
+                        float* poses12, int32_t* status, void* stream);
+/* status (device int32, may be NULL; bits are OR-ed in, the caller reads it when it chooses - no host sync here):
+ * the reference's runtime guards on this path.  shift: host float[3], with scale the WorldCube of loner_ray_build. */
+#define LONER_STATUS_ORIGIN_OUTSIDE 1 /* "ray origins are outside the world cube" assert, common/ray_utils.py:301-303 */
+#define LONER_STATUS_BAD_POSE_GRAD 2  /* "Fatal: Encountered invalid gradient in pose.", mapping/optimizer.py:368-370 */
+#define LONER_STATUS_BAD_POSE 4       /* "Fatal: Encountered invalid pose tensor.", mapping/optimizer.py:372-374 */
 
 /* chain rule of the above + the pose half of the optimiser (mapping/optimizer.py:249-267,:376): d_poses12 [K,12] ->
  * grad6 [n_keyframes,6] (rows of the window; zero for rows with free_rows[row] == 0), and, if apply != 0, one
- * torch.optim.Adam step on the free rows (per-row step counts in steps [n_keyframes], moments [n_keyframes,6]). */
+ * torch.optim.Adam step on the free rows (per-row step counts in steps [n_keyframes], moments [n_keyframes,6]).
+ * A row whose gradient is not finite keeps its pose and sets LONER_STATUS_BAD_POSE_GRAD (the reference raises before
+ * optimizer.step()). */
 int loner_pose_step(float* poses6, const int32_t* rows, const uint8_t* free_rows, int32_t K, const float* d_poses12,
                     float* grad6, float* exp_avg, float* exp_avg_sq, int32_t* steps, float lr, float beta1,
-                    float beta2, float eps, int32_t apply, void* stream);
+                    float beta2, float eps, int32_t apply, int32_t* status, void* stream);
 
 /* ---- a18  torch.optim.Adam step on the flat fp32 params (mapping/optimizer.py:257-267,:376)
  * fused with the fp16 repack.  step >= 1. */

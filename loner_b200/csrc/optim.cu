@@ -70,12 +70,28 @@ __device__ __forceinline__ void axis_angle_rotation(const float aa[3], D3 R[9]) 
   R[6] = two_s * (i * k - j * r);       R[7] = two_s * (j * k + i * r);       R[8] = one - two_s * (i * i + j * j);
 }
 
+__device__ __forceinline__ bool finite6(const float* p) {
+  bool ok = true;
+#pragma unroll
+  for (int e = 0; e < 6; ++e) ok = ok && isfinite(p[e]);
+  return ok;
+}
+
 __global__ void pose_matrices_kernel(const float* __restrict__ store, const int32_t* __restrict__ rows, int K,
-                                     float* __restrict__ poses12) {
+                                     float sx, float sy, float sz, float scale, float* __restrict__ poses12,
+                                     int32_t* __restrict__ status) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   const float* p = store + (int64_t)rows[k] * 6;
   const float aa[3] = {p[3], p[4], p[5]};
+  if (status != nullptr) {
+    int bits = 0;
+    if (!finite6(p)) bits |= LONER_STATUS_BAD_POSE;
+    // the sensor origin (every ray origin of this keyframe) must lie inside the world cube [-1,1]^3
+    const float ox = (p[0] + sx) / scale, oy = (p[1] + sy) / scale, oz = (p[2] + sz) / scale;
+    if (fmaxf(fabsf(ox), fmaxf(fabsf(oy), fabsf(oz))) > 1.f) bits |= LONER_STATUS_ORIGIN_OUTSIDE;
+    if (bits) atomicOr(status, bits);
+  }
   D3 R[9];
   axis_angle_rotation(aa, R);
 #pragma unroll
@@ -88,7 +104,7 @@ __global__ void pose_matrices_kernel(const float* __restrict__ store, const int3
 __global__ void pose_step_kernel(float* __restrict__ store, const int32_t* __restrict__ rows, const uint8_t* __restrict__ free_rows,
                                  int K, const float* __restrict__ d_poses12, float* __restrict__ grad6,
                                  float* __restrict__ m, float* __restrict__ v, int32_t* __restrict__ steps, float lr,
-                                 float b1, float b2, float eps, int apply) {
+                                 float b1, float b2, float eps, int apply, int32_t* __restrict__ status) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   const int64_t row = rows[k];
@@ -106,6 +122,10 @@ __global__ void pose_step_kernel(float* __restrict__ store, const int32_t* __res
 #pragma unroll
   for (int e = 0; e < 6; ++e) grad6[row * 6 + e] = is_free ? g[e] : 0.f;
   if (!apply || !is_free) return;
+  if (!finite6(g)) {                        // the reference raises before optimizer.step(): the row keeps its pose
+    if (status != nullptr) atomicOr(status, LONER_STATUS_BAD_POSE_GRAD);
+    return;
+  }
   const int t = steps[row] + 1;
   steps[row] = t;
   const float bc1 = 1.f - powf(b1, (float)t), bc2_sqrt = sqrtf(1.f - powf(b2, (float)t));
@@ -116,6 +136,7 @@ __global__ void pose_step_kernel(float* __restrict__ store, const int32_t* __res
     m[row * 6 + e] = mi; v[row * 6 + e] = vi;
     p[e] = p[e] - (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
   }
+  if (status != nullptr && !finite6(p)) atomicOr(status, LONER_STATUS_BAD_POSE);
 }
 
 // One warp per ray.  The samples of a ray are sorted, so consecutive samples fall into the same voxel
@@ -218,23 +239,27 @@ extern "C" int loner_adam_step(float* params, const float* grads, float* exp_avg
   return LONER_OK;
 }
 
-extern "C" int loner_pose_matrices(const float* poses6, const int32_t* rows, int32_t K, float* poses12, void* stream) {
+extern "C" int loner_pose_matrices(const float* poses6, const int32_t* rows, int32_t K, const float* shift, float scale,
+                                   float* poses12, int32_t* status, void* stream) {
   if (K == 0) return LONER_OK;
-  if (!poses6 || !rows || !poses12 || K < 0) return LONER_E_BAD_ARG;
-  loner::pose_matrices_kernel<<<(K + 63) / 64, 64, 0, (cudaStream_t)stream>>>(poses6, rows, K, poses12);
+  if (!poses6 || !rows || !poses12 || K < 0 || (status && (!shift || !(scale > 0.f)))) return LONER_E_BAD_ARG;
+  const float sx = shift ? shift[0] : 0.f, sy = shift ? shift[1] : 0.f, sz = shift ? shift[2] : 0.f;
+  loner::pose_matrices_kernel<<<(K + 63) / 64, 64, 0, (cudaStream_t)stream>>>(poses6, rows, K, sx, sy, sz, scale, poses12,
+                                                                              status);
   LONER_CHECK_LAUNCH();
   return LONER_OK;
 }
 
 extern "C" int loner_pose_step(float* poses6, const int32_t* rows, const uint8_t* free_rows, int32_t K,
                                const float* d_poses12, float* grad6, float* exp_avg, float* exp_avg_sq, int32_t* steps,
-                               float lr, float beta1, float beta2, float eps, int32_t apply, void* stream) {
+                               float lr, float beta1, float beta2, float eps, int32_t apply, int32_t* status,
+                               void* stream) {
   if (K == 0) return LONER_OK;
   if (!poses6 || !rows || !free_rows || !d_poses12 || !grad6 || K < 0) return LONER_E_BAD_ARG;
   if (apply && (!exp_avg || !exp_avg_sq || !steps)) return LONER_E_BAD_ARG;
   loner::pose_step_kernel<<<(K + 63) / 64, 64, 0, (cudaStream_t)stream>>>(poses6, rows, free_rows, K, d_poses12, grad6,
                                                                           exp_avg, exp_avg_sq, steps, lr, beta1, beta2, eps,
-                                                                          apply);
+                                                                          apply, status);
   LONER_CHECK_LAUNCH();
   return LONER_OK;
 }

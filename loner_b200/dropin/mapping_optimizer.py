@@ -233,6 +233,7 @@ class FusedOptimizer:
                 phase_losses.append(loss)
                 self._global_step += 1
             self._depth_eps = float(self._engine.last["depth_eps"])
+            self._engine.check_status()        # the pose / world-cube guards of optimizer.py:368-374, ray_utils.py:301-303
             # hand the optimised poses back to the keyframes (their tensors are what the mapper emits)
             for kf, k in zip(active, ids):
                 if k in free and optimize_poses:

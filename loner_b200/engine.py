@@ -140,6 +140,7 @@ class MappingEngine:
         self._pose_cap = 0
         self.poses6 = []
         self._grow_pose_store(256)
+        self.status = torch.zeros(1, device=self.dev, dtype=torch.int32)      # LONER_STATUS_* bits, see check_status
         self._pose_free_host = []   # per keyframe: its pose is optimised in the current phase
         self.pose_phase = False     # a pose-optimising phase is open (new_phase(optimize_poses=True))
         self._pose_rows = None      # (window, int32 device rows)
@@ -179,6 +180,19 @@ class MappingEngine:
         self.poses6 = [store[k] for k in range(n)]
         self._pose_rows = None
         self._grad_rows = []
+
+    def check_status(self):
+        """The reference's runtime guards, checked lazily: the kernels OR LONER_STATUS_* bits into a device word and
+        this call (one 4-byte read, a host sync) raises what the reference would have raised inside the iteration."""
+        bits = int(self.status.item())
+        if bits:
+            self.status.zero_()
+        if bits & ops.STATUS_ORIGIN_OUTSIDE:          # common/ray_utils.py:301-303
+            raise AssertionError("ray origins are outside the world cube")
+        if bits & ops.STATUS_BAD_POSE_GRAD:           # mapping/optimizer.py:368-370
+            raise RuntimeError("Fatal: Encountered invalid gradient in pose.")
+        if bits & ops.STATUS_BAD_POSE:                # mapping/optimizer.py:372-374
+            raise RuntimeError("Fatal: Encountered invalid pose tensor.")
 
     def pose_state_dict(self):
         """The pose group of the current phase in torch.optim.Adam's state_dict format (checkpoint surface)."""
@@ -365,7 +379,8 @@ class MappingEngine:
             return self._pose_cache[1]
         if self._pose_rows is None or self._pose_rows[0] != key:
             self._pose_rows = (key, torch.tensor(list(window), dtype=torch.int32).to(self.dev))
-        p12 = ops.pose_matrices(self.pose_store, self._pose_rows[1])
+        p12 = ops.pose_matrices(self.pose_store, self._pose_rows[1], shift=self.cfg.shift, scale=self.cfg.scale,
+                                status=self.status)
         self.launches += 1
         self._pose_cache = None if optimize_poses else (key, p12)
         return p12
@@ -420,7 +435,8 @@ class MappingEngine:
         if d_poses12 is not None:
             # chain rule to the 6-vectors + the pose group's Adam step (optimizer.py:249-267,:376): one kernel
             ops.pose_step(self.pose_store, self._pose_rows[1], self.pose_free, self._last_d_poses12, self.pose_grad,
-                          self.pose_m, self.pose_v, self.pose_steps, self._lr(cfg.lrate_pose), apply=self.pose_phase)
+                          self.pose_m, self.pose_v, self.pose_steps, self._lr(cfg.lrate_pose), apply=self.pose_phase,
+                          status=self.status)
             self.launches += 1
             for k in self._grad_rows:
                 self.poses6[k].grad = None

@@ -62,8 +62,8 @@ _SIGS = {
     "loner_adam_step": (_c.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "loner_ogm_grad": (_c.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp]),
     "loner_sgd_step": (_c.c_int, [_vp, _vp, _i64, _f32, _vp]),
-    "loner_pose_matrices": (_c.c_int, [_vp, _vp, _i32, _vp, _vp]),
-    "loner_pose_step": (_c.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _vp]),
+    "loner_pose_matrices": (_c.c_int, [_vp, _vp, _i32, _vp, _f32, _vp, _vp, _vp]),
+    "loner_pose_step": (_c.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
 }
 
 _lib = None

@@ -307,22 +307,27 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.9
                                      float(grad_unscale), L.stream_ptr()), "loner_adam_step")
 
 
-def pose_matrices(poses6, rows, out=None):
-    """poses6 [n_keyframes,6] store, rows int32 [K] -> [K,12] = R row-major | t."""
+STATUS_ORIGIN_OUTSIDE, STATUS_BAD_POSE_GRAD, STATUS_BAD_POSE = 1, 2, 4      # LONER_STATUS_*
+
+
+def pose_matrices(poses6, rows, out=None, shift=None, scale=1.0, status=None):
+    """poses6 [n_keyframes,6] store, rows int32 [K] -> [K,12] = R row-major | t.  status: device int32 word that
+    collects LONER_STATUS_* bits (origin outside the world cube given by shift / scale, non-finite pose)."""
     K = rows.shape[0]
     p12 = torch.empty(K, 12, device=poses6.device, dtype=torch.float32) if out is None else out
-    L.check(L.load().loner_pose_matrices(L.ptr(_f32(poses6)), L.ptr(rows), K, L.ptr(p12), L.stream_ptr()),
-            "loner_pose_matrices")
+    sh = L.host_floats(shift) if shift is not None else None
+    L.check(L.load().loner_pose_matrices(L.ptr(_f32(poses6)), L.ptr(rows), K, sh, float(scale), L.ptr(p12),
+                                         L.ptr(status), L.stream_ptr()), "loner_pose_matrices")
     return p12
 
 
 def pose_step(poses6, rows, free_rows, d_poses12, grad6, exp_avg=None, exp_avg_sq=None, steps=None, lr=0.0,
-              beta1=0.9, beta2=0.999, eps=1e-8, apply=True):
+              beta1=0.9, beta2=0.999, eps=1e-8, apply=True, status=None):
     """Chain rule d_poses12 -> grad6 rows of the window; apply: Adam step on the rows with free_rows != 0."""
     L.check(L.load().loner_pose_step(L.ptr(_f32(poses6)), L.ptr(rows), L.ptr(free_rows), rows.shape[0],
                                      L.ptr(_f32(d_poses12)), L.ptr(grad6), L.ptr(exp_avg), L.ptr(exp_avg_sq),
                                      L.ptr(steps), float(lr), float(beta1), float(beta2), float(eps), int(bool(apply)),
-                                     L.stream_ptr()), "loner_pose_step")
+                                     L.ptr(status), L.stream_ptr()), "loner_pose_step")
     return grad6
 
 

@@ -522,3 +522,45 @@ def test_pose_kernels_match_autograd_and_torch_adam():
     assert (st.cpu() - want).abs().max() < 2e-6
     assert torch.equal(st.cpu()[[0, 4]], store[[0, 4]])                 # anchored rows untouched
     assert steps.cpu().tolist() == [0, 3, 3, 3, 0, 3, 0]                # row 6 is free but outside the window
+
+
+def test_pose_guards_set_status_and_raise_like_the_reference():
+    """optimizer.py:368-374 and ray_utils.py:301-303 as a lazily checked device status word."""
+    st = torch.zeros(3, 6, device=DEV)
+    st[1, :3] = torch.tensor([1000.0, 0.0, 0.0], device=DEV)          # far outside any world cube
+    rows = torch.tensor([0, 1, 2], dtype=torch.int32, device=DEV)
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.pose_matrices(st, rows[:1], shift=(0.0, 0.0, 0.0), scale=50.0, status=status)
+    assert int(status.item()) == 0
+    ops.pose_matrices(st, rows, shift=(0.0, 0.0, 0.0), scale=50.0, status=status)
+    assert int(status.item()) == ops.STATUS_ORIGIN_OUTSIDE
+    # a non-finite gradient: the row keeps its pose, the finite row steps
+    status.zero_()
+    free = torch.ones(3, dtype=torch.uint8, device=DEV)
+    d12 = torch.ones(3, 12, device=DEV)
+    d12[2, 10] = float("nan")
+    grad6, m, v = (torch.zeros(3, 6, device=DEV) for _ in range(3))
+    steps = torch.zeros(3, dtype=torch.int32, device=DEV)
+    before = st.clone()
+    ops.pose_step(st, rows, free, d12, grad6, m, v, steps, 1e-2, status=status)
+    assert int(status.item()) == ops.STATUS_BAD_POSE_GRAD
+    assert torch.equal(st[2], before[2]) and not torch.equal(st[0], before[0])
+    assert steps.cpu().tolist() == [1, 1, 0]
+    # through the engine: a keyframe whose origin leaves the cube raises the reference's assertion at check_status()
+    c = Case("kf2_2x128_fp16")
+    e = _engine(c)
+    for k in range(c.K):
+        e.add_keyframe(c.scans[k].ray_directions, c.scans[k].distances, c.poses6[k])
+    e.new_phase(False)
+    e.step([0, 1], 64)
+    e.check_status()
+    e.poses6[1].data[:3] += 10.0 * c.scale
+    e._pose_cache = None
+    e.step([0, 1], 64)
+    with pytest.raises(AssertionError, match="outside the world cube"):
+        e.check_status()
+    e.pose_store[1, 3] = float("inf")
+    e._pose_cache = None
+    e.step([0, 1], 64)
+    with pytest.raises((AssertionError, RuntimeError)):
+        e.check_status()
