@@ -126,9 +126,10 @@ int loner_mlp_wgrad(const loner_net_t* net, const void* packed, int64_t P, const
 
 /* ---- a12 (shipped configuration), SURVEY 8f rank 1: multiresolution hash encoding + one hidden layer
  * of 64 neurons = the reference's default `pos_encoding_sigma` / `sigma_network`
- * (cfg/nerf_config/default_nerf_hash.yaml; models/nerf_tcnn.py:35-38, :59-78).  tiny-cuda-nn semantics
+ * (cfg/nerf_config/default_nerf_hash.yaml; models/nerf_tcnn.py:35-38, :59-78), and the same encoding with
+ * 2-4 hidden layers of 64 (other `sigma_network.n_hidden_layers`).  tiny-cuda-nn semantics
  * (grid type Hash, linear interpolation, fp16 table / weights / activations, fp32 accumulation).
- * Flat fp32 params, tcnn order: W1 [64, E_pad] | W_out [16, 64] (row 0 used) | table [entries, 2]. */
+ * Flat fp32 params, tcnn order: W1 [64, E_pad] | W_2 .. W_L [64, 64] | W_out [16, 64] (row 0 used) | table [entries, 2]. */
 typedef struct {
   int32_t n_levels;              /* <= 16 */
   int32_t n_features_per_level;  /* 2 */
@@ -136,7 +137,7 @@ typedef struct {
   int32_t base_resolution;
   float per_level_scale;         /* <= 0: tcnn's default 2.0 */
   int32_t n_neurons;             /* 64 */
-  int32_t n_hidden_layers;       /* 1 */
+  int32_t n_hidden_layers;       /* 1 (shipped) .. 4 */
   int32_t flags;                 /* 0 = production kernels (warp-level tensor-core head); LONER_HASH_* A/B variants */
 } loner_hashnet_t;
 /* the head (32 -> 64 -> 1) on scalar CUDA-core code instead of mma.sync tiles (round 1's kernels) */

@@ -23,10 +23,12 @@ namespace hashgrid {
 constexpr int kMaxLevels = 16;
 constexpr int kW = 64;             // hidden width
 constexpr int kThreads = 256;
+constexpr int kMaxHidden = 4;      // hidden layers supported (tcnn FullyFusedMLP width 64)
 
 struct HashNet {
   int flags;                       // LONER_HASH_* (kernel variants)
   int n_levels, E, Epad;           // E = 2 * n_levels encoded features, padded to 16 with 1.0
+  int L;                           // hidden layers of 64 neurons (1 = the shipped head; 2-4 run on the "deep" kernels)
   float scale[kMaxLevels];
   uint32_t res[kMaxLevels];
   uint32_t entries[kMaxLevels];    // "hashmap size" of the level
@@ -38,7 +40,9 @@ __host__ inline bool net_from(const loner_hashnet_t* n, HashNet& o) {
   if (!n) return false;
   if (n->n_levels < 1 || n->n_levels > kMaxLevels || n->n_features_per_level != 2) return false;
   if (n->log2_hashmap_size < 4 || n->log2_hashmap_size > 24 || n->base_resolution < 1) return false;
-  if (n->n_neurons != kW || n->n_hidden_layers != 1) return false;
+  if (n->n_neurons != kW || n->n_hidden_layers < 1 || n->n_hidden_layers > kMaxHidden) return false;
+  if (n->n_hidden_layers > 1 && (n->flags & LONER_HASH_SCALAR)) return false;     // the scalar A/B kernels are 1 x 64 only
+  o.L = n->n_hidden_layers;
   const float pls = n->per_level_scale > 0.f ? n->per_level_scale : 2.0f;
   o.n_levels = n->n_levels;
   o.flags = n->flags;
@@ -67,14 +71,15 @@ __host__ inline bool net_from(const loner_hashnet_t* n, HashNet& o) {
 }
 __host__ __device__ inline int64_t n_entries(const HashNet& n) { return n.offset[kMaxLevels]; }
 __host__ __device__ inline int64_t w1_floats(const HashNet& n) { return (int64_t)kW * n.Epad; }
-__host__ __device__ inline int64_t net_floats(const HashNet& n) { return w1_floats(n) + 16 * kW; }   // + padded [16, W] output matrix
-// packed image: W1 fp16 [64][Epad] | w_out fp32 [64] (values of the fp16-rounded row 0) | table half2 [entries]
-__host__ __device__ inline int64_t packed_wout_off(const HashNet& n) { return w1_floats(n) * 2; }
+__host__ __device__ inline int64_t wh_floats(const HashNet& n) { return (int64_t)(n.L - 1) * kW * kW; }   // hidden matrices 2..L
+__host__ __device__ inline int64_t net_floats(const HashNet& n) { return w1_floats(n) + wh_floats(n) + 16 * kW; }   // + padded [16, W] output matrix
+// packed image: W1 fp16 [64][Epad] | W_2..W_L fp16 [64][64] | w_out fp32 [64] (values of the fp16-rounded row 0) | table half2 [entries]
+__host__ __device__ inline int64_t packed_wout_off(const HashNet& n) { return (w1_floats(n) + wh_floats(n)) * 2; }
 __host__ __device__ inline int64_t packed_table_off(const HashNet& n) { return packed_wout_off(n) + kW * 4; }
 __host__ __device__ inline int64_t packed_total(const HashNet& n) { return packed_table_off(n) + n_entries(n) * 4; }
 
 __global__ void __launch_bounds__(256) pack_kernel(HashNet net, const float* __restrict__ params, uint8_t* __restrict__ packed) {
-  const int64_t nw1 = w1_floats(net), nt = n_entries(net);
+  const int64_t nw1 = w1_floats(net) + wh_floats(net), nt = n_entries(net);      // all fp16 matrices, contiguous
   __half* w1 = reinterpret_cast<__half*>(packed);
   float* wo = reinterpret_cast<float*>(packed + packed_wout_off(net));
   __half2* tb = reinterpret_cast<__half2*>(packed + packed_table_off(net));
@@ -504,6 +509,84 @@ __global__ void __launch_bounds__(kThreads, 2) hash_fwd_mma_kernel(const Args a)
   }
 }
 
+// Table-gradient scatter of one sample per lane (denc_row = its 32 encoding gradients), and d_pos through the
+// interpolation weights.
+template <bool kDx>
+__device__ __forceinline__ void scatter_levels(const Args& a, const HashNet& net, const __half2* __restrict__ table,
+                                               const float (&x)[3], const float* denc_row, bool in, float ds, int lane,
+                                               int64_t s) {
+  // ---- scatter into the gradient table, and d_pos through the interpolation weights.
+  // The COARSE levels are aggregated inside the warp first: the lanes of a warp are consecutive samples of one ray,
+  // so on a coarse level they sit in the same cell for long runs, and near the sensor origin EVERY ray of the
+  // keyframe hits the same few cells - up to 4 x 10^5 reductions per address and step, which the L2 serialises
+  // (measured: 6.5 ms on ray-ordered samples sharing an origin against 4.0 ms on independent positions).  Each
+  // maximal run of equal cells is summed with a segmented shuffle reduction and only its first lane issues the
+  // eight vector reductions.
+  float dx[3] = {0.f, 0.f, 0.f};
+  const bool act = in && ds != 0.f;
+#pragma unroll 2
+  for (int l = 0; l < net.n_levels; ++l) {
+    const Cell q = locate(net.scale[l], x);
+    const uint32_t res = net.res[l], ent = net.entries[l];
+    const bool dense = net.dense[l] != 0u;
+    float2* gt = reinterpret_cast<float2*>(a.d_table) + net.offset[l];
+    const float gx = act ? denc_row[2 * l] : 0.f, gy = act ? denc_row[2 * l + 1] : 0.f;
+    const bool agg = l < kAggLevels && res <= 1024u;          // warp-uniform
+    float v[16];
+    bool issue = act;
+    if (agg) {
+      const uint32_t key = act ? q.c[0] + res * (q.c[1] + res * q.c[2]) : 0xFFFFFFFFu;
+      const uint32_t prev = __shfl_up_sync(kFull, key, 1);
+      const bool head = lane == 0 || prev != key;
+      const uint32_t heads = __ballot_sync(kFull, head);
+      const uint32_t later = heads & ~((2u << lane) - 1u);    // run heads behind this lane
+      const int run_end = later ? (__ffs(later) - 2) : 31;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { const float w = corner_weight(q, c); v[2 * c] = w * gx; v[2 * c + 1] = w * gy; }
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const bool take = lane + off <= run_end;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float o = __shfl_down_sync(kFull, v[k], off);
+          if (take) v[k] += o;
+        }
+      }
+      issue = act && head;
+    }
+    float lx[3] = {0.f, 0.f, 0.f};
+    if (act) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t idx = entry_index(q.c[0] + (c & 1), q.c[1] + ((c >> 1) & 1), q.c[2] + (c >> 2), res, ent, dense);
+        if (agg) {
+          if (issue) atomicAdd(gt + idx, make_float2(v[2 * c], v[2 * c + 1]));
+        } else {
+          const float w = corner_weight(q, c);
+          atomicAdd(gt + idx, make_float2(w * gx, w * gy));
+        }
+        if (kDx) {
+          const float2 tv = __half22float2(__ldg(table + net.offset[l] + idx));
+          const float dot = tv.x * gx + tv.y * gy;
+          const float w0 = (c & 1) ? q.f[0] : 1.0f - q.f[0], w1 = (c & 2) ? q.f[1] : 1.0f - q.f[1],
+                      w2 = (c & 4) ? q.f[2] : 1.0f - q.f[2];
+          lx[0] += ((c & 1) ? 1.0f : -1.0f) * w1 * w2 * dot;
+          lx[1] += ((c & 2) ? 1.0f : -1.0f) * w0 * w2 * dot;
+          lx[2] += ((c & 4) ? 1.0f : -1.0f) * w0 * w1 * dot;
+        }
+      }
+      if (kDx) {
+#pragma unroll
+        for (int dd = 0; dd < 3; ++dd) dx[dd] = fmaf(net.scale[l], lx[dd], dx[dd]);
+      }
+    }
+  }
+  if (kDx && in) {
+#pragma unroll
+    for (int dd = 0; dd < 3; ++dd) a.d_pos[s * 3 + dd] = 0.5f * dx[dd];     // x = (pos + 1) / 2
+  }
+}
+
 template <bool kDx>
 __global__ void __launch_bounds__(kThreads, 2) hash_bwd_mma_kernel(const Args a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -580,76 +663,7 @@ __global__ void __launch_bounds__(kThreads, 2) hash_bwd_mma_kernel(const Args a)
       }
     }
     __syncwarp();
-    // ---- scatter into the gradient table, and d_pos through the interpolation weights.
-    // The COARSE levels are aggregated inside the warp first: the lanes of a warp are consecutive samples of one ray,
-    // so on a coarse level they sit in the same cell for long runs, and near the sensor origin EVERY ray of the
-    // keyframe hits the same few cells - up to 4 x 10^5 reductions per address and step, which the L2 serialises
-    // (measured: 6.5 ms on ray-ordered samples sharing an origin against 4.0 ms on independent positions).  Each
-    // maximal run of equal cells is summed with a segmented shuffle reduction and only its first lane issues the
-    // eight vector reductions.
-    float dx[3] = {0.f, 0.f, 0.f};
-    const bool act = in && ds != 0.f;
-#pragma unroll 2
-    for (int l = 0; l < net.n_levels; ++l) {
-      const Cell q = locate(net.scale[l], x);
-      const uint32_t res = net.res[l], ent = net.entries[l];
-      const bool dense = net.dense[l] != 0u;
-      float2* gt = reinterpret_cast<float2*>(a.d_table) + net.offset[l];
-      const float gx = act ? wt.denc[lane][2 * l] : 0.f, gy = act ? wt.denc[lane][2 * l + 1] : 0.f;
-      const bool agg = l < kAggLevels && res <= 1024u;          // warp-uniform
-      float v[16];
-      bool issue = act;
-      if (agg) {
-        const uint32_t key = act ? q.c[0] + res * (q.c[1] + res * q.c[2]) : 0xFFFFFFFFu;
-        const uint32_t prev = __shfl_up_sync(kFull, key, 1);
-        const bool head = lane == 0 || prev != key;
-        const uint32_t heads = __ballot_sync(kFull, head);
-        const uint32_t later = heads & ~((2u << lane) - 1u);    // run heads behind this lane
-        const int run_end = later ? (__ffs(later) - 2) : 31;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) { const float w = corner_weight(q, c); v[2 * c] = w * gx; v[2 * c + 1] = w * gy; }
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const bool take = lane + off <= run_end;
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const float o = __shfl_down_sync(kFull, v[k], off);
-            if (take) v[k] += o;
-          }
-        }
-        issue = act && head;
-      }
-      float lx[3] = {0.f, 0.f, 0.f};
-      if (act) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t idx = entry_index(q.c[0] + (c & 1), q.c[1] + ((c >> 1) & 1), q.c[2] + (c >> 2), res, ent, dense);
-          if (agg) {
-            if (issue) atomicAdd(gt + idx, make_float2(v[2 * c], v[2 * c + 1]));
-          } else {
-            const float w = corner_weight(q, c);
-            atomicAdd(gt + idx, make_float2(w * gx, w * gy));
-          }
-          if (kDx) {
-            const float2 tv = __half22float2(__ldg(table + net.offset[l] + idx));
-            const float dot = tv.x * gx + tv.y * gy;
-            const float w0 = (c & 1) ? q.f[0] : 1.0f - q.f[0], w1 = (c & 2) ? q.f[1] : 1.0f - q.f[1],
-                        w2 = (c & 4) ? q.f[2] : 1.0f - q.f[2];
-            lx[0] += ((c & 1) ? 1.0f : -1.0f) * w1 * w2 * dot;
-            lx[1] += ((c & 2) ? 1.0f : -1.0f) * w0 * w2 * dot;
-            lx[2] += ((c & 4) ? 1.0f : -1.0f) * w0 * w1 * dot;
-          }
-        }
-        if (kDx) {
-#pragma unroll
-          for (int dd = 0; dd < 3; ++dd) dx[dd] = fmaf(net.scale[l], lx[dd], dx[dd]);
-        }
-      }
-    }
-    if (kDx && in) {
-#pragma unroll
-      for (int dd = 0; dd < 3; ++dd) a.d_pos[s * 3 + dd] = 0.5f * dx[dd];     // x = (pos + 1) / 2
-    }
+    scatter_levels<kDx>(a, net, table, x, &wt.denc[lane][0], in, ds, lane, s);
     __syncthreads();
     // ---- dW1 [64 x 32] += dH^T [64 x 256] Enc [256 x 32] over the CTA tile: warp w owns C tiles (m = w >> 1, n = 2 (w & 1) + {0, 1})
     {
@@ -700,10 +714,348 @@ __global__ void __launch_bounds__(kThreads, 2) hash_bwd_mma_kernel(const Args a)
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Heads with 2 .. kMaxHidden hidden layers of 64 neurons (tcnn's FullyFusedMLP takes any n_hidden_layers; the shipped
+// yaml uses 1, which stays on the kernels above).  Same structure, with the extra 64 x 64 GEMMs chained in registers:
+// the C fragments of layer l (ReLU, fp16) ARE the A fragments of layer l + 1.  The backward keeps h_1 .. h_{L-1} of the
+// CTA's 256 samples in shared memory for the weight gradients, one ReLU mask word per layer and m-tile in a register,
+// and walks the layers down with a CTA-level dW_l GEMM per layer.
+constexpr int kWhLd = 72;           // halves per row of a hidden matrix [64][64 + 8]
+template <int kL>
+struct DeepTiles {
+  __align__(16) __half enc[32][kEncLd];
+  __align__(16) __half dh[32][kDhLd];             // dH_l of the layer being processed
+  __align__(16) __half h[kL - 1][32][kDhLd];      // h_1 .. h_{L-1}; h[kL-2] is dead after dW_L and then holds dEnc (fp32 [32][33])
+};
+template <int kL>
+struct DeepSmem {
+  __align__(16) __half w1[kW][kW1Ld];
+  __align__(16) __half wh[kL - 1][kW][kWhLd];
+  float wout[kW];
+  float red[8][kW];
+  DeepTiles<kL> wt[8];
+};
+
+template <int kL>
+__device__ __forceinline__ void load_weights_deep(const Args& a, DeepSmem<kL>& sm, int tid) {
+  const __half* w1 = reinterpret_cast<const __half*>(a.packed);
+  const int E = a.net.Epad;
+  for (int i = tid; i < kW * kW1Ld; i += kThreads) {
+    const int j = i / kW1Ld, k = i % kW1Ld;
+    sm.w1[j][k] = k < E ? w1[j * E + k] : __float2half_rn(0.f);
+  }
+  const __half* wh = w1 + w1_floats(a.net);
+  for (int i = tid; i < (kL - 1) * kW * kW; i += kThreads) {
+    const int l = i / (kW * kW), j = (i / kW) % kW, k = i % kW;
+    sm.wh[l][j][k] = wh[i];
+  }
+  const float* wo = reinterpret_cast<const float*>(a.packed + packed_wout_off(a.net));
+  for (int j = tid; j < kW; j += kThreads) sm.wout[j] = wo[j];
+}
+
+// first layer: pre-activations of 16 samples (m-tile mt) from the warp's encoding tile
+__device__ __forceinline__ void first_gemm(const __half (*w1)[kW1Ld], const __half (*enc)[kEncLd], int mt, int lane, float (&c)[8][4]) {
+  uint32_t a0[4], a1[4];
+  ldsm4(a0, &enc[mt * 16 + (lane & 15)][(lane >> 4) * 8]);
+  ldsm4(a1, &enc[mt * 16 + (lane & 15)][16 + (lane >> 4) * 8]);
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    uint32_t b[4];
+    ldsm4(b, &w1[nt * 8 + (lane & 7)][(lane >> 3) * 8]);
+    c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+    mma16816(c[nt], a0, b[0], b[1]);
+    mma16816(c[nt], a1, b[2], b[3]);
+  }
+}
+// hidden layer: c = hp [16 x 64] W^T, hp = the previous layer's activations as A fragments (C layout, packed half2)
+__device__ __forceinline__ void next_gemm(const __half (*W)[kWhLd], const uint32_t (&hp)[8][2], int lane, float (&c)[8][4]) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    uint32_t b0[4], b1[4];           // W[n][k], k contiguous: k 0-31 and 32-63
+    ldsm4(b0, &W[nt * 8 + (lane & 7)][(lane >> 3) * 8]);
+    ldsm4(b1, &W[nt * 8 + (lane & 7)][32 + (lane >> 3) * 8]);
+    c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+    const uint32_t a0[4] = {hp[0][0], hp[0][1], hp[1][0], hp[1][1]}, a1[4] = {hp[2][0], hp[2][1], hp[3][0], hp[3][1]};
+    const uint32_t a2[4] = {hp[4][0], hp[4][1], hp[5][0], hp[5][1]}, a3[4] = {hp[6][0], hp[6][1], hp[7][0], hp[7][1]};
+    mma16816(c[nt], a0, b0[0], b0[1]);
+    mma16816(c[nt], a1, b0[2], b0[3]);
+    mma16816(c[nt], a2, b1[0], b1[1]);
+    mma16816(c[nt], a3, b1[2], b1[3]);
+  }
+}
+// ReLU + fp16 rounding of a C tile: packed activations, and the mask word (bit 4 nt + e = element e of n-tile nt is active)
+__device__ __forceinline__ uint32_t relu_pack(const float (&c)[8][4], uint32_t (&hp)[8][2]) {
+  uint32_t m = 0u;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    hp[nt][0] = pack_h2(fmaxf(c[nt][0], 0.f), fmaxf(c[nt][1], 0.f));
+    hp[nt][1] = pack_h2(fmaxf(c[nt][2], 0.f), fmaxf(c[nt][3], 0.f));
+    // active = the ROUNDED activation is positive (what the backward of an fp16 network sees)
+    const __half2 lo = *reinterpret_cast<const __half2*>(&hp[nt][0]), hi = *reinterpret_cast<const __half2*>(&hp[nt][1]);
+    m |= (__low2float(lo) > 0.f ? 1u : 0u) << (4 * nt) | (__high2float(lo) > 0.f ? 2u : 0u) << (4 * nt) |
+         (__low2float(hi) > 0.f ? 4u : 0u) << (4 * nt) | (__high2float(hi) > 0.f ? 8u : 0u) << (4 * nt);
+  }
+  return m;
+}
+__device__ __forceinline__ float sat_h(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+
+template <int kL>
+__global__ void __launch_bounds__(kThreads, 1) hash_fwd_deep_kernel(const Args a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  DeepSmem<kL>& sm = *reinterpret_cast<DeepSmem<kL>*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  load_weights_deep<kL>(a, sm, tid);
+  __syncthreads();
+  DeepTiles<kL>& wt = sm.wt[warp];
+  const __half2* table = reinterpret_cast<const __half2*>(a.packed + packed_table_off(a.net));
+  const int64_t n_tiles = (a.P + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t s = tile * kThreads + tid;
+    float x[3] = {0.f, 0.f, 0.f};
+    if (s < a.P) position01(a, s, x);
+    __syncwarp();
+    encode_to_tile(a.net, table, x, &wt.enc[lane][0]);
+    __syncwarp();
+    const int64_t row0 = tile * kThreads + warp * 32;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float c[8][4];
+      first_gemm(sm.w1, wt.enc, mt, lane, c);
+#pragma unroll
+      for (int l = 2; l <= kL; ++l) {
+        uint32_t hp[8][2];
+        relu_pack(c, hp);
+        next_gemm(sm.wh[l - 2], hp, lane, c);
+      }
+      float s_lo = 0.f, s_hi = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float w0 = sm.wout[nt * 8 + 2 * t], w1 = sm.wout[nt * 8 + 2 * t + 1];
+        s_lo = fmaf(round_h(fmaxf(c[nt][0], 0.f)), w0, s_lo);
+        s_lo = fmaf(round_h(fmaxf(c[nt][1], 0.f)), w1, s_lo);
+        s_hi = fmaf(round_h(fmaxf(c[nt][2], 0.f)), w0, s_hi);
+        s_hi = fmaf(round_h(fmaxf(c[nt][3], 0.f)), w1, s_hi);
+      }
+      s_lo += __shfl_xor_sync(kFull, s_lo, 1); s_lo += __shfl_xor_sync(kFull, s_lo, 2);
+      s_hi += __shfl_xor_sync(kFull, s_hi, 1); s_hi += __shfl_xor_sync(kFull, s_hi, 2);
+      if (t == 0) {
+        const int64_t r_lo = row0 + mt * 16 + g, r_hi = r_lo + 8;
+        if (r_lo < a.P) a.sigma[r_lo] = s_lo;
+        if (r_hi < a.P) a.sigma[r_hi] = s_hi;
+      }
+    }
+  }
+}
+
+template <int kL, bool kDx>
+__global__ void __launch_bounds__(kThreads, 1) hash_bwd_deep_kernel(const Args a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  DeepSmem<kL>& sm = *reinterpret_cast<DeepSmem<kL>*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  load_weights_deep<kL>(a, sm, tid);
+  __syncthreads();
+  DeepTiles<kL>& wt = sm.wt[warp];
+  float (*denc)[kDencLd] = reinterpret_cast<float (*)[kDencLd]>(&wt.h[kL - 2][0][0]);
+  const HashNet& net = a.net;
+  const __half2* table = reinterpret_cast<const __half2*>(a.packed + packed_table_off(net));
+  const int mtile = warp >> 1, nhalf = warp & 1;      // this warp's C tiles of the CTA-level weight-gradient GEMMs
+  float accW[2][4];                                   // dW1: rows 16 mtile .., columns 16 nhalf + 8 i ..
+  float accH[kL - 1][4][4];                           // dW_l (l = 2 .. L): rows 16 mtile .., columns 32 nhalf + 8 i ..
+  float accOut[8][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) accW[i][0] = accW[i][1] = accW[i][2] = accW[i][3] = 0.f;
+#pragma unroll
+  for (int l = 0; l < kL - 1; ++l)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) accH[l][i][0] = accH[l][i][1] = accH[l][i][2] = accH[l][i][3] = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) accOut[nt][0] = accOut[nt][1] = 0.f;
+  const float inv_g = 1.0f / a.gscale;
+  const int64_t n_tiles = (a.P + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t s = tile * kThreads + tid;
+    const bool in = s < a.P;
+    float x[3] = {0.f, 0.f, 0.f};
+    if (in) position01(a, s, x);
+    encode_to_tile(net, table, x, &wt.enc[lane][0]);
+    const float ds = in ? __ldg(a.d_sigma + s) : 0.f;
+    __syncwarp();
+    // ---- forward recompute of both m-tiles: h_1 .. h_{L-1} to shared memory, their masks and dH_L to registers
+    uint32_t dhp[2][8][2];
+    uint32_t msk[2][kL - 1];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float c[8][4];
+      first_gemm(sm.w1, wt.enc, mt, lane, c);
+#pragma unroll
+      for (int l = 1; l < kL; ++l) {
+        uint32_t hp[8][2];
+        msk[mt][l - 1] = relu_pack(c, hp);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          *reinterpret_cast<uint32_t*>(&wt.h[l - 1][mt * 16 + g][nt * 8 + 2 * t]) = hp[nt][0];
+          *reinterpret_cast<uint32_t*>(&wt.h[l - 1][mt * 16 + g + 8][nt * 8 + 2 * t]) = hp[nt][1];
+        }
+        next_gemm(sm.wh[l - 1], hp, lane, c);
+      }
+      const float ds_lo = __shfl_sync(kFull, ds, mt * 16 + g), ds_hi = __shfl_sync(kFull, ds, mt * 16 + g + 8);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float w0 = sm.wout[nt * 8 + 2 * t], w1 = sm.wout[nt * 8 + 2 * t + 1];
+        const float h00 = round_h(fmaxf(c[nt][0], 0.f)), h01 = round_h(fmaxf(c[nt][1], 0.f));
+        const float h10 = round_h(fmaxf(c[nt][2], 0.f)), h11 = round_h(fmaxf(c[nt][3], 0.f));
+        accOut[nt][0] += ds_lo * h00 + ds_hi * h10;
+        accOut[nt][1] += ds_lo * h01 + ds_hi * h11;
+        const float k = a.gscale;
+        dhp[mt][nt][0] = pack_h2(h00 > 0.f ? sat_h(ds_lo * w0 * k) : 0.f, h01 > 0.f ? sat_h(ds_lo * w1 * k) : 0.f);
+        dhp[mt][nt][1] = pack_h2(h10 > 0.f ? sat_h(ds_hi * w0 * k) : 0.f, h11 > 0.f ? sat_h(ds_hi * w1 * k) : 0.f);
+      }
+    }
+    // ---- layers L .. 2: dW_l += dH_l^T h_{l-1} over the CTA's 256 samples, then dH_{l-1} = (dH_l W_l) * relu'(h_{l-1})
+#pragma unroll
+    for (int l = kL; l >= 2; --l) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          *reinterpret_cast<uint32_t*>(&wt.dh[mt * 16 + g][nt * 8 + 2 * t]) = dhp[mt][nt][0];
+          *reinterpret_cast<uint32_t*>(&wt.dh[mt * 16 + g + 8][nt * 8 + 2 * t]) = dhp[mt][nt][1];
+        }
+      __syncthreads();
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) {
+        const DeepTiles<kL>& o = sm.wt[w8];
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+          uint32_t af[4];
+          ldsm4t(af, &o.dh[kt * 16 + (lane & 7) + ((lane >> 4) & 1) * 8][mtile * 16 + ((lane >> 3) & 1) * 8]);
+#pragma unroll
+          for (int np = 0; np < 2; ++np) {
+            uint32_t bf[4];
+            ldsm4t(bf, &o.h[l - 2][kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][nhalf * 32 + np * 16 + ((lane >> 4) & 1) * 8]);
+            mma16816(accH[l - 2][2 * np], af, bf[0], bf[1]);
+            mma16816(accH[l - 2][2 * np + 1], af, bf[2], bf[3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        float d[8][4];
+#pragma unroll
+        for (int nf = 0; nf < 8; ++nf) d[nf][0] = d[nf][1] = d[nf][2] = d[nf][3] = 0.f;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+          const uint32_t a0[4] = {dhp[mt][4 * kp][0], dhp[mt][4 * kp][1], dhp[mt][4 * kp + 1][0], dhp[mt][4 * kp + 1][1]};
+          const uint32_t a1[4] = {dhp[mt][4 * kp + 2][0], dhp[mt][4 * kp + 2][1], dhp[mt][4 * kp + 3][0], dhp[mt][4 * kp + 3][1]};
+#pragma unroll
+          for (int nf = 0; nf < 8; ++nf) {
+            uint32_t b[4];                 // W_l[k = out][n = in], n contiguous -> transposed load
+            ldsm4t(b, &sm.wh[l - 2][32 * kp + lane][nf * 8]);
+            mma16816(d[nf], a0, b[0], b[1]);
+            mma16816(d[nf], a1, b[2], b[3]);
+          }
+        }
+        const uint32_t m = msk[mt][l - 2];
+#pragma unroll
+        for (int nf = 0; nf < 8; ++nf) {
+          dhp[mt][nf][0] = pack_h2((m >> (4 * nf)) & 1u ? sat_h(d[nf][0]) : 0.f, (m >> (4 * nf + 1)) & 1u ? sat_h(d[nf][1]) : 0.f);
+          dhp[mt][nf][1] = pack_h2((m >> (4 * nf + 2)) & 1u ? sat_h(d[nf][2]) : 0.f, (m >> (4 * nf + 3)) & 1u ? sat_h(d[nf][3]) : 0.f);
+        }
+      }
+      __syncthreads();                     // every warp is done with this layer's dh / h tiles
+    }
+    // ---- layer 1: dH_1 to shared memory, dEnc = dH_1 W1, scatter, dW1 (as in the one-layer kernel)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        *reinterpret_cast<uint32_t*>(&wt.dh[mt * 16 + g][nt * 8 + 2 * t]) = dhp[mt][nt][0];
+        *reinterpret_cast<uint32_t*>(&wt.dh[mt * 16 + g + 8][nt * 8 + 2 * t]) = dhp[mt][nt][1];
+      }
+      float d[4][4];
+#pragma unroll
+      for (int nf = 0; nf < 4; ++nf) d[nf][0] = d[nf][1] = d[nf][2] = d[nf][3] = 0.f;
+#pragma unroll
+      for (int kp = 0; kp < 2; ++kp) {
+        const uint32_t a0[4] = {dhp[mt][4 * kp][0], dhp[mt][4 * kp][1], dhp[mt][4 * kp + 1][0], dhp[mt][4 * kp + 1][1]};
+        const uint32_t a1[4] = {dhp[mt][4 * kp + 2][0], dhp[mt][4 * kp + 2][1], dhp[mt][4 * kp + 3][0], dhp[mt][4 * kp + 3][1]};
+#pragma unroll
+        for (int nf = 0; nf < 4; ++nf) {
+          uint32_t b[4];
+          ldsm4t(b, &sm.w1[32 * kp + lane][nf * 8]);
+          mma16816(d[nf], a0, b[0], b[1]);
+          mma16816(d[nf], a1, b[2], b[3]);
+        }
+      }
+#pragma unroll
+      for (int nf = 0; nf < 4; ++nf) {
+        denc[mt * 16 + g][nf * 8 + 2 * t] = d[nf][0] * inv_g;
+        denc[mt * 16 + g][nf * 8 + 2 * t + 1] = d[nf][1] * inv_g;
+        denc[mt * 16 + g + 8][nf * 8 + 2 * t] = d[nf][2] * inv_g;
+        denc[mt * 16 + g + 8][nf * 8 + 2 * t + 1] = d[nf][3] * inv_g;
+      }
+    }
+    __syncwarp();
+    scatter_levels<kDx>(a, net, table, x, &denc[lane][0], in, ds, lane, s);
+    __syncthreads();
+    {
+      const int npair = nhalf;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) {
+        const DeepTiles<kL>& o = sm.wt[w8];
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+          uint32_t af[4], bf[4];
+          ldsm4t(af, &o.dh[kt * 16 + (lane & 7) + ((lane >> 4) & 1) * 8][mtile * 16 + ((lane >> 3) & 1) * 8]);
+          ldsm4t(bf, &o.enc[kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][npair * 16 + ((lane >> 4) & 1) * 8]);
+          mma16816(accW[0], af, bf[0], bf[1]);
+          mma16816(accW[1], af, bf[2], bf[3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- per-CTA partials: dW1 [64][Epad] | dW_2 .. dW_L [64][64] (loss-scaled) | dW_out [64]
+  float* part = a.partials + (int64_t)blockIdx.x * (w1_floats(net) + wh_floats(net) + kW);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int col = nhalf * 16 + i * 8 + 2 * t;
+    const int r0 = mtile * 16 + g;
+    if (col < net.Epad) { part[r0 * net.Epad + col] = accW[i][0]; part[(r0 + 8) * net.Epad + col] = accW[i][2]; }
+    if (col + 1 < net.Epad) { part[r0 * net.Epad + col + 1] = accW[i][1]; part[(r0 + 8) * net.Epad + col + 1] = accW[i][3]; }
+  }
+#pragma unroll
+  for (int l = 0; l < kL - 1; ++l) {
+    float* ph = part + w1_floats(net) + (int64_t)l * kW * kW;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = nhalf * 32 + i * 8 + 2 * t;
+      const int r0 = mtile * 16 + g;
+      ph[r0 * kW + col] = accH[l][i][0]; ph[r0 * kW + col + 1] = accH[l][i][1];
+      ph[(r0 + 8) * kW + col] = accH[l][i][2]; ph[(r0 + 8) * kW + col + 1] = accH[l][i][3];
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float v = accOut[nt][j];
+      v += __shfl_xor_sync(kFull, v, 4); v += __shfl_xor_sync(kFull, v, 8); v += __shfl_xor_sync(kFull, v, 16);
+      if (g == 0) sm.red[warp][nt * 8 + 2 * t + j] = v;
+    }
+  __syncthreads();
+  if (tid < kW) {
+    float v = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) v += sm.red[w8][tid];
+    part[w1_floats(net) + wh_floats(net) + tid] = v;
+  }
+}
+
 // d_params[W1] += sum_b partials[b][W1] / gscale;  d_params[W_out row 0] += sum_b partials[b][W_out]
 __global__ void __launch_bounds__(256) hash_reduce_kernel(HashNet net, const float* __restrict__ partials, int n_blocks,
                                                          float inv_gscale, float* __restrict__ d_params) {
-  const int64_t nw1 = w1_floats(net), per = nw1 + kW;
+  const int64_t nw1 = w1_floats(net) + wh_floats(net), per = nw1 + kW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
     for (int b = 0; b < n_blocks; ++b) s += partials[(int64_t)b * per + i];
@@ -746,7 +1098,7 @@ extern "C" int64_t loner_hash_packed_bytes(const loner_hashnet_t* n) {
 extern "C" int64_t loner_hash_bwd_scratch_bytes(const loner_hashnet_t* n, int64_t P) {
   HashNet net;
   if (!net_from(n, net) || P < 0) return -1;
-  return (int64_t)bwd_blocks() * (w1_floats(net) + kW) * 4;
+  return (int64_t)bwd_blocks() * (w1_floats(net) + wh_floats(net) + kW) * 4;
 }
 
 extern "C" int loner_hash_pack(const loner_hashnet_t* n, const float* params, void* packed, void* stream) {
@@ -776,7 +1128,18 @@ extern "C" int loner_hash_fwd(const loner_hashnet_t* n, const void* packed, cons
   if (!sigma) return LONER_E_BAD_ARG;
   a.sigma = sigma;
   const int64_t want = (P + kThreads - 1) / kThreads;
-  if (a.net.flags & LONER_HASH_SCALAR) {
+  if (a.net.L > 1) {
+    const int64_t cap = sm_count();
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+#define LONER_HASH_FWD_DEEP(L_)                                                                           \
+  do {                                                                                                    \
+    const int smem = (int)sizeof(DeepSmem<L_>);                                                           \
+    cudaFuncSetAttribute(hash_fwd_deep_kernel<L_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);    \
+    hash_fwd_deep_kernel<L_><<<grid, kThreads, smem, (cudaStream_t)stream>>>(a);                          \
+  } while (0)
+    if (a.net.L == 2) LONER_HASH_FWD_DEEP(2); else if (a.net.L == 3) LONER_HASH_FWD_DEEP(3); else LONER_HASH_FWD_DEEP(4);
+#undef LONER_HASH_FWD_DEEP
+  } else if (a.net.flags & LONER_HASH_SCALAR) {
     const int64_t cap = (int64_t)sm_count() * 8;
     hash_fwd_kernel<<<(unsigned)(want < cap ? want : cap), kThreads, 0, (cudaStream_t)stream>>>(a);
   } else {
@@ -800,7 +1163,8 @@ extern "C" int loner_hash_bwd(const loner_hashnet_t* n, const void* packed, cons
   a.d_sigma = d_sigma; a.gscale = grad_scale; a.d_pos = d_pos; a.partials = (float*)scratch;
   a.d_table = d_params + net_floats(a.net);
   const int64_t tiles = (P + kThreads - 1) / kThreads;
-  const int blocks = (int)(tiles < bwd_blocks() ? tiles : bwd_blocks());
+  const int max_blocks = a.net.L > 1 ? sm_count() : bwd_blocks();     // the deep kernels hold one CTA per SM
+  const int blocks = (int)(tiles < max_blocks ? tiles : max_blocks);
   cudaStream_t st = (cudaStream_t)stream;
   const bool scalar = (a.net.flags & LONER_HASH_SCALAR) != 0;
   const int smem = scalar ? (int)sizeof(BwdSmem) : (int)sizeof(MmaSmem);
@@ -809,8 +1173,23 @@ extern "C" int loner_hash_bwd(const loner_hashnet_t* n, const void* packed, cons
     cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                  \
     K<<<blocks, kThreads, smem, st>>>(a);                                                        \
   } while (0)
-  if (scalar) { if (d_pos) LONER_HASH_BWD(hash_bwd_kernel<true>); else LONER_HASH_BWD(hash_bwd_kernel<false>); }
-  else        { if (d_pos) LONER_HASH_BWD(hash_bwd_mma_kernel<true>); else LONER_HASH_BWD(hash_bwd_mma_kernel<false>); }
+#define LONER_HASH_BWD_DEEP(L_)                                                                          \
+  do {                                                                                                   \
+    const int dsmem = (int)sizeof(DeepSmem<L_>);                                                         \
+    if (d_pos) {                                                                                         \
+      cudaFuncSetAttribute(hash_bwd_deep_kernel<L_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsmem);  \
+      hash_bwd_deep_kernel<L_, true><<<blocks, kThreads, dsmem, st>>>(a);                                \
+    } else {                                                                                             \
+      cudaFuncSetAttribute(hash_bwd_deep_kernel<L_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dsmem); \
+      hash_bwd_deep_kernel<L_, false><<<blocks, kThreads, dsmem, st>>>(a);                               \
+    }                                                                                                    \
+  } while (0)
+  if (a.net.L == 2) LONER_HASH_BWD_DEEP(2);
+  else if (a.net.L == 3) LONER_HASH_BWD_DEEP(3);
+  else if (a.net.L == 4) LONER_HASH_BWD_DEEP(4);
+  else if (scalar) { if (d_pos) LONER_HASH_BWD(hash_bwd_kernel<true>); else LONER_HASH_BWD(hash_bwd_kernel<false>); }
+  else             { if (d_pos) LONER_HASH_BWD(hash_bwd_mma_kernel<true>); else LONER_HASH_BWD(hash_bwd_mma_kernel<false>); }
+#undef LONER_HASH_BWD_DEEP
 #undef LONER_HASH_BWD
   LONER_CHECK_LAUNCH();
   hash_reduce_kernel<<<16, 256, 0, st>>>(a.net, a.partials, blocks, 1.0f / grad_scale, d_params);

@@ -1,6 +1,7 @@
 """models.nerf_tcnn of the reference (/root/reference/src/models/nerf_tcnn.py): DecoupledNeRF with the
 sigma head on the hand-written sm_100a kernels: Frequency + MLP on the tensor cores (loner_mlp_fwd /
-loner_mlp_bwd) or the shipped HashGrid + 1 x 64 configuration (loner_hash_fwd / loner_hash_bwd).  Driven by
+loner_mlp_bwd) or the shipped HashGrid + 1 x 64 configuration and its 2-4 x 64 variants (loner_hash_fwd /
+loner_hash_bwd).  Driven by
 the same `nerf_config` keys (nerf_tcnn.py:29-33).  The intensity head exists only as frozen empty modules:
 the reference never enables the camera (mapping/optimizer.py:433-434)."""
 import torch

@@ -57,7 +57,7 @@ class Net:
 class HashNet:
     """The reference's shipped sigma head: multiresolution hash encoding + 1 x 64 MLP
     (cfg/nerf_config/default_nerf_hash.yaml `pos_encoding_sigma` / `sigma_network`, models/nerf_tcnn.py:35-38).
-    Flat fp32 params in tcnn's order: W1 [64, e_pad] | W_out [16, 64] | table [entries, 2]."""
+    Flat fp32 params in tcnn's order: W1 [64, e_pad] | W_2 .. W_L [64, 64] | W_out [16, 64] | table [entries, 2]."""
 
     def __init__(self, n_levels=16, n_features_per_level=2, log2_hashmap_size=18, base_resolution=16,
                  per_level_scale=2.0, n_neurons=64, n_hidden_layers=1, flags=0):
@@ -70,12 +70,12 @@ class HashNet:
         if self.param_count < 0:
             raise RuntimeError(f"unsupported hash-grid sigma network {n_levels=} {n_features_per_level=} "
                                f"{log2_hashmap_size=} {n_neurons=} {n_hidden_layers=} (kernels implement <=16 levels "
-                               "x 2 features, one hidden layer of 64 neurons)")
+                               "x 2 features, 1-4 hidden layers of 64 neurons)")
         self.n_levels, self.n_neurons, self.n_hidden_layers = int(n_levels), int(n_neurons), int(n_hidden_layers)
         self.e_pad = (2 * self.n_levels + 15) // 16 * 16
         self.table_entries = lib.loner_hash_table_entries(ctypes.byref(self.c))
         self.packed_bytes = lib.loner_hash_packed_bytes(ctypes.byref(self.c))
-        self.n_network_params = self.n_neurons * self.e_pad + 16 * self.n_neurons
+        self.n_network_params = sum(o * i for o, i in self.layer_shapes())
 
     def ref(self):
         return ctypes.byref(self.c)
@@ -84,7 +84,8 @@ class HashNet:
         return L.load().loner_hash_bwd_scratch_bytes(self.ref(), P)
 
     def layer_shapes(self):
-        return [(self.n_neurons, self.e_pad), (16, self.n_neurons)]
+        return ([(self.n_neurons, self.e_pad)] + [(self.n_neurons, self.n_neurons)] * (self.n_hidden_layers - 1) +
+                [(16, self.n_neurons)])
 
 
 def hash_pack(net: HashNet, params, packed=None):

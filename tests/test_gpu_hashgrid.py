@@ -98,6 +98,92 @@ def test_hash_backward_matches_autograd(name, flags):
     assert norm_relerr(d_params2[net.n_network_params:], d_params[net.n_network_params:]) < 1e-5
 
 
+def _setup_deep(cfg, L, P, seed=0):
+    hs = H.HashGridSpec(**cfg)
+    spec = orc.NetSpec(n_neurons=64, n_hidden_layers=L, precision="fp16", hash=hs)
+    net = ops.HashNet(n_levels=hs.n_levels, log2_hashmap_size=hs.log2_hashmap_size, base_resolution=hs.base_resolution,
+                      per_level_scale=hs.per_level_scale, n_hidden_layers=L)
+    assert net.layer_shapes() == spec.shapes and net.param_count == spec.n_params
+    g = torch.Generator().manual_seed(seed)
+    w = tcnn_standin.xavier_uniform_flat(spec.shapes, 1337) * 1.5
+    table = (torch.rand(hs.n_params, generator=g) - 0.5)
+    pos = torch.rand(P, 3, generator=g) * 1.9 - 0.95
+    return hs, spec, net, torch.cat([w, table]), pos
+
+
+@pytest.mark.parametrize("L", [2, 3, 4])
+@pytest.mark.parametrize("name", ["shipped", "odd"])
+def test_hash_deep_heads_match_oracle(name, L):
+    """HashGrid + L x 64 heads (tcnn FullyFusedMLP takes any n_hidden_layers; the shipped yaml uses 1): forward and
+    every gradient against the oracle's autograd.  P is not a multiple of the CTA tile and spans several tiles."""
+    hs, spec, net, params, pos = _setup_deep(CONFIGS[name], L, 256 * 5 + 77, seed=11)
+    P = pos.shape[0]
+    g = torch.Generator().manual_seed(9)
+    d_sigma = torch.randn(P, generator=g) * 1e-3
+    p_ref = params.clone().requires_grad_(True)
+    pos_ref = pos.clone().requires_grad_(True)
+    ref = orc.sigma_net(pos_ref, p_ref, spec)
+    (ref * d_sigma).sum().backward()
+    packed = ops.hash_pack(net, params.to(DEV))
+    posd = pos.to(DEV).contiguous()
+    sigma = ops.hash_fwd(net, packed, P, pos=posd)
+    e = norm_relerr(sigma, ref.detach())
+    print(f"[hash {L}x64 {name}] sigma norm-rel err {e:.2e}")
+    assert e < 3e-3
+    d_params = torch.zeros(net.param_count, device=DEV)
+    d_pos = ops.hash_bwd(net, packed, P, d_sigma.to(DEV), 2.0 ** 10, d_params, pos=posd, want_dpos=True)
+    torch.cuda.synchronize()
+    off, parts = 0, {}
+    for i, (o, k) in enumerate(spec.shapes):
+        parts[f"dW{i + 1}" if i < L else "dW_out"] = (off, off + (o * k if i < L else 64))
+        off += o * k
+    parts["d_table"] = (net.n_network_params, net.param_count)
+    for k, (a, b) in parts.items():
+        e = norm_relerr(d_params[a:b], p_ref.grad[a:b])
+        print(f"[hash {L}x64 {name}] {k} norm-rel err {e:.2e} (|ref| {float(p_ref.grad[a:b].norm()):.3e})")
+        assert e < 5e-3
+    e = norm_relerr(d_pos, pos_ref.grad)
+    print(f"[hash {L}x64 {name}] d_pos norm-rel err {e:.2e}")
+    assert e < 3e-2
+    d_params2 = torch.zeros(net.param_count, device=DEV)
+    assert ops.hash_bwd(net, packed, P, d_sigma.to(DEV), 2.0 ** 10, d_params2, pos=posd) is None
+    assert torch.equal(d_params2[:net.n_network_params], d_params[:net.n_network_params])
+
+
+def test_hash_deep_head_in_the_engine_step():
+    """A mapping iteration with HashGrid + 2 x 64 through MappingEngine against the oracle's iteration."""
+    from golden_util import Case
+    from gpu_util import relerr
+    from loner_b200 import engine as eng
+    c = Case("hash_1x64_fp16")
+    hs = c.hash_spec
+    spec = orc.NetSpec(n_neurons=64, n_hidden_layers=2, precision="fp16", hash=hs)
+    g = torch.Generator().manual_seed(2)
+    params = torch.cat([tcnn_standin.xavier_uniform_flat(spec.shapes, 7), (torch.rand(hs.n_params, generator=g) - 0.5) * 0.2])
+    cfg = eng.EngineConfig(scale=c.scale, shift=tuple(c.shift.tolist()), ray_range=c.ray_range, encoding="HashGrid",
+                           n_levels=hs.n_levels, log2_hashmap_size=hs.log2_hashmap_size,
+                           base_resolution=hs.base_resolution, per_level_scale=hs.per_level_scale,
+                           n_neurons=64, n_hidden_layers=2, n_samples=c.S, sampler="OGM")
+    e = eng.MappingEngine(cfg, params=params)
+    e.grid.copy_(c.grid[0, 0])
+    for k in range(c.K):
+        e.add_keyframe(c.scans[k].ray_directions, c.scans[k].distances, c.poses6[k])
+    e.new_phase(optimize_poses=False)
+    ray_point = torch.cat([c.idx[k] + e.kf_offsets[k] for k in range(c.K)])
+    loss = e.step(list(range(c.K)), c.n, injected=dict(ray_point=ray_point, u1=c.u1, u2=c.u2, noise=c.noise),
+                  want_outputs=True)
+    p_ref = params.clone().requires_grad_(True)
+    _, _, res, out = orc.mapping_iteration(c.scans, c.poses6, c.idx, p_ref, spec, c.grid, c.S, c.scale, c.shift,
+                                           c.ray_range, 1.0, c.u1, c.u2, c.noise, c.loss_cfg, sampler=c.sampler)
+    out["loss"].backward()
+    depth = torch.cat([o["depth"] for o in e.last["outs"]]).cpu()
+    errs = dict(depth=relerr(depth, res["depth_fine"].detach()),
+                loss=abs(float(loss) - float(out["loss"])) / abs(float(out["loss"])),
+                d_net=norm_relerr(e.d_params[:spec.n_network_params], p_ref.grad[:spec.n_network_params]))
+    print("[hash 2x64 step]", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["depth"] < 1e-4 and errs["loss"] < 1e-4 and errs["d_net"] < 5e-3
+
+
 def test_hash_empty_and_unsupported():
     net = ops.HashNet()
     packed = torch.zeros(net.packed_bytes, dtype=torch.uint8, device=DEV)

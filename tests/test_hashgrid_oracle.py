@@ -75,7 +75,13 @@ def test_library_level_table_matches_the_oracle():
         assert net.param_count == spec.n_params
         assert net.e_pad == spec.e_pad
         assert net.layer_shapes() == spec.shapes
-    for bad in (dict(n_neurons=128), dict(n_hidden_layers=2), dict(n_features_per_level=4), dict(n_levels=17)):
+        for L in (2, 3, 4):                      # deeper 64-wide heads
+            deep = ops.HashNet(n_levels=hs.n_levels, log2_hashmap_size=hs.log2_hashmap_size,
+                               base_resolution=hs.base_resolution, per_level_scale=hs.per_level_scale, n_hidden_layers=L)
+            dspec = orc.NetSpec(n_neurons=64, n_hidden_layers=L, hash=hs)
+            assert deep.param_count == dspec.n_params and deep.layer_shapes() == dspec.shapes
+    for bad in (dict(n_neurons=128), dict(n_hidden_layers=5), dict(n_hidden_layers=2, flags=ops.HASH_SCALAR),
+                dict(n_features_per_level=4), dict(n_levels=17)):
         try:
             ops.HashNet(**bad)
         except RuntimeError:
