@@ -726,9 +726,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
     };
     auto load_ds = [&](int64_t tile) {
       const int64_t gs = tile * kTile + row;
-      return (tile < a.tiles && gs < a.P) ? ldg_now(a.d_sigma + gs) * a.gscale : 0.f;
+      return (tile < a.tiles && gs < a.P) ? ldg_now(a.d_sigma + gs) : 0.f;     // unscaled: nothing consumes the load here
     };
-    uint32_t mw[2][kMw];      // masks of the NEXT step of each tile, fetched one step ahead
+    // Masks (and d_sigma) of the NEXT step of each tile are fetched one step ahead, and AFTER the step's hand-off: the
+    // loop-carried copy of a prefetched register waits for its load (ncu: 32 % of this kernel's stall samples sat on
+    // those MOVs and on the d_sigma multiply, in front of the a_ready arrive - a memory latency on the
+    // epilogue -> MMA -> epilogue chain of every step).
+    uint32_t mw[2][kMw];
     float ds[2];
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
@@ -751,6 +755,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
         const uint32_t srow = stile + row * 128;
         if (want_dx && h == 0) rin[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, in ? gs : a.P - 1);
         // dZ_L = d_sigma * w_out * relu'(Z_L)
+        const float dsv = ds[t] * a.gscale;
 #pragma unroll
         for (int it = 0; it < kMw; ++it) {
           const uint32_t bits = mw[t][it];
@@ -759,18 +764,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
 #define LONER_DZL(P)                                                                        \
   {                                                                                         \
     const float2 w2 = *reinterpret_cast<const float2*>(sm.wout() + col0 + 2 * P);           \
-    hh[P] = cvt_sat_h2(ds[t] * w2.x, ds[t] * w2.y) & half2_mask<P>(bits);                   \
+    hh[P] = cvt_sat_h2(dsv * w2.x, dsv * w2.y) & half2_mask<P>(bits);                       \
   }
           LONER_DZL(0) LONER_DZL(1) LONER_DZL(2) LONER_DZL(3) LONER_DZL(4) LONER_DZL(5) LONER_DZL(6) LONER_DZL(7)
           LONER_DZL(8) LONER_DZL(9) LONER_DZL(10) LONER_DZL(11) LONER_DZL(12) LONER_DZL(13) LONER_DZL(14) LONER_DZL(15)
 #undef LONER_DZL
           store32(srow, xs, col0, hh);
-        }
-        if (net.L >= 2) {
-          load_masks(tile, net.L - 2, mw[t]);      // for step (t, L-1)
-        } else if (!want_dx) {                     // single hidden layer, no GEMM steps: next pair's first step
-          load_masks(tile + next_tile, net.L - 1, mw[t]);
-          ds[t] = load_ds(tile + next_tile);
         }
         fence_async_smem();
         if (elected) bulk_wait_read0();
@@ -779,6 +778,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
         if (a.stash_last && elected && active) {
           bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(net.L - 1) * kNb * kBlk, stile, (uint32_t)(kNb * kBlk));
           bulk_commit();
+        }
+        if (net.L >= 2) {
+          load_masks(tile, net.L - 2, mw[t]);      // for step (t, L-1)
+        } else if (!want_dx) {                     // single hidden layer, no GEMM steps: next pair's first step
+          load_masks(tile + next_tile, net.L - 1, mw[t]);
+          ds[t] = load_ds(tile + next_tile);
         }
       }
       for (int l = net.L - 1; l >= l_lo; --l) {
@@ -804,13 +809,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
               store32(srow, xs, h * kCols + i * 32, v);
             });
             tc_fence_before();
-            // masks (and d_sigma) of this tile's next step: layer l-2 of this pair, or the first step of the next pair
-            if (l >= 2) {
-              load_masks(tile, l - 2, mw[t]);
-            } else if (!want_dx) {
-              load_masks(tile + next_tile, net.L - 1, mw[t]);
-              ds[t] = load_ds(tile + next_tile);
-            }
             fence_async_smem();
             if (elected) bulk_wait_read0();
             if (feeds_gemm) arrive_a<kCtas>(a_rdy[t], lane);
@@ -818,6 +816,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
             if (elected && active) {
               bulk_s2g(a.dz + tile * dz_tile_bytes(net) + (int64_t)(l - 1) * kNb * kBlk, stile, (uint32_t)(kNb * kBlk));
               bulk_commit();
+            }
+            // masks (and d_sigma) of this tile's next step: layer l-2 of this pair, or the first step of the next pair
+            if (l >= 2) {
+              load_masks(tile, l - 2, mw[t]);
+            } else if (!want_dx) {
+              load_masks(tile + next_tile, net.L - 1, mw[t]);
+              ds[t] = load_ds(tile + next_tile);
             }
           } else {
             // l == 0: dEnc [128 x Epad] -> d_pos through the sin/cos encoding (lower-half warps only)
