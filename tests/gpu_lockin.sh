@@ -16,7 +16,9 @@ tail -3 gpurun_out/${tag}_pytest.log
 (timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_hashgrid.py tests/test_gpu_round2.py -q \
    -k "deep_heads or pose or sky or occupancy" > gpurun_out/${tag}_sanitizer.log 2>&1; echo "memcheck rc=$?" >> gpurun_out/${tag}_sanitizer.log
  timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_hashgrid.py -q \
-   -k "deep_heads and odd" >> gpurun_out/${tag}_sanitizer.log 2>&1; echo "racecheck rc=$?" >> gpurun_out/${tag}_sanitizer.log)
+   -k "deep_heads and odd" >> gpurun_out/${tag}_sanitizer.log 2>&1; echo "racecheck rc=$?" >> gpurun_out/${tag}_sanitizer.log
+ timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py -q \
+   -k "mlp_backward and 128-2-640 or mlp_forward_layers and 256-4-1000" >> gpurun_out/${tag}_sanitizer.log 2>&1; echo "memcheck (tcgen05 kernels) rc=$?" >> gpurun_out/${tag}_sanitizer.log)
 grep -E "rc=|ERROR SUMMARY|RACECHECK SUMMARY|passed|failed" gpurun_out/${tag}_sanitizer.log | tail -8
 (timeout 200 python tests/gpu_probe_l2.py > gpurun_out/${tag}_probe_l2.json 2>&1; timeout 200 python tests/gpu_probe_store.py > gpurun_out/${tag}_probe_bulk_store.txt 2>&1; timeout 200 python tests/gpu_hash_hotspot.py > gpurun_out/${tag}_hash_hotspot.json 2>&1)
 # launch list of a short bench run (every launch with its device time; shares, not absolutes)
