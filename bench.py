@@ -193,7 +193,8 @@ def build_engine(wl, device, seed, world=1):
     wc = synth.world_cube(wl["geom"])
     cfg = eng.EngineConfig(scale=wc.scale_factor, shift=wc.shift, ray_range=synth.GEOMETRY[wl["geom"]]["ray_range"],
                            n_frequencies=10, n_neurons=wl["W"], n_hidden_layers=wl["L"], n_samples=wl["S"],
-                           sampler="OGM", seed=seed, encoding=wl.get("encoding", "Frequency"))
+                           sampler="OGM", seed=seed, encoding=wl.get("encoding", "Frequency"),
+                           net_flags=wl.get("net_flags"))      # kernel A/B variants (tests/gpu_hash_agg.py); None = production
     e = eng.MappingEngine(cfg, device=device)
     scans, poses = synth.make_window(wl["geom"], wl["K"], seed=0)
     for k in range(wl["K"]):

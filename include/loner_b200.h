@@ -142,6 +142,8 @@ typedef struct {
 } loner_hashnet_t;
 /* the head (32 -> 64 -> 1) on scalar CUDA-core code instead of mma.sync tiles (round 1's kernels) */
 #define LONER_HASH_SCALAR 1
+/* number of coarse levels whose table reductions are aggregated per warp run (0 = built-in default; A/B) */
+#define LONER_HASH_AGG_LEVELS(n) (((n) & 0xF) << 4)
 
 int64_t loner_hash_param_count(const loner_hashnet_t* net);
 int64_t loner_hash_table_entries(const loner_hashnet_t* net);

@@ -389,7 +389,8 @@ constexpr int kEncLd = 40;          // halves per row of the per-warp encoding t
 constexpr int kDhLd = 72;           // halves per row of the per-warp dH tile (64 + 8)
 constexpr int kDencLd = 33;         // floats per row of the per-warp dEnc tile
 constexpr int kW1Ld = 40;           // halves per row of W1 [64][32 + 8]
-constexpr int kAggLevels = 4;       // coarse levels whose table reductions are aggregated inside the warp
+constexpr int kAggLevels = 4;       // coarse levels whose table reductions are aggregated inside the warp (sweep on a B200, backward ms
+                                    // at the C2 size / default operating point: 2 levels 3.65 / 2.27, 4: 3.37 / 2.04, 5: 3.36 / 2.04, 6: 3.40 / 2.04, 8: 3.31 / 2.04)
 struct WarpTiles {
   __align__(16) __half enc[32][kEncLd];      // 2560 B
   __align__(16) __half dh[32][kDhLd];        // 4608 B
@@ -524,6 +525,7 @@ __device__ __forceinline__ void scatter_levels(const Args& a, const HashNet& net
   // eight vector reductions.
   float dx[3] = {0.f, 0.f, 0.f};
   const bool act = in && ds != 0.f;
+  const int n_agg = ((net.flags >> 4) & 0xF) ? ((net.flags >> 4) & 0xF) : kAggLevels;   // LONER_HASH_AGG_LEVELS(n), A/B
 #pragma unroll 2
   for (int l = 0; l < net.n_levels; ++l) {
     const Cell q = locate(net.scale[l], x);
@@ -531,7 +533,7 @@ __device__ __forceinline__ void scatter_levels(const Args& a, const HashNet& net
     const bool dense = net.dense[l] != 0u;
     float2* gt = reinterpret_cast<float2*>(a.d_table) + net.offset[l];
     const float gx = act ? denc_row[2 * l] : 0.f, gy = act ? denc_row[2 * l + 1] : 0.f;
-    const bool agg = l < kAggLevels && res <= 1024u;          // warp-uniform
+    const bool agg = l < n_agg && res <= 1024u;               // warp-uniform
     float v[16];
     bool issue = act;
     if (agg) {

@@ -108,7 +108,7 @@ class MappingEngine:
         self.hash = cfg.encoding == "HashGrid"
         if self.hash:
             self.net = ops.HashNet(cfg.n_levels, 2, cfg.log2_hashmap_size, cfg.base_resolution, cfg.per_level_scale,
-                                   cfg.n_neurons, cfg.n_hidden_layers)
+                                   cfg.n_neurons, cfg.n_hidden_layers, flags=cfg.net_flags or 0)
         else:
             self.net = ops.Net(cfg.n_frequencies, cfg.n_neurons, cfg.n_hidden_layers, flags=cfg.net_flags)
         if params is None:
