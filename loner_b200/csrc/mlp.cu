@@ -116,13 +116,17 @@ __global__ void pack_kernel(Net net, const float* __restrict__ params, uint8_t* 
 //    (tests/gpu_probe.py: 8 warps reach 99 / 140 B/clk with one / two 4 KB loads in flight);
 //  * no local memory at all (tables are address computations or live in shared memory): behind a
 //    saturated HBM a local load misses the 28 KB L1 and stalls its warp for microseconds;
-//  * the weight chunks are fetched once per TILE (LONER_MMA_ORDER=pair shares them between the tiles of
-//    a pair: X[c0,c1] Y[c0,c1] X[c2,c3] Y[c2,c3]; half the L2->SM traffic, but then a tile's epilogue
-//    overlaps only a quarter of the other tile's tensor work - slower in training, equal in inference);
-//  * what bounds the kernels now is the shared-memory data pipe: per tile and layer the tensor core
-//    reads 192 KB of operands (ncu: l1tex__data_pipe_tc_wavefronts), the epilogue stores 64 KB, the
-//    weight ring receives 128 KB and the stash copy reads 64 KB - 448 KB against 2048 tensor clocks.
-//    The next step is cta_group::2 (each SM holds half of B): -64 KB operands, -64 KB ring per tile-layer.
+//  * the weight chunks are fetched once per TILE (sharing them between the tiles of a pair - issue order
+//    X[c0,c1] Y[c0,c1] X[c2,c3] Y[c2,c3] - halves the L2->SM traffic, but then a tile's epilogue overlaps only a
+//    quarter of the other tile's tensor work: measured slower in training, equal in inference, round 1);
+//  * as CTA PAIRS (cta_group::2, kCtas = 2: training forward and dgrad) each SM stages half of every weight
+//    chunk and one M = 256 MMA covers a tile of each CTA: -64 KB of operand reads and -64 KB of ring writes per
+//    tile and layer in each SM's shared-memory pipe, half the weight re-streaming through the L2 fabric;
+//  * what bounds the kernels (profiles/README.md): all run at 3200 - 3400 clk per tile and
+//    layer against 2048 nominal tensor clocks - the inference forward on the per-SM L2->SM ingest of its weight
+//    re-streaming (9.7 TB/s over 148 SMs), the training forward / dgrad on the L2 fabric ceiling for stash writes
+//    next to weight loads (5.1 TB/s, tests/gpu_probe_store.py).  16 epilogue warps were tried and changed nothing
+//    (profiles/experiments/r2_epilogue16.md).
 constexpr int kPipeThreads = 320;
 constexpr int kGroupThreads = 256;
 constexpr int kRingBytes = 98304;                    // weight ring: 3 x 32 KB (one CTA) or 6 x 16 KB (CTA pair)
