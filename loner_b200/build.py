@@ -61,5 +61,16 @@ def build_probe():
     return out
 
 
+def build_trace():
+    """mlp.cu with -DLONER_TRACE (timeline instrumentation of the pipelined kernels, tests/gpu_trace.py) as a
+    separate probe library; NOT part of the product library."""
+    d = os.path.join(HERE, "..", "tests", "probes")
+    src = os.path.join(CSRC, "mlp.cu")
+    out = os.path.join(d, "libloner_trace.so")
+    if not os.path.exists(out) or os.path.getmtime(src) > os.path.getmtime(out):
+        subprocess.check_call([NVCC] + [f for f in FLAGS if f not in ("-Xptxas", "-v")] + ["-DLONER_TRACE", "-shared", src, "-o", out, "-lcudart"])
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -22,6 +22,36 @@ namespace mlp {
 
 using namespace sm100;
 
+// ---- timeline instrumentation of the pipelined kernels.  Compiled ONLY into tests/probes/libloner_trace.so
+// (-DLONER_TRACE, loner_b200.build.build_trace): one thread per role of CTAs 0 and 1 stores (tag, clock64) pairs into
+// its own slice of a buffer set with loner_trace_setup; the product library contains none of this.
+#ifdef LONER_TRACE
+__device__ unsigned long long* g_trace_buf = nullptr;     // [2 CTAs][4 roles][cap][2]
+__device__ unsigned int g_trace_cap = 0;
+struct Trace {
+  unsigned long long* p = nullptr;
+  unsigned int n = 0, cap = 0;
+  __device__ __forceinline__ void open(int role) {
+    if (blockIdx.x < 2 && g_trace_buf != nullptr) {
+      cap = g_trace_cap;
+      p = g_trace_buf + ((size_t)(blockIdx.x * 4 + role) * cap) * 2;
+    }
+  }
+  __device__ __forceinline__ void ev(unsigned event, unsigned unit, unsigned layer, unsigned tile, unsigned extra = 0) {
+    if (p != nullptr && n < cap) {
+      p[2 * n] = ((unsigned long long)event << 48) | ((unsigned long long)unit << 32) | (layer << 16) | (tile << 8) | extra;
+      p[2 * n + 1] = (unsigned long long)clock64();
+      ++n;
+    }
+  }
+};
+#define LONER_TRACE_OPEN(tr, role) Trace tr; tr.open(role)
+#define LONER_TRACE_EV(tr, ...) tr.ev(__VA_ARGS__)
+#else
+#define LONER_TRACE_OPEN(tr, role)
+#define LONER_TRACE_EV(tr, ...)
+#endif
+
 constexpr int kTile = 128;            // samples per tile = UMMA M
 constexpr int kBlk = 16384;           // bytes of one [128 x 64] fp16 column block
 
@@ -434,6 +464,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
     // ---------------- producer (whole warp, converged): one contiguous bulk copy per 64-row weight chunk
     const uint8_t* fimg = a.packed + packed_fwd_base(net) + units.rank * kMyBytes;
     uint32_t g = 0;
+    LONER_TRACE_OPEN(tr, 3);
     for (int64_t u = units.first; u < units.count; u += units.stride) {
       for (int l = 0; l < net.L; ++l) {
         const int nch = (l == 0) ? 1 : kNb;
@@ -441,6 +472,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
           for (int c = 0; c < nch; ++c, ++g) {
             const uint32_t slot = g % nslots, use = g / nslots;
             if (use > 0) mbar_wait_warp(sm.w_empty(slot), (use - 1) & 1);
+            if (lane == 0) LONER_TRACE_EV(tr, 0, (unsigned)((u - units.first) / units.stride), l, t, c);      // chunk load issued
             mbar_expect_tx_warp(sm.w_full(slot), kMyBytes);
             bulk_g2s_warp(sm.ring(slot), fimg + fwd_off(net, l) + (int64_t)c * kChunkBytes, kMyBytes, sm.w_full(slot));
           }
@@ -451,18 +483,22 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
     // ---------------- MMA issuer (whole warp, converged; one lane is elected inside each asm statement)
     constexpr uint32_t idesc = make_idesc_f16(128 * kCtas, W, 0, 1);
     uint32_t g = 0, par_a = 0u;
+    LONER_TRACE_OPEN(tr, 0);
     for (int64_t u = units.first; u < units.count; u += units.stride) {
       for (int l = 0; l < net.L; ++l) {
         const int nch = (l == 0) ? 1 : kNb;
         const int ksteps0 = (l == 0) ? net.Epad / 16 : 4;   // layer 0 contracts over Epad (<= 64) features
         for (int t = 0; t < 2; ++t) {
+          if (lane == 0) LONER_TRACE_EV(tr, 0, (unsigned)((u - units.first) / units.stride), l, t);           // waits for A
           mbar_wait_warp(sm.a_ready(t), par_a);
           tc_fence_after();
+          if (lane == 0) LONER_TRACE_EV(tr, 1, (unsigned)((u - units.first) / units.stride), l, t);           // A is ready
           for (int c = 0; c < nch; ++c, ++g) {
             const uint32_t slot = g % nslots, par_w = (g / nslots) & 1;
             mbar_wait_warp(sm.w_full(slot), par_w);
             if (kCtas == 2) mbar_wait_warp(sm.w_peer(slot), par_w);
             tc_fence_after();
+            if (lane == 0) LONER_TRACE_EV(tr, 2, (unsigned)((u - units.first) / units.stride), l, t, c);      // chunk c has landed
             const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
             if (ksteps0 == 4) {
               if (kCtas == 2)
@@ -480,8 +516,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
               }
               if (kCtas == 2) umma2_commit_warp(sm.w_empty(slot)); else umma_commit_warp(sm.w_empty(slot));
             }
+            if (lane == 0) LONER_TRACE_EV(tr, 4, (unsigned)((u - units.first) / units.stride), l, t, c);      // chunk c's MMAs issued
           }
           if (kCtas == 2) umma2_commit_warp(sm.acc_full(t)); else umma_commit_warp(sm.acc_full(t));
+          if (lane == 0) LONER_TRACE_EV(tr, 3, (unsigned)((u - units.first) / units.stride), l, t);           // all MMAs of the tile-step issued
         }
         par_a ^= 1u;
       }
@@ -523,6 +561,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
       return gs < a.P ? gs : a.P - 1;
     };
     RowIn nxt[2];
+    LONER_TRACE_OPEN(tr, e == 0 ? 1 : 2);     // first and (below) last epilogue warp
 #pragma unroll
     for (int t = 0; t < 2; ++t) nxt[t] = load_row(a.pos, a.rays, a.z, a.S, a.s_shift, row_index(units.pair(units.first), t));
     for (int64_t u = units.first; u < units.count; u += units.stride) {
@@ -558,8 +597,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
           const uint32_t sA = sm.tileA(t);
           const uint32_t srow = sA + row * 128;
           float* part = sm.part() + t * 128;
+          if (lane == 0 && (e == 0 || e == 7)) LONER_TRACE_EV(tr, 0, (unsigned)((u - units.first) / units.stride), l, t);   // waits for the accumulator
           mbar_wait(sm.acc_full(t), par_acc);
           tc_fence_after();
+          if (lane == 0 && (e == 0 || e == 7)) LONER_TRACE_EV(tr, 1, (unsigned)((u - units.first) / units.stride), l, t);   // accumulator complete
           float sig0 = 0.f, sig1 = 0.f;
           uint32_t mbits[kCols / 32];
           drain32<kCols>(acc_base + t * 256, [&](int i, uint32_t (&v)[32]) {
@@ -582,6 +623,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
           });
           const float sig = sig0 + sig1;
           tc_fence_before();
+          if (lane == 0 && (e == 0 || e == 7)) LONER_TRACE_EV(tr, 2, (unsigned)((u - units.first) / units.stride), l, t);   // drained + stored
           if (kStash && active) {
             uint32_t* mrow = reinterpret_cast<uint32_t*>(a.masks + tile * mask_tile_bytes(net)) +
                              ((int64_t)l * kTile + row) * (W / 32) + h * (kCols / 32);
@@ -596,6 +638,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
           if (kStash && elected) bulk_wait_read0();
           if (!last) arrive_a<kCtas>(a_rdy[t], lane);
           else if (h == 1) part[row] = sig;
+          if (lane == 0 && (e == 0 || e == 7)) LONER_TRACE_EV(tr, 3, (unsigned)((u - units.first) / units.stride), l, t);   // handed off
           if (kStash || last) epi_bar();
           if (last && h == 0 && in) a.sigma[gs] = sig + part[row];
           if (kStash && elected && active) {
@@ -1260,6 +1303,15 @@ inline WgradPlan plan_wgrad(const Net& net, bool gen_last) {
 
 using namespace loner::mlp;
 
+#ifdef LONER_TRACE
+extern "C" int loner_trace_setup(void* buf, uint32_t cap_per_role) {
+  unsigned long long* p = (unsigned long long*)buf;
+  if (cudaMemcpyToSymbol(loner::mlp::g_trace_buf, &p, sizeof(p)) != cudaSuccess) return LONER_E_LAUNCH;
+  if (cudaMemcpyToSymbol(loner::mlp::g_trace_cap, &cap_per_role, sizeof(cap_per_role)) != cudaSuccess) return LONER_E_LAUNCH;
+  return LONER_OK;
+}
+#endif
+
 extern "C" int64_t loner_mlp_param_count(const loner_net_t* n) {
   Net net;
   if (!net_from(n, net)) return -1;
@@ -1336,7 +1388,7 @@ extern "C" int loner_mlp_fwd(const loner_net_t* n, const void* packed, const flo
   // CTA pairs pay off where the shared-memory data pipe is the limit (the training forward: operands + epilogue +
   // ring + stash copy); the inference forward is bound by the X/Y hand-off latency, which the pair's remote
   // arrives lengthen (measured 1.48 vs 1.34 ms at C2), so it stays on single CTAs.
-  const int ctas = acts ? pipe_ctas(net) : 1;
+  const int ctas = (acts || (net.flags & LONER_NET_PAIR_INFER)) ? pipe_ctas(net) : 1;
   cudaStream_t st = (cudaStream_t)stream;
 #define LONER_FWD(W_, S_) \
   (ctas == 2 ? launch_pipe(mlp_fwd_kernel<W_, S_, 2>, a, a.tiles, 2, st) : launch_pipe(mlp_fwd_kernel<W_, S_, 1>, a, a.tiles, 1, st))
