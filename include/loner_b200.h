@@ -94,8 +94,6 @@ typedef struct {
 #define LONER_NET_SINGLE_CTA 1
 /* dgrad stashes dZ_L and wgrad reads it, instead of wgrad rebuilding it from the ReLU masks, d_sigma and w_out */
 #define LONER_NET_STASH_DZL 2
-/* the inference forward as CTA pairs too (measured slower than single CTAs: 1.48 vs 1.35 ms at C2) */
-#define LONER_NET_PAIR_INFER 16
 
 int64_t loner_mlp_param_count(const loner_net_t* net);       /* flat fp32 params, [out,in] row-major per layer */
 int64_t loner_mlp_packed_bytes(const loner_net_t* net);      /* fp16 tensor-core image of the params */

@@ -167,8 +167,8 @@ constexpr int kPipeSmem = 2 * 65536 + kRingBytes + kPipeExtra;
 // pointers): a table indexed by a run-time slot number would live in local memory, and local loads
 // miss the (tiny, 28 KB) L1 behind a saturated HBM.
 // kCtas = 2: the CTA pair variant (cta_group::2) - each CTA stages only ITS half (N/2 columns) of every weight
-// chunk, so the ring has twice the slots at half the size, and the leader also watches `w_peer`, the barriers the
-// peer's relay warp arrives on when the peer's half of a slot has landed.
+// chunk, so the ring has twice the slots at half the size; the leader's `w_full` barriers count two arrivals: its own
+// producer's expect_tx and the peer's relay warp, which arrives (remotely) when the peer's half of the slot has landed.
 template <int kCtas>
 struct PipeSmem {
   static constexpr uint32_t kSlots = kCtas == 2 ? 6 : 3;
@@ -186,7 +186,6 @@ struct PipeSmem {
   __device__ __forceinline__ uint32_t w_empty(uint32_t i) const { return bars() + 8u * (kSlots + i); }
   __device__ __forceinline__ uint32_t a_ready(int t) const { return bars() + 8u * (2 * kSlots + t); }
   __device__ __forceinline__ uint32_t acc_full(int t) const { return bars() + 8u * (2 * kSlots + 2 + t); }
-  __device__ __forceinline__ uint32_t w_peer(uint32_t i) const { return bars() + 8u * (2 * kSlots + 4 + i); }
   __device__ __forceinline__ uint32_t* tmem_slot() const { return reinterpret_cast<uint32_t*>(base + kX + 2304); }
   // encoding table: feature pair p -> {kind, 2^f}; kind 0..2 = input dimension, 3 = padding ones, 4 = zeros
   __device__ __forceinline__ uint2* enc_tab() const { return reinterpret_cast<uint2*>(base + kX + 2320); }
@@ -210,8 +209,9 @@ __device__ __forceinline__ void pipe_init(const PipeSmem<kCtas>& sm, int tid, in
   }
   if (tid == 0) {
     for (uint32_t i = 0; i < kSlots; ++i) {
-      mbar_init(sm.w_full(i), 1); mbar_init(sm.w_empty(i), 1);
-      if (kCtas == 2) mbar_init(sm.w_peer(i), 1);
+      // pair, leader: a slot is full when its own half has landed (expect_tx arrive + bytes) AND the peer's relay warp
+      // has arrived for the peer's half - ONE barrier for the issuer to wait on per chunk
+      mbar_init(sm.w_full(i), (kCtas == 2 && cluster_ctarank() == 0) ? 2 : 1); mbar_init(sm.w_empty(i), 1);
     }
     // pair: one arrive per epilogue WARP of either CTA (8 + 8); single CTA: one per epilogue thread
     for (int t = 0; t < 2; ++t) { mbar_init(sm.a_ready(t), kCtas == 2 ? 16 : kGroupThreads); mbar_init(sm.acc_full(t), 1); }
@@ -496,7 +496,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
           for (int c = 0; c < nch; ++c, ++g) {
             const uint32_t slot = g % nslots, par_w = (g / nslots) & 1;
             mbar_wait_warp(sm.w_full(slot), par_w);
-            if (kCtas == 2) mbar_wait_warp(sm.w_peer(slot), par_w);
             tc_fence_after();
             if (lane == 0) LONER_TRACE_EV(tr, 2, (unsigned)((u - units.first) / units.stride), l, t, c);      // chunk c has landed
             const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
@@ -533,7 +532,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
         for (int i = 0; i < n; ++i, ++g) {
           const uint32_t slot = g % nslots;
           mbar_wait_warp(sm.w_full(slot), (g / nslots) & 1);
-          if (lane == 0) mbar_arrive_cluster(mapa_u32(sm.w_peer(slot), 0));
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(sm.w_full(slot), 0));
           __syncwarp();
         }
       }
@@ -721,7 +720,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
           for (int c = 0; c < kNb; ++c, ++g) {
             const uint32_t slot = g % nslots, par_w = (g / nslots) & 1;
             mbar_wait_warp(sm.w_full(slot), par_w);
-            if (kCtas == 2) mbar_wait_warp(sm.w_peer(slot), par_w);
             tc_fence_after();
             const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);
             if (kCtas == 2)
@@ -744,7 +742,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
         for (int i = 0; i < 2 * kNb; ++i, ++g) {
           const uint32_t slot = g % nslots;
           mbar_wait_warp(sm.w_full(slot), (g / nslots) & 1);
-          if (lane == 0) mbar_arrive_cluster(mapa_u32(sm.w_peer(slot), 0));
+          if (lane == 0) mbar_arrive_cluster(mapa_u32(sm.w_full(slot), 0));
           __syncwarp();
         }
       }
@@ -1385,10 +1383,10 @@ extern "C" int loner_mlp_fwd(const loner_net_t* n, const void* packed, const flo
   a.s_shift = (S > 0 && (S & (S - 1)) == 0) ? __builtin_ctz((unsigned)S) : -1;
   a.tiles = n_tiles(P); a.sigma = sigma; a.acts = (uint8_t*)acts;
   a.masks = acts ? (uint8_t*)acts + a.tiles * act_tile_bytes(net) : nullptr;
-  // CTA pairs pay off where the shared-memory data pipe is the limit (the training forward: operands + epilogue +
-  // ring + stash copy); the inference forward is bound by the X/Y hand-off latency, which the pair's remote
-  // arrives lengthen (measured 1.48 vs 1.34 ms at C2), so it stays on single CTAs.
-  const int ctas = (acts || (net.flags & LONER_NET_PAIR_INFER)) ? pipe_ctas(net) : 1;
+  // CTA pairs for the training AND the inference forward: each SM stages half of every weight chunk (half the L2 -> SM
+  // stream that bounds the single-CTA inference kernel: 1.35 ms at C2; pairs 1.32 ms since the leader waits on ONE
+  // barrier per chunk - with a separate barrier for the peer's half the pair was the slower one, 1.48 ms).
+  const int ctas = pipe_ctas(net);
   cudaStream_t st = (cudaStream_t)stream;
 #define LONER_FWD(W_, S_) \
   (ctas == 2 ? launch_pipe(mlp_fwd_kernel<W_, S_, 2>, a, a.tiles, 2, st) : launch_pipe(mlp_fwd_kernel<W_, S_, 1>, a, a.tiles, 1, st))
