@@ -491,11 +491,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
         for (int t = 0; t < 2; ++t) {
           if (lane == 0) LONER_TRACE_EV(tr, 0, (unsigned)((u - units.first) / units.stride), l, t);           // waits for A
           mbar_wait_warp(sm.a_ready(t), par_a);
+          if (lane == 0) LONER_TRACE_EV(tr, 5, (unsigned)((u - units.first) / units.stride), l, t);           // a_ready observed (before the fence)
           tc_fence_after();
           if (lane == 0) LONER_TRACE_EV(tr, 1, (unsigned)((u - units.first) / units.stride), l, t);           // A is ready
           for (int c = 0; c < nch; ++c, ++g) {
             const uint32_t slot = g % nslots, par_w = (g / nslots) & 1;
             mbar_wait_warp(sm.w_full(slot), par_w);
+            if (lane == 0) LONER_TRACE_EV(tr, 6, (unsigned)((u - units.first) / units.stride), l, t, c);      // chunk observed (before the fence)
             tc_fence_after();
             if (lane == 0) LONER_TRACE_EV(tr, 2, (unsigned)((u - units.first) / units.stride), l, t, c);      // chunk c has landed
             const uint32_t sa = sm.tileA(t) + c * kBlk, sb = sm.ring(slot);

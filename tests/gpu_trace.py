@@ -51,7 +51,7 @@ assert T.loner_trace_setup(buf.data_ptr(), CAP) == 0
 run()
 assert T.loner_trace_setup(None, 0) == 0
 raw = buf.cpu().view(2, 4, CAP, 2)
-names = {0: {0: "mma.wait_a", 1: "mma.a_ready", 2: "mma.chunk", 3: "mma.issued", 4: "mma.chunk_issued"},
+names = {0: {0: "mma.wait_a", 1: "mma.a_ready", 2: "mma.chunk", 3: "mma.issued", 4: "mma.chunk_issued", 5: "mma.a_seen", 6: "mma.chunk_seen"},
          1: {0: "epi0.wait_acc", 1: "epi0.acc_full", 2: "epi0.drained", 3: "epi0.handoff"},
          2: {0: "epi7.wait_acc", 1: "epi7.acc_full", 2: "epi7.drained", 3: "epi7.handoff"},
          3: {0: "prod.issue"}}
@@ -70,7 +70,7 @@ for cta in (0, 1):
     t0 = sel[0][0]
     print(f"==== CTA {cta}: {len(ev)} events; units {UNITS}; clk relative to the first listed event")
     for clk, role, e, unit, layer, tile, extra in sel:
-        print(f"{clk - t0:8d}  u{unit} L{layer} {'XY'[tile]}  {names[role][e]}{' c%d' % extra if (role == 0 and e in (2, 4)) or role == 3 else ''}")
+        print(f"{clk - t0:8d}  u{unit} L{layer} {'XY'[tile]}  {names[role][e]}{' c%d' % extra if (role == 0 and e in (2, 4, 6)) or role == 3 else ''}")
     # summary: per (unit, layer, tile) intervals
     idx = {(r, e, u, l, t, x): c for c, r, e, u, l, t, x in ev}
     print("---- intervals (clk): unit layer tile | a_wait = mma.a_ready - mma.wait_a | issue = mma.issued - mma.a_ready | "

@@ -10,6 +10,11 @@
 namespace loner {
 using namespace sm100;
 
+__device__ __forceinline__ uint32_t ld_acquire_cta_probe(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -117,5 +122,58 @@ extern "C" int loner_probe_mma(int iters, int load_kb_per_chunk, int store_kb_pe
   cudaFuncSetAttribute(loner::probe_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   loner::probe_mma_kernel<<<blocks, 320, smem, (cudaStream_t)stream>>>(iters, load_kb_per_chunk, store_kb_per_chunk,
                                                                        tmem_lds_per_chunk, mode, (const uint8_t*)src, cycles);
+  return cudaGetLastError() == cudaSuccess ? LONER_OK : LONER_E_LAUNCH;
+}
+
+// ---- latency of the synchronisation primitives the MMA issuer executes between chunks (one warp, dependent chain):
+// what[0] mbarrier.try_wait on a completed phase, [1] mbarrier.test_wait, [2] ld.acquire.cta.shared, [3] ld.volatile.shared,
+// [4] tcgen05.fence::after_thread_sync, [5] try_wait + __syncwarp (= mbar_wait_warp)
+namespace loner {
+__global__ void probe_sync_kernel(int iters, long long* out) {
+  __shared__ uint64_t bar;
+  __shared__ uint32_t word;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); fence_mbar_init(); word = 1u; }
+  __syncthreads();
+  if (threadIdx.x == 0) mbar_arrive(smem_u32(&bar));       // phase 0 completes
+  __syncthreads();
+  const uint32_t b = smem_u32(&bar), w = smem_u32(&word);
+  uint32_t acc = 0;
+  long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) acc += mbar_try_wait(b, 0) ? 1u : 0u;
+  long long t1 = clock64();
+  if (threadIdx.x == 0) out[0] = (t1 - t0);
+  t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(b), "r"(0u) : "memory");
+    acc += ok;
+  }
+  t1 = clock64();
+  if (threadIdx.x == 0) out[1] = (t1 - t0);
+  t0 = clock64();
+  for (int i = 0; i < iters; ++i) acc += ld_acquire_cta_probe(w + (acc & 0u));
+  t1 = clock64();
+  if (threadIdx.x == 0) out[2] = (t1 - t0);
+  t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(w + (acc & 0u)) : "memory");
+    acc += v;
+  }
+  t1 = clock64();
+  if (threadIdx.x == 0) out[3] = (t1 - t0);
+  t0 = clock64();
+  for (int i = 0; i < iters; ++i) tc_fence_after();
+  t1 = clock64();
+  if (threadIdx.x == 0) out[4] = (t1 - t0);
+  t0 = clock64();
+  for (int i = 0; i < iters; ++i) { mbar_wait(b, 0); __syncwarp(); }
+  t1 = clock64();
+  if (threadIdx.x == 0) { out[5] = (t1 - t0); out[6] = acc; }
+}
+}  // namespace loner
+
+extern "C" int loner_probe_sync(int iters, long long* out, void* stream) {
+  loner::probe_sync_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(iters, out);
   return cudaGetLastError() == cudaSuccess ? LONER_OK : LONER_E_LAUNCH;
 }
