@@ -5,10 +5,9 @@
 import ctypes as C, os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from loner_b200 import lib as L, synth, engine as eng, ops
+from loner_b200 import build, lib as L, synth, engine as eng, ops
 
-here = os.path.dirname(os.path.abspath(__file__))
-T = C.CDLL(os.path.join(here, "probes", "libloner_trace.so"))
+T = C.CDLL(build.build_trace())
 vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
 T.loner_mlp_packed_bytes.restype = i64; T.loner_mlp_packed_bytes.argtypes = [vp]
 T.loner_mlp_act_bytes.restype = i64; T.loner_mlp_act_bytes.argtypes = [vp, i64]
