@@ -33,3 +33,17 @@ for load_kb, store_kb, lds, mode, what in (
              clk_per_mma_max=round(float(c.max()) / (iters * 4), 1), kernel_clk_per_mma=round(float(tot.mean()) / (iters * 4), 1), flop_per_clk_per_sm=round(2 * 128 * 256 * 16 * iters * 4 / float(c.mean())))
     out.append(r)
     print(json.dumps(r), flush=True)
+
+# ---- CTA pairs: tcgen05.mma.cta_group::2 (M = 256 over two SMs)
+lib.loner_probe_mma2.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+clusters = blocks // 2
+cyc2 = torch.zeros(clusters, dtype=torch.int64, device="cuda")
+for commit in (0, 1):
+    for rep in range(2):
+        rc = lib.loner_probe_mma2(iters, commit, clusters, cyc2.data_ptr(), L.stream_ptr())
+        assert rc == 0, rc
+        torch.cuda.synchronize()
+    c = cyc2.float()
+    print(json.dumps(dict(what="cta_group::2 MMAs (M256 N256 K16 over a CTA pair)" + (" with a multicast commit per chunk" if commit else ""),
+                          clk_per_mma_mean=round(float(c.mean()) / (iters * 4), 1), clk_per_mma_max=round(float(c.max()) / (iters * 4), 1),
+                          flop_per_clk_per_sm=round(2 * 256 * 256 * 16 * iters * 4 / float(c.mean()) / 2))), flush=True)

@@ -177,3 +177,54 @@ extern "C" int loner_probe_sync(int iters, long long* out, void* stream) {
   loner::probe_sync_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(iters, out);
   return cudaGetLastError() == cudaSuccess ? LONER_OK : LONER_E_LAUNCH;
 }
+
+// ---- the same question for the CTA-pair instruction: tcgen05.mma.cta_group::2, M = 256 over two SMs (each CTA holds its 128
+// rows of A and its N/2 = 128 columns of B, like the pair variants of the pipelined kernels), issued back to back by the
+// leader; optionally with a multicast commit per chunk.  cycles[cluster] = the leader's MMA stream duration.
+namespace loner {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64, 1) probe_mma2_kernel(int iters, int commit_per_chunk,
+                                                                                       long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t sA = smem_u32(smem), sB = sA + 16384;       // A [128 x 64] 16 KB | B half [64 K x 128 N] 16 KB
+  for (int i = tid; i < 32768 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 1) tmem_alloc2<512>(smem_u32(&tmem_slot));
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t done = smem_u32(&bars[0]), scratch = smem_u32(&bars[1]);
+  const long long t0 = clock64();
+  if (warp == 1) {
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(256, 256, 0, 1);
+      for (int it = 0; it < iters; ++it)
+        umma2_f16_x4_warp<2, 128>(tmem, desc_lo_sw128(sA, 16), desc_hi_sw128(1024), desc_lo_sw128(sB, 8192), desc_hi_sw128(1024),
+                                  idesc, it > 0 ? 1u : 0u, it == iters - 1 ? done : (commit_per_chunk ? scratch : 0u));
+    }
+    mbar_wait_warp(done, 0);                                  // both CTAs: the last commit is multicast
+    if (rank == 0 && lane == 0) cycles[blockIdx.x >> 1] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc2<512>(tmem);
+}
+}  // namespace loner
+
+extern "C" int loner_probe_mma2(int iters, int commit_per_chunk, int clusters, long long* cycles, void* stream) {
+  if (iters <= 0 || clusters <= 0 || !cycles) return LONER_E_BAD_ARG;
+  cudaFuncSetAttribute(loner::probe_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
+  loner::probe_mma2_kernel<<<2 * clusters, 64, 32768, (cudaStream_t)stream>>>(iters, commit_per_chunk, cycles);
+  return cudaGetLastError() == cudaSuccess ? LONER_OK : LONER_E_LAUNCH;
+}
