@@ -94,6 +94,9 @@ typedef struct {
 #define LONER_NET_SINGLE_CTA 1
 /* dgrad stashes dZ_L and wgrad reads it, instead of wgrad rebuilding it from the ReLU masks, d_sigma and w_out */
 #define LONER_NET_STASH_DZL 2
+/* training forward with ONE MMA-issuing warp for both tiles (and a weight stream per tile) instead of one issuing warp per
+ * tile sharing one weight stream */
+#define LONER_NET_ONE_ISSUER 32
 
 int64_t loner_mlp_param_count(const loner_net_t* net);       /* flat fp32 params, [out,in] row-major per layer */
 int64_t loner_mlp_packed_bytes(const loner_net_t* net);      /* fp16 tensor-core image of the params */

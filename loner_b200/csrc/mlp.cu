@@ -159,6 +159,13 @@ __global__ void pack_kernel(Net net, const float* __restrict__ params, uint8_t* 
 //    (profiles/experiments/r2_epilogue16.md).
 constexpr int kPipeThreads = 320;
 constexpr int kGroupThreads = 256;
+// kIss = 2: one MMA-issuing warp PER TILE (warp 1 issues tile X, warp 10 tile Y) instead of one warp issuing X's and then
+// Y's MMAs.  The issue of an MMA blocks until the tensor pipe accepts it, so a single issuer serialises 2 x 2048 clk of
+// issue with all of its own waits, fences and descriptor set-up (tile-step 3250 clk instead of 2048,
+// profiles/experiments/r2_timeline.md); with two issuers the pipe interleaves the two tiles' MMAs and each issuer's
+// boundary work overlaps the other tile's MMAs.  Both tiles also consume the SAME weight chunk before its slot is
+// released (w_empty counts two commits): every layer's weights are streamed once per unit, not once per tile.
+template <int kIss> __host__ __device__ constexpr int pipe_threads() { return kPipeThreads + (kIss == 2 ? 32 : 0); }
 constexpr int kRingBytes = 98304;                    // weight ring: 3 x 32 KB (one CTA) or 6 x 16 KB (CTA pair)
 constexpr int kPipeExtra = 2576;
 constexpr int kPipeSmem = 2 * 65536 + kRingBytes + kPipeExtra;
@@ -199,7 +206,7 @@ __device__ __forceinline__ PipeSmem<kCtas> carve(uint8_t* base) {
   return p;
 }
 
-template <int kCtas>
+template <int kCtas, int kIss = 1>
 __device__ __forceinline__ void pipe_init(const PipeSmem<kCtas>& sm, int tid, int warp, const float* wout_src, int W,
                                           const Net& net) {
   constexpr uint32_t kSlots = PipeSmem<kCtas>::kSlots;
@@ -211,13 +218,13 @@ __device__ __forceinline__ void pipe_init(const PipeSmem<kCtas>& sm, int tid, in
     for (uint32_t i = 0; i < kSlots; ++i) {
       // pair, leader: a slot is full when its own half has landed (expect_tx arrive + bytes) AND the peer's relay warp
       // has arrived for the peer's half - ONE barrier for the issuer to wait on per chunk
-      mbar_init(sm.w_full(i), (kCtas == 2 && cluster_ctarank() == 0) ? 2 : 1); mbar_init(sm.w_empty(i), 1);
+      mbar_init(sm.w_full(i), (kCtas == 2 && cluster_ctarank() == 0) ? 2 : 1); mbar_init(sm.w_empty(i), kIss);
     }
     // pair: one arrive per epilogue WARP of either CTA (8 + 8); single CTA: one per epilogue thread
     for (int t = 0; t < 2; ++t) { mbar_init(sm.a_ready(t), kCtas == 2 ? 16 : kGroupThreads); mbar_init(sm.acc_full(t), 1); }
     fence_mbar_init();
   }
-  for (int j = tid; j < W; j += kPipeThreads) sm.wout()[j] = wout_src[j];
+  for (int j = tid; j < W; j += pipe_threads<kIss>()) sm.wout()[j] = wout_src[j];
   if (tid >= 64 && tid < 96) {          // features [0, 6F): sin/cos pairs ordered [dim][freq]; [6F, Epad): ones; rest zeros
     const int p = tid - 64, dim = p / net.F, f = p % net.F;
     uint2 e;
@@ -444,19 +451,20 @@ struct Units {
   __device__ __forceinline__ int64_t pair(int64_t unit) const { return kCtas == 2 ? 2 * unit + rank : unit; }
 };
 
-template <int W, bool kStash, int kCtas>
-__global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs a) {
+template <int W, bool kStash, int kCtas, int kIss>
+__global__ void __launch_bounds__(pipe_threads<kIss>(), 1) mlp_fwd_kernel(const FwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   using Smem = PipeSmem<kCtas>;
   const Smem sm = carve<kCtas>(smem_raw);
   const Net net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pipe_init<kCtas>(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W, net);
+  pipe_init<kCtas, kIss>(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W, net);
   const uint32_t tmem = *sm.tmem_slot();
   constexpr uint32_t nslots = Smem::kSlots;
   const Units<kCtas> units(a.tiles);
   constexpr int kNb = W / 64;
+  constexpr int kFetches = (kIss == 2) ? 1 : 2;     // weight streams per unit and layer: one per tile, or one shared by both
   constexpr uint32_t kChunkBytes = kNb * 8192;      // 64 K-rows x W out-features, fp16
   constexpr uint32_t kMyBytes = kChunkBytes / kCtas;   // pair: this CTA stages column blocks [rank*kNb/2, (rank+1)*kNb/2)
 
@@ -468,7 +476,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
     for (int64_t u = units.first; u < units.count; u += units.stride) {
       for (int l = 0; l < net.L; ++l) {
         const int nch = (l == 0) ? 1 : kNb;
-        for (int t = 0; t < 2; ++t) {            // every tile fetches its own chunks: X[all K] then Y[all K]
+        for (int t = 0; t < kFetches; ++t) {     // one issuer: every tile fetches its own chunks, X[all K] then Y[all K]
           for (int c = 0; c < nch; ++c, ++g) {
             const uint32_t slot = g % nslots, use = g / nslots;
             if (use > 0) mbar_wait_warp(sm.w_empty(slot), (use - 1) & 1);
@@ -479,16 +487,18 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
         }
       }
     }
-  } else if (warp == 1 && units.rank == 0) {
-    // ---------------- MMA issuer (whole warp, converged; one lane is elected inside each asm statement)
+  } else if ((warp == 1 || (kIss == 2 && warp == 10)) && units.rank == 0) {
+    // ---------------- MMA issuer(s) (whole warp, converged; one lane is elected inside each asm statement).
+    // kIss = 1: this warp issues tile X, then tile Y; kIss = 2: warp 1 owns tile X, warp 10 tile Y, same chunk sequence.
     constexpr uint32_t idesc = make_idesc_f16(128 * kCtas, W, 0, 1);
     uint32_t g = 0, par_a = 0u;
+    const int t_lo = (kIss == 2 && warp == 10) ? 1 : 0, t_hi = (kIss == 2 && warp == 1) ? 1 : 2;
     LONER_TRACE_OPEN(tr, 0);
     for (int64_t u = units.first; u < units.count; u += units.stride) {
       for (int l = 0; l < net.L; ++l) {
         const int nch = (l == 0) ? 1 : kNb;
         const int ksteps0 = (l == 0) ? net.Epad / 16 : 4;   // layer 0 contracts over Epad (<= 64) features
-        for (int t = 0; t < 2; ++t) {
+        for (int t = t_lo; t < t_hi; ++t) {
           if (lane == 0) LONER_TRACE_EV(tr, 0, (unsigned)((u - units.first) / units.stride), l, t);           // waits for A
           mbar_wait_warp(sm.a_ready(t), par_a);
           if (lane == 0) LONER_TRACE_EV(tr, 5, (unsigned)((u - units.first) / units.stride), l, t);           // a_ready observed (before the fence)
@@ -530,7 +540,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
     uint32_t g = 0;
     for (int64_t u = units.first; u < units.count; u += units.stride) {
       for (int l = 0; l < net.L; ++l) {
-        const int n = 2 * ((l == 0) ? 1 : kNb);
+        const int n = kFetches * ((l == 0) ? 1 : kNb);
         for (int i = 0; i < n; ++i, ++g) {
           const uint32_t slot = g % nslots;
           mbar_wait_warp(sm.w_full(slot), (g / nslots) & 1);
@@ -539,7 +549,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_fwd_kernel(const FwdArgs 
         }
       }
     }
-  } else {
+  } else if (warp < 10) {
     // ---------------- epilogue warps: thread = (sample row, column half); tile X, then tile Y.
     // Stash mode: every finished image (A_0 .. A_L) leaves its tile buffer as ONE bulk copy issued by
     // the elected thread after the step's barrier.  The elected thread waits for the reads of all
@@ -1330,12 +1340,12 @@ static inline bool wgrad_rebuilds_last(const Net& net) { return (net.flags & LON
 
 // Launch of a pipelined kernel: one CTA per SM, as CTA pairs (clusters of 2 on one TPC) or single CTAs.
 template <class Kern, class Args>
-static void launch_pipe(Kern kern, const Args& args, int64_t tiles, int ctas, cudaStream_t st) {
+static void launch_pipe(Kern kern, const Args& args, int64_t tiles, int ctas, cudaStream_t st, int threads = kPipeThreads) {
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPipeSmem);
   const int sms = device_sm_count();
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
-  cfg.blockDim = dim3(kPipeThreads);
+  cfg.blockDim = dim3((unsigned)threads);
   cfg.dynamicSmemBytes = kPipeSmem;
   cfg.stream = st;
   if (ctas == 2) {
@@ -1390,11 +1400,19 @@ extern "C" int loner_mlp_fwd(const loner_net_t* n, const void* packed, const flo
   // barrier per chunk - with a separate barrier for the peer's half the pair was the slower one, 1.48 ms).
   const int ctas = pipe_ctas(net);
   cudaStream_t st = (cudaStream_t)stream;
-#define LONER_FWD(W_, S_) \
-  (ctas == 2 ? launch_pipe(mlp_fwd_kernel<W_, S_, 2>, a, a.tiles, 2, st) : launch_pipe(mlp_fwd_kernel<W_, S_, 1>, a, a.tiles, 1, st))
+  // One MMA-issuing warp per tile for the training forward of CTA pairs (2.009 vs 2.066 ms at C2 in tests/gpu_ab.py,
+  // gpurun_out/r2d_ab.jsonl: both tiles share one weight stream, half the L2 -> SM traffic next to the stash copies);
+  // inference and single CTAs keep one issuer (two consumers per slot were not faster there: the ring's three 32 KB slots
+  // are too few for two tiles in lock-step).
+  const bool two = acts != nullptr && ctas == 2 && !(net.flags & LONER_NET_ONE_ISSUER);
+#define LONER_FWD_I(W_, S_, I_)                                                                              \
+  (ctas == 2 ? launch_pipe(mlp_fwd_kernel<W_, S_, 2, I_>, a, a.tiles, 2, st, pipe_threads<I_>())             \
+             : launch_pipe(mlp_fwd_kernel<W_, S_, 1, I_>, a, a.tiles, 1, st, pipe_threads<I_>()))
+#define LONER_FWD(W_, S_) (two ? LONER_FWD_I(W_, S_, 2) : LONER_FWD_I(W_, S_, 1))
   if (net.W == 256) { if (acts) LONER_FWD(256, true); else LONER_FWD(256, false); }
   else              { if (acts) LONER_FWD(128, true); else LONER_FWD(128, false); }
 #undef LONER_FWD
+#undef LONER_FWD_I
   LONER_CHECK_LAUNCH();
   return LONER_OK;
 }

@@ -98,10 +98,10 @@ def _rand_pos(P, seed):
 
 
 # kernel variants (loner_net_t.flags): CTA pairs + dZ_L rebuilt inside wgrad, and the round-1 single-CTA pipeline
-VARIANTS = [0, ops.NET_SINGLE_CTA | ops.NET_STASH_DZL, ops.NET_STASH_DZL, ops.NET_SINGLE_CTA]
+VARIANTS = [0, ops.NET_SINGLE_CTA | ops.NET_STASH_DZL, ops.NET_STASH_DZL, ops.NET_SINGLE_CTA, ops.NET_ONE_ISSUER]
 
 
-@pytest.mark.parametrize("flags", VARIANTS[:2])
+@pytest.mark.parametrize("flags", [VARIANTS[0], VARIANTS[1], VARIANTS[4]])
 @pytest.mark.parametrize("W,L,P", [(256, 4, 1000), (128, 2, 640), (256, 1, 128), (256, 4, 128 * 7 + 5), (64, 2, 300)])
 def test_mlp_forward_layers(W, L, P, flags):
     spec = orc.NetSpec(n_frequencies=10, n_neurons=W, n_hidden_layers=L, precision="fp16")
