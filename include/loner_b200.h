@@ -97,6 +97,8 @@ typedef struct {
 /* training forward with ONE MMA-issuing warp for both tiles (and a weight stream per tile) instead of one issuing warp per
  * tile sharing one weight stream */
 #define LONER_NET_ONE_ISSUER 32
+/* dgrad alone with one MMA-issuing warp (A/B of the dgrad pipeline) */
+#define LONER_NET_DGRAD_ONE_ISSUER 64
 
 int64_t loner_mlp_param_count(const loner_net_t* net);       /* flat fp32 params, [out,in] row-major per layer */
 int64_t loner_mlp_packed_bytes(const loner_net_t* net);      /* fp16 tensor-core image of the params */

@@ -685,18 +685,19 @@ struct BwdArgs {
   float* d_pos;          // [P,3] or null
 };
 
-template <int W, bool kDx, int kCtas>
-__global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArgs a) {
+template <int W, bool kDx, int kCtas, int kIss>
+__global__ void __launch_bounds__(pipe_threads<kIss>(), 1) mlp_dgrad_kernel(const BwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
   using Smem = PipeSmem<kCtas>;
   const Smem sm = carve<kCtas>(smem_raw);
   const Net net = a.net;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pipe_init<kCtas>(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W, net);
+  pipe_init<kCtas, kIss>(sm, tid, warp, reinterpret_cast<const float*>(a.packed + packed_wout_off(net)), W, net);
   const uint32_t tmem = *sm.tmem_slot();
   constexpr uint32_t nslots = Smem::kSlots;
   const Units<kCtas> units(a.tiles);
+  constexpr int kFetches = (kIss == 2) ? 1 : 2;   // weight streams per unit and layer (see mlp_fwd_kernel)
   constexpr bool want_dx = kDx;            // d_pos requested: one more GEMM (layer 0) and the encoding backward
   const int l_lo = want_dx ? 0 : 1;        // GEMMs run for l = L-1 .. l_lo : dA_l = dZ_{l+1} * W_l
   constexpr int kNb = W / 64;              // contraction (out-features of layer l) in 64-wide chunks
@@ -709,7 +710,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
       for (int l = net.L - 1; l >= l_lo; --l) {
         const uint32_t bytes = (uint32_t)layer_K(net, l) * 128u;     // one column block: K_l rows x 128 B
         const uint32_t mine = bytes / kCtas;
-        for (int t = 0; t < 2; ++t) {
+        for (int t = 0; t < kFetches; ++t) {
           for (int c = 0; c < kNb; ++c, ++g) {
             const uint32_t slot = g % nslots, use = g / nslots;
             if (use > 0) mbar_wait_warp(sm.w_empty(slot), (use - 1) & 1);
@@ -720,13 +721,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
         }
       }
     }
-  } else if (warp == 1 && units.rank == 0) {
-    // ---------------- MMA issuer (whole warp, converged)
+  } else if ((warp == 1 || (kIss == 2 && warp == 10)) && units.rank == 0) {
+    // ---------------- MMA issuer(s) (whole warp, converged); kIss = 2: warp 1 owns tile X, warp 10 tile Y
     uint32_t g = 0, par_a = 0u;
+    const int t_lo = (kIss == 2 && warp == 10) ? 1 : 0, t_hi = (kIss == 2 && warp == 1) ? 1 : 2;
     for (int64_t u = units.first; u < units.count; u += units.stride) {
       for (int l = net.L - 1; l >= l_lo; --l) {
         const uint32_t idesc = make_idesc_f16(128 * kCtas, layer_K(net, l), 0, 0);
-        for (int t = 0; t < 2; ++t) {
+        for (int t = t_lo; t < t_hi; ++t) {
           mbar_wait_warp(sm.a_ready(t), par_a);
           tc_fence_after();
           for (int c = 0; c < kNb; ++c, ++g) {
@@ -751,7 +753,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
     uint32_t g = 0;
     for (int64_t u = units.first; u < units.count; u += units.stride) {
       for (int l = net.L - 1; l >= l_lo; --l) {
-        for (int i = 0; i < 2 * kNb; ++i, ++g) {
+        for (int i = 0; i < kFetches * kNb; ++i, ++g) {
           const uint32_t slot = g % nslots;
           mbar_wait_warp(sm.w_full(slot), (g / nslots) & 1);
           if (lane == 0) mbar_arrive_cluster(mapa_u32(sm.w_full(slot), 0));
@@ -759,7 +761,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) mlp_dgrad_kernel(const BwdArg
         }
       }
     }
-  } else {
+  } else if (warp < 10) {
     // ---------------- epilogue warps: thread = (sample row, column half); tile X, then tile Y
     // (same step / barrier / bulk-copy protocol as the forward kernel).
     const int e = warp - 2;
@@ -1440,11 +1442,16 @@ extern "C" int loner_mlp_dgrad(const loner_net_t* n, const void* packed, const f
   b.stash_last = wgrad_rebuilds_last(net) ? 0 : 1;
   const int ctas = pipe_ctas(net);
   cudaStream_t st = (cudaStream_t)stream;
-#define LONER_DGRAD(W_, D_) \
-  (ctas == 2 ? launch_pipe(mlp_dgrad_kernel<W_, D_, 2>, b, tiles, 2, st) : launch_pipe(mlp_dgrad_kernel<W_, D_, 1>, b, tiles, 1, st))
+  // CTA pairs: one MMA-issuing warp per tile and one weight stream for both tiles, as in the training forward
+  const bool two = ctas == 2 && !(net.flags & (LONER_NET_ONE_ISSUER | LONER_NET_DGRAD_ONE_ISSUER));
+#define LONER_DGRAD_I(W_, D_, I_)                                                                                \
+  (ctas == 2 ? launch_pipe(mlp_dgrad_kernel<W_, D_, 2, I_>, b, tiles, 2, st, pipe_threads<I_>())                 \
+             : launch_pipe(mlp_dgrad_kernel<W_, D_, 1, 1>, b, tiles, 1, st, pipe_threads<1>()))
+#define LONER_DGRAD(W_, D_) (two ? LONER_DGRAD_I(W_, D_, 2) : LONER_DGRAD_I(W_, D_, 1))
   if (net.W == 256) { if (d_pos) LONER_DGRAD(256, true); else LONER_DGRAD(256, false); }
   else              { if (d_pos) LONER_DGRAD(128, true); else LONER_DGRAD(128, false); }
 #undef LONER_DGRAD
+#undef LONER_DGRAD_I
   LONER_CHECK_LAUNCH();
   return LONER_OK;
 }
