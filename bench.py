@@ -153,7 +153,7 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-NCU_SUMMARY = ("profiles/r2_ncu_summary.csv", "profiles/r1_ncu_summary.csv")
+NCU_SUMMARY = ("profiles/r2f_ncu_summary.csv", "profiles/r2_ncu_summary.csv", "profiles/r1_ncu_summary.csv")
 
 
 def ncu_traffic_bytes(kernel_substr, stash=True):
@@ -343,14 +343,17 @@ def kernel_table(wl, secs, per_chunk, peaks, net_flags):
         spec["mlp_fwd"] = ("l2-gather", 2 * (32 * 64 + 64), 512.0, "hash_fwd: 128 gathers x 4 B per sample from the L2-resident table")
         spec["mlp_dgrad"] = ("l2-atomic", 6 * (32 * 64 + 64), 1536.0, "hash_bwd: re-gathers 128 x 4 B and issues 128 x 8 B vector atomics per sample")
     else:
-        stash = 16384 * (1 + L * nb) / 128 + L * (max(W, 128) // 32) * 4
+        gen = gen and L >= 2                  # mlp.cu wgrad_rebuilds_last
+        fold = gen and not (net_flags & 128)  # mlp.cu wgrad_folds_out: A_L is neither stashed nor read (dW_out from dW_{L-1}'s partials)
+        stash = 16384 * (1 + (L - (1 if fold else 0)) * nb) / 128 + L * (max(W, 128) // 32) * 4
         dz = 16384 * nb * (L - (1 if gen else 0)) / 128
-        rd = 16384 * ((1 + nb + nb) + (L - 2) * 2 * nb + (nb if gen else 2 * nb)) / 128 if L >= 2 else 16384 * (1 + nb + (0 if gen else nb)) / 128
+        rd = (16384 * ((1 + nb + (0 if fold else nb)) + (L - 2) * 2 * nb + (nb if gen else 2 * nb)) / 128 if L >= 2
+              else 16384 * (1 + nb + nb) / 128)
         spec["mlp_fwd"] = ("tensor", f_fwd, stash, "tcgen05 forward; also writes the activation stash (design traffic, bytes_per_sample)")
         spec["mlp_dgrad"] = ("tensor", 2 * ((L - 1) * W * W + (e_pad * W if wl["poses"] else 0)), dz,
                              "tcgen05 dgrad; also writes the dZ stash (design traffic)")
         spec["mlp_wgrad"] = ("hbm", 2 * (e_pad * W + (L - 1) * W * W + W), rd,
-                             "tcgen05 wgrad incl. dW_out: streams the stash once (design traffic), accumulators in TMEM")
+                             "tcgen05 wgrad incl. dW_out (folded into the last hidden layer's partials): streams the stash once (design traffic), accumulators in TMEM")
     out = {}
     for k, (t, cnt) in secs.items():
         bound, flops, byts, what = spec.get(k, ("hbm", None, None, ""))

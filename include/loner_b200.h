@@ -99,6 +99,9 @@ typedef struct {
 #define LONER_NET_ONE_ISSUER 32
 /* dgrad alone with one MMA-issuing warp (A/B of the dgrad pipeline) */
 #define LONER_NET_DGRAD_ONE_ISSUER 64
+/* the forward stashes A_L too and wgrad accumulates dW_out from it, instead of deriving dW_out from the last hidden
+ * layer's weight-gradient partials (no biases: A_L = mask_L * (A_{L-1} W_{L-1}^T)) */
+#define LONER_NET_STASH_AL 128
 
 int64_t loner_mlp_param_count(const loner_net_t* net);       /* flat fp32 params, [out,in] row-major per layer */
 int64_t loner_mlp_packed_bytes(const loner_net_t* net);      /* fp16 tensor-core image of the params */

@@ -395,6 +395,7 @@ struct FwdArgs {
   float* sigma;          // [P]
   uint8_t* acts;         // activation stash or null
   uint8_t* masks;        // relu bit masks or null
+  int stash_last;        // 1: A_L is stashed too; 0: nothing reads it (wgrad derives dW_out from dW_{L-1}'s partials)
 };
 
 // sin/cos(pi * 2^f * x).  2^f * x is exact in fp32, and so is its reduction r to [-1, 1]; sin(pi r) and
@@ -565,6 +566,7 @@ __global__ void __launch_bounds__(pipe_threads<kIss>(), 1) mlp_fwd_kernel(const 
     const uint32_t acc_base = tmem + ((uint32_t)(q * 32) << 16) + h * kCols;
     uint32_t par_acc = 0;
     const bool pos_mode = a.pos != nullptr;
+    const bool keep_last = kStash && a.stash_last != 0;      // the last layer's image is written (and copied out) at all
     const uint32_t a_rdy[2] = {kCtas == 2 ? mapa_u32(sm.a_ready(0), 0) : sm.a_ready(0),
                                kCtas == 2 ? mapa_u32(sm.a_ready(1), 0) : sm.a_ready(1)};
     auto row_index = [&](int64_t pair, int t) {
@@ -621,7 +623,7 @@ __global__ void __launch_bounds__(pipe_threads<kIss>(), 1) mlp_fwd_kernel(const 
 #pragma unroll
             for (int p = 0; p < 16; ++p) v[p] = cvt_relu_h2(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]));
             if (kStash) mbits[i] = relu_mask_word(v);
-            if (!last || kStash) store32(srow, xs, col0, v);
+            if (!last || keep_last) store32(srow, xs, col0, v);
             if (last) {
 #pragma unroll
               for (int p = 0; p < 16; ++p) {
@@ -652,7 +654,7 @@ __global__ void __launch_bounds__(pipe_threads<kIss>(), 1) mlp_fwd_kernel(const 
           if (lane == 0 && (e == 0 || e == 7)) LONER_TRACE_EV(tr, 3, (unsigned)((u - units.first) / units.stride), l, t);   // handed off
           if (kStash || last) epi_bar();
           if (last && h == 0 && in) a.sigma[gs] = sig + part[row];
-          if (kStash && elected && active) {
+          if (kStash && elected && active && (!last || keep_last)) {
             bulk_s2g(a.acts + tile * act_tile_bytes(net) + kBlk + (int64_t)l * kNb * kBlk, sA, (uint32_t)(kNb * kBlk));
             bulk_commit();
           }
@@ -936,10 +938,16 @@ __global__ void __launch_bounds__(pipe_threads<kIss>(), 1) mlp_dgrad_kernel(cons
 //    times a rank-1 matrix - and eight otherwise idle warps rebuild its half-tile image in shared
 //    memory from the mask words, d_sigma and w_out while the producer streams A_{L-1}
 //    (-64 KB/tile written by dgrad, -64 KB/tile read here).
-//  * CTAs of layer 0 (the lightest stream: A_0 is 16 KB per tile) also stream A_L and accumulate the
-//    OUTPUT layer's gradient dW_out[n] = sum_s d_sigma[s] * A_L[s,n] on the CUDA cores of those same
-//    warps, reduced deterministically like every other partial (round 1: a separate 0.5 ms kernel that
-//    ended in atomics).
+//  * The OUTPUT layer's gradient dW_out[n] = sum_s d_sigma[s] * A_L[s,n] needs no A_L at all ("fold", the
+//    default when dZ_L is rebuilt): the network has no biases, so A_L[s,n] = mask_L[s,n] * sum_k A_{L-1}[s,k] W_{L-1}[n,k],
+//    and with G[n,k] = sum_s d_sigma[s] mask_L[s,n] A_{L-1}[s,k] (what the CTAs of layer L-1 accumulate when the
+//    rebuilt operand leaves out w_out)   dW_{L-1}[n,k] = w_out[n] G[n,k]   and   dW_out[n] = sum_k W_{L-1}[n,k] G[n,k],
+//    both applied in fp32 by wgrad_reduce_kernel.  The forward then does not stash A_L (-64 KB/tile written,
+//    -64 KB/tile read: 22 % of the forward's and 14 % of this kernel's HBM traffic).  The rebuilt operand is
+//    fp16(d_sigma * gscale * c), c = the power of two >= max |w_out| (same dynamic range as d_sigma * gscale * w_out).
+//  * Without the fold (LONER_NET_STASH_AL, a single hidden layer, or a stashed dZ_L) CTAs of layer 0 (the lightest
+//    stream: A_0 is 16 KB per tile) also stream A_L and accumulate dW_out on the CUDA cores of the helper warps,
+//    reduced deterministically like every other partial (round 1: a separate 0.5 ms kernel that ended in atomics).
 struct WgradArgs {
   Net net;
   const uint8_t* acts;
@@ -952,9 +960,21 @@ struct WgradArgs {
   float gscale;
   int64_t P;
   int gen_last;              // 1: CTAs of layer L-1 rebuild dZ_L; 0: they read dgrad's stash of it
+  int fold_out;              // 1 (needs gen_last): the rebuilt operand omits w_out, dW_out comes from layer L-1's partials
+  const uint8_t* packed;     // fp16 weight images (the reduce kernel reads W_{L-1} for the fold)
   int item_begin[9];         // first item of each layer (prefix), item_begin[L] = total
   int64_t part_off[10];      // float offset of each layer's first partial; [L] = dW_out partials; [L+1] = total
 };
+
+// The power of two >= m (clamped to 2^-14 .. 2^14; 1 for m = 0): an exact scale factor, computed identically by the
+// wgrad kernel (operand) and the reduce kernel (un-scaling).
+__device__ __forceinline__ float pow2_ceil(float m) {
+  if (!(m > 0.f)) return 1.f;
+  const uint32_t b = __float_as_uint(m);
+  int e = (int)(b >> 23) + ((b & 0x7FFFFFu) ? 1 : 0);
+  e = e < 113 ? 113 : (e > 141 ? 141 : e);
+  return __uint_as_float((uint32_t)e << 23);
+}
 
 constexpr int kWgStages = 3;
 constexpr int kWgThreads = 320;     // warp 0 producer, warp 1 MMA, warps 2-9 helpers (generate dZ_L / accumulate dW_out), 2-5 epilogue
@@ -998,7 +1018,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
   auto in_slot = [&](int j) { return base + (j % kWgStages) * kWgStageBytes + 65536 + (j / kWgStages) * kWgInBytes; };   // masks | d_sigma
 
   const bool gen_y = a.gen_last && (l == net.L - 1);   // this CTA rebuilds dZ_L instead of loading it
-  const bool do_out = (l == 0);                        // this CTA also streams A_L and accumulates dW_out
+  const bool fold = gen_y && a.fold_out != 0;          // ... without w_out: this CTA accumulates G (see above)
+  const bool do_out = (l == 0) && a.fold_out == 0;     // this CTA also streams A_L and accumulates dW_out
   // stage geometry ("X" = A_l half image, "Y" = dZ_{l+1} half image, "Z" = A_L half image)
   const int nbA = (l == 0) ? 1 : net.nb;          // column blocks of A_l
   const int nbY = net.nb;
@@ -1106,6 +1127,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
     const int oj = g & 31, rg = g >> 5;
     const bool out_on = do_out && (oj < net.nb * 8);
     const uint32_t out_off = (uint32_t)(oj >> 3) * 8192u + ((uint32_t)((oj & 7) ^ rg) << 4);
+    float cfold = 1.f;
+    if (fold) {
+      float m = 0.f;
+      for (int j = 0; j < net.W; ++j) m = fmaxf(m, fabsf(s_wout[j]));
+      cfold = pow2_ceil(m);
+    }
     for (int64_t i = 0; i < n_half; ++i) {
       const int s = (int)(i % kWgStages);
       const uint32_t ph = (uint32_t)((i / kWgStages) & 1);
@@ -1119,7 +1146,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
         const uint32_t* mrow = reinterpret_cast<const uint32_t*>(in) + r * mwords + qc * (cpt / 32);
         const uint32_t mw0 = mrow[0], mw1 = cpt > 32 ? mrow[1] : 0u;
         float ds = full ? reinterpret_cast<const float*>(in + 2048)[r] : (gs_half + r < a.P ? __ldg(a.d_sigma + gs_half + r) : 0.f);
-        ds *= a.gscale;
+        ds *= a.gscale * cfold;
+        const uint32_t hfold = cvt_sat_h2(ds, ds);
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t srow = stage + offY + (uint32_t)r * 128u;
         const uint32_t xs = (uint32_t)(r & 7) << 4;
@@ -1129,14 +1157,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
             const uint32_t bits = it == 0 ? mw0 : mw1;
             const int col0 = qc * cpt + it * 32;
             uint32_t hh[16];
+            if (fold) {
+#define LONER_GEN(P) hh[P] = hfold & half2_mask<P>(bits);
+              LONER_GEN(0) LONER_GEN(1) LONER_GEN(2) LONER_GEN(3) LONER_GEN(4) LONER_GEN(5) LONER_GEN(6) LONER_GEN(7)
+              LONER_GEN(8) LONER_GEN(9) LONER_GEN(10) LONER_GEN(11) LONER_GEN(12) LONER_GEN(13) LONER_GEN(14) LONER_GEN(15)
+#undef LONER_GEN
+            } else {
 #define LONER_GEN(P)                                                                      \
   {                                                                                       \
     const float2 w2 = *reinterpret_cast<const float2*>(s_wout + col0 + 2 * P);            \
     hh[P] = cvt_sat_h2(ds * w2.x, ds * w2.y) & half2_mask<P>(bits);                       \
   }
-            LONER_GEN(0) LONER_GEN(1) LONER_GEN(2) LONER_GEN(3) LONER_GEN(4) LONER_GEN(5) LONER_GEN(6) LONER_GEN(7)
-            LONER_GEN(8) LONER_GEN(9) LONER_GEN(10) LONER_GEN(11) LONER_GEN(12) LONER_GEN(13) LONER_GEN(14) LONER_GEN(15)
+              LONER_GEN(0) LONER_GEN(1) LONER_GEN(2) LONER_GEN(3) LONER_GEN(4) LONER_GEN(5) LONER_GEN(6) LONER_GEN(7)
+              LONER_GEN(8) LONER_GEN(9) LONER_GEN(10) LONER_GEN(11) LONER_GEN(12) LONER_GEN(13) LONER_GEN(14) LONER_GEN(15)
 #undef LONER_GEN
+            }
             // same image as dgrad's store32, with 8 KB (64-row) column blocks
             const uint32_t cb_off = (uint32_t)(col0 >> 6) * 8192u;
             const uint32_t j0 = ((uint32_t)(col0 & 63) >> 3) << 4;
@@ -1232,6 +1267,53 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const WgradArg
 __global__ void wgrad_reduce_kernel(Net net, const float* __restrict__ partials, WgradArgs w, float inv_gscale,
                                     float* __restrict__ d_params) {
   const int l = blockIdx.y;
+  __shared__ float s_c;
+  if (w.fold_out) {     // the scale of the rebuilt operand (see pow2_ceil)
+    if (threadIdx.x < 32) {
+      float m = 0.f;
+      for (int j = threadIdx.x; j < net.W; j += 32) m = fmaxf(m, fabsf(w.wout[j]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (threadIdx.x == 0) s_c = pow2_ceil(m);
+    }
+    __syncthreads();
+  }
+  if (l == net.L && w.fold_out) {
+    // dW_out[n] = sum_k W_{L-1}[n,k] * G[n,k] / (gscale * c): one warp per out-feature n, lanes over k (coalesced reads of
+    // every item's partial row), fixed summation order
+    const int lw = net.L - 1, K = net.W;
+    const int64_t sz = (int64_t)K * net.W;
+    const int n_items = w.item_begin[lw + 1] - w.item_begin[lw];
+    const float* p = partials + w.part_off[lw];
+    const uint8_t* img = w.packed + packed_off(net, lw);      // "bwd" image: [column block][K rows][128 B], swizzled
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < net.Wr; n += warps) {
+      const int cb = n >> 6, j = (n & 63) >> 3;
+      float g[8];            // k = lane + 32 q: eight independent loads per item (K <= 256)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) g[q] = 0.f;
+      for (int it = 0; it < n_items; ++it) {
+        const float* row = p + (int64_t)it * sz + (int64_t)n * K + lane;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (32 * q < K) g[q] += row[32 * q];
+      }
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int k = lane + 32 * q;
+        if (k < K) {
+          const __half wv = *reinterpret_cast<const __half*>(img + (int64_t)cb * K * 128 + (int64_t)k * 128 + ((j ^ (k & 7)) * 16) + (n & 7) * 2);
+          acc = fmaf(__half2float(wv), g[q], acc);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) d_params[param_off(net, net.L) + n] += acc * (inv_gscale / s_c);
+    }
+    return;
+  }
   if (l == net.L) {     // dW_out: one partial [W] per item of layer 0; d_sigma entered unscaled
     const int n_items = w.item_begin[1] - w.item_begin[0];
     const float* p = partials + w.part_off[net.L];
@@ -1251,7 +1333,8 @@ __global__ void wgrad_reduce_kernel(Net net, const float* __restrict__ partials,
     if (n >= net.Wr || k >= Kr) continue;                 // zero-padded part of a 64-wide network
     float s = 0.f;
     for (int g = 0; g < n_items; ++g) s += p[(int64_t)g * sz + i];
-    d_params[param_off(net, l) + (int64_t)n * Kr + k] += s * inv_gscale;
+    const float sc = (w.fold_out && l == net.L - 1) ? inv_gscale * (w.wout[n] / s_c) : inv_gscale;   // fold: the partials are G
+    d_params[param_off(net, l) + (int64_t)n * Kr + k] += s * sc;
   }
 }
 
@@ -1273,7 +1356,7 @@ inline int device_sm_count() {
   return sms;
 }
 
-inline WgradPlan plan_wgrad(const Net& net, bool gen_last) {
+inline WgradPlan plan_wgrad(const Net& net, bool gen_last, bool fold_out) {
   // The kernel is HBM-bound (it streams the A_l and dZ_{l+1} images once): give every layer a share
   // of the SMs proportional to the BYTES it reads per tile, not to its flops.  In 8 KB column blocks per
   // half tile: layer 0 reads A_0 (1) + dZ_1 (nb) + A_L (nb, for dW_out); a middle layer A_l + dZ_{l+1} (2 nb);
@@ -1286,16 +1369,30 @@ inline WgradPlan plan_wgrad(const Net& net, bool gen_last) {
     // (a dZ_L-rebuilding CTA keeps only 3 x 32 KB of loads in flight instead of 3 x 64 KB, so under a saturated HBM it
     // streams at about half the rate of the others: weighted as if it still read dZ_L.  Sweep on a B200, C2, wgrad ms:
     // weight 0.25 nb 3.04, 0.75 nb 2.34, 1.0 nb 2.26, 1.25 nb 2.26, 1.5 nb 2.26)
-    double w = (l == 0 ? 1.0 : (double)net.nb) + (double)net.nb + (l == 0 ? (double)net.nb : 0.0);
-    (void)last;
+    double w = (l == 0 ? 1.0 : (double)net.nb) + (double)net.nb + ((l == 0 && !fold_out) ? (double)net.nb : 0.0);
+    (void)last; (void)gen_last;
     wgt[l] = w;
     total += w;
+  }
+  // shares rounded down, the SMs left over go to the layers with the largest remainders (every SM streams)
+  int cnt[8], sum = 0;
+  double rem[8];
+  for (int l = 0; l < net.L; ++l) {
+    const double share = (double)sms * wgt[l] / total;
+    cnt[l] = (int)share < 1 ? 1 : (int)share;
+    rem[l] = share - (double)cnt[l];
+    sum += cnt[l];
+  }
+  for (; sum < sms; ++sum) {
+    int best = 0;
+    for (int l = 1; l < net.L; ++l) if (rem[l] > rem[best]) best = l;
+    ++cnt[best];
+    rem[best] -= 1.0;
   }
   int used = 0;
   int64_t off = 0;
   for (int l = 0; l < net.L; ++l) {
-    int g = (int)((double)sms * wgt[l] / total);
-    if (g < 1) g = 1;
+    const int g = cnt[l];
     p.item_begin[l] = used;
     p.part_off[l] = off;
     used += g;
@@ -1339,6 +1436,8 @@ static inline int64_t n_tiles(int64_t P) { return (P + kTile - 1) / kTile; }
 static inline int pipe_ctas(const Net& net) { return (net.flags & LONER_NET_SINGLE_CTA) ? 1 : 2; }
 // (a single hidden layer keeps the stash: its one wgrad CTA type already fills its stages with A_0, dZ_1 and A_1)
 static inline bool wgrad_rebuilds_last(const Net& net) { return (net.flags & LONER_NET_STASH_DZL) == 0 && net.L >= 2; }
+// dW_out from layer L-1's partials, no A_L stash (needs the rebuilt dZ_L operand)
+static inline bool wgrad_folds_out(const Net& net) { return wgrad_rebuilds_last(net) && (net.flags & LONER_NET_STASH_AL) == 0; }
 
 // Launch of a pipelined kernel: one CTA per SM, as CTA pairs (clusters of 2 on one TPC) or single CTAs.
 template <class Kern, class Args>
@@ -1372,7 +1471,7 @@ extern "C" int64_t loner_mlp_act_bytes(const loner_net_t* n, int64_t P) {
 extern "C" int64_t loner_mlp_bwd_scratch_bytes(const loner_net_t* n, int64_t P) {
   Net net;
   if (!net_from(n, net) || P < 0) return -1;
-  const WgradPlan p = plan_wgrad(net, wgrad_rebuilds_last(net));
+  const WgradPlan p = plan_wgrad(net, wgrad_rebuilds_last(net), wgrad_folds_out(net));
   return n_tiles(P) * dz_tile_bytes(net) + p.total_floats * 4;
 }
 
@@ -1397,6 +1496,7 @@ extern "C" int loner_mlp_fwd(const loner_net_t* n, const void* packed, const flo
   a.s_shift = (S > 0 && (S & (S - 1)) == 0) ? __builtin_ctz((unsigned)S) : -1;
   a.tiles = n_tiles(P); a.sigma = sigma; a.acts = (uint8_t*)acts;
   a.masks = acts ? (uint8_t*)acts + a.tiles * act_tile_bytes(net) : nullptr;
+  a.stash_last = wgrad_folds_out(net) ? 0 : 1;
   // CTA pairs for the training AND the inference forward: each SM stages half of every weight chunk (half the L2 -> SM
   // stream that bounds the single-CTA inference kernel: 1.35 ms at C2; pairs 1.32 ms since the leader waits on ONE
   // barrier per chunk - with a separate barrier for the peer's half the pair was the slower one, 1.48 ms).
@@ -1467,10 +1567,11 @@ extern "C" int loner_mlp_wgrad(const loner_net_t* n, const void* packed, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* dz = (uint8_t*)scratch;
   float* partials = (float*)(dz + tiles * dz_tile_bytes(net));
-  const WgradPlan plan = plan_wgrad(net, wgrad_rebuilds_last(net));
+  const WgradPlan plan = plan_wgrad(net, wgrad_rebuilds_last(net), wgrad_folds_out(net));
   WgradArgs w;
   w.net = net; w.acts = (const uint8_t*)acts; w.dz = dz; w.tiles = tiles; w.partials = partials;
   w.masks = (const uint8_t*)acts + tiles * act_tile_bytes(net); w.d_sigma = d_sigma; w.gen_last = wgrad_rebuilds_last(net) ? 1 : 0;
+  w.fold_out = wgrad_folds_out(net) ? 1 : 0; w.packed = (const uint8_t*)packed;
   w.wout = reinterpret_cast<const float*>((const uint8_t*)packed + packed_wout_off(net)); w.gscale = grad_scale; w.P = P;
   for (int i = 0; i <= net.L; ++i) w.item_begin[i] = plan.item_begin[i];
   for (int i = 0; i <= net.L + 1; ++i) w.part_off[i] = plan.part_off[i];

@@ -16,9 +16,9 @@ def _f32(t):
     return t.contiguous()
 
 
-NET_SINGLE_CTA, NET_STASH_DZL, NET_ONE_ISSUER, NET_DGRAD_ONE_ISSUER = 1, 2, 32, 64      # LONER_NET_* (include/loner_b200.h)
+NET_SINGLE_CTA, NET_STASH_DZL, NET_ONE_ISSUER, NET_DGRAD_ONE_ISSUER, NET_STASH_AL = 1, 2, 32, 64, 128   # LONER_NET_* (include/loner_b200.h)
 HASH_SCALAR = 1                            # LONER_HASH_*
-DEFAULT_NET_FLAGS = 0                       # production: CTA pairs, dZ_L rebuilt inside wgrad
+DEFAULT_NET_FLAGS = 0                       # production: CTA pairs, dZ_L rebuilt inside wgrad, dW_out folded (no A_L stash)
 
 
 class Net:
@@ -40,6 +40,12 @@ class Net:
 
     def ref(self):
         return ctypes.byref(self.c)
+
+    @property
+    def stashes_last_activation(self):
+        """False when the forward leaves A_L out of the stash: wgrad then derives dW_out from the last hidden layer's
+        weight-gradient partials (mlp.cu `wgrad_folds_out`); the slot stays in the layout, unwritten."""
+        return self.n_hidden_layers < 2 or bool(self.flags & (NET_STASH_DZL | NET_STASH_AL))
 
     def act_bytes(self, P):
         return L.load().loner_mlp_act_bytes(self.ref(), P)

@@ -1,10 +1,11 @@
 """A/B of the kernel variants selected by loner_net_t.flags (not a test): runs tests/gpu_microbench.py in
 sub-processes and prints one line per run.   python tests/gpu_ab.py
 flags: 0 = CTA pairs + dZ_L rebuilt in wgrad + one issuing warp per tile in the training forward (production),
-1 = single CTA, 2 = dZ_L stashed, 3 = round-1 pipeline, 32 = one issuing warp (forward and dgrad), 64 = one issuing warp in dgrad only."""
+1 = single CTA, 2 = dZ_L stashed, 3 = round-1 pipeline, 32 = one issuing warp (forward and dgrad), 64 = one issuing warp in dgrad only,
+128 = A_L stashed and dW_out accumulated from it (no fold)."""
 import json, os, subprocess, sys
 here = os.path.dirname(os.path.abspath(__file__))
-for flags in (0, 32, 64, 1, 2, 3, 64, 32, 0):
+for flags in (0, 128, 32, 1, 2, 3, 128, 0):
     env = dict(os.environ, MB_SHORT="1", MB_FLAGS=str(flags))
     try:
         out = subprocess.run([sys.executable, os.path.join(here, "gpu_microbench.py")], env=env, capture_output=True, text=True,

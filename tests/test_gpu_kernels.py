@@ -99,10 +99,10 @@ def _rand_pos(P, seed):
 
 # kernel variants (loner_net_t.flags): CTA pairs + dZ_L rebuilt inside wgrad, and the round-1 single-CTA pipeline
 VARIANTS = [0, ops.NET_SINGLE_CTA | ops.NET_STASH_DZL, ops.NET_STASH_DZL, ops.NET_SINGLE_CTA, ops.NET_ONE_ISSUER,
-            ops.NET_DGRAD_ONE_ISSUER]
+            ops.NET_DGRAD_ONE_ISSUER, ops.NET_STASH_AL, ops.NET_STASH_AL | ops.NET_SINGLE_CTA]
 
 
-@pytest.mark.parametrize("flags", [VARIANTS[0], VARIANTS[1], VARIANTS[4]])
+@pytest.mark.parametrize("flags", [VARIANTS[0], VARIANTS[1], VARIANTS[4], VARIANTS[6]])
 @pytest.mark.parametrize("W,L,P", [(256, 4, 1000), (128, 2, 640), (256, 1, 128), (256, 4, 128 * 7 + 5), (64, 2, 300)])
 def test_mlp_forward_layers(W, L, P, flags):
     spec = orc.NetSpec(n_frequencies=10, n_neurons=W, n_hidden_layers=L, precision="fp16")
@@ -126,7 +126,7 @@ def test_mlp_forward_layers(W, L, P, flags):
         blob = acts[t * tile_bytes:(t + 1) * tile_bytes]
         a0 = decode_image(blob[:16384], 1)[: hi - lo]
         worst["enc"] = max(worst.get("enc", 0), float((a0 - enc[lo:hi].half().float()).abs().max()))
-        for l in range(L):
+        for l in range(L if net.stashes_last_activation else L - 1):      # A_L is not stashed when dW_out is folded
             al = decode_image(blob[16384 + l * nb * 16384: 16384 + (l + 1) * nb * 16384], nb)[: hi - lo]
             assert not al[:, W:].any()        # padded neurons stay exactly zero
             al = al[:, :W]
