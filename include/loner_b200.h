@@ -102,6 +102,8 @@ typedef struct {
 /* the forward stashes A_L too and wgrad accumulates dW_out from it, instead of deriving dW_out from the last hidden
  * layer's weight-gradient partials (no biases: A_L = mask_L * (A_{L-1} W_{L-1}^T)) */
 #define LONER_NET_STASH_AL 128
+/* wgrad gives layer 0 a share of the CTAs in proportion to the bytes it streams, instead of bytes per byte in flight */
+#define LONER_NET_WG_PLAN_BYTES 256
 
 int64_t loner_mlp_param_count(const loner_net_t* net);       /* flat fp32 params, [out,in] row-major per layer */
 int64_t loner_mlp_packed_bytes(const loner_net_t* net);      /* fp16 tensor-core image of the params */

@@ -1278,42 +1278,7 @@ __global__ void wgrad_reduce_kernel(Net net, const float* __restrict__ partials,
     }
     __syncthreads();
   }
-  if (l == net.L && w.fold_out) {
-    // dW_out[n] = sum_k W_{L-1}[n,k] * G[n,k] / (gscale * c): one warp per out-feature n, lanes over k (coalesced reads of
-    // every item's partial row), fixed summation order
-    const int lw = net.L - 1, K = net.W;
-    const int64_t sz = (int64_t)K * net.W;
-    const int n_items = w.item_begin[lw + 1] - w.item_begin[lw];
-    const float* p = partials + w.part_off[lw];
-    const uint8_t* img = w.packed + packed_off(net, lw);      // "bwd" image: [column block][K rows][128 B], swizzled
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < net.Wr; n += warps) {
-      const int cb = n >> 6, j = (n & 63) >> 3;
-      float g[8];            // k = lane + 32 q: eight independent loads per item (K <= 256)
-#pragma unroll
-      for (int q = 0; q < 8; ++q) g[q] = 0.f;
-      for (int it = 0; it < n_items; ++it) {
-        const float* row = p + (int64_t)it * sz + (int64_t)n * K + lane;
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (32 * q < K) g[q] += row[32 * q];
-      }
-      float acc = 0.f;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int k = lane + 32 * q;
-        if (k < K) {
-          const __half wv = *reinterpret_cast<const __half*>(img + (int64_t)cb * K * 128 + (int64_t)k * 128 + ((j ^ (k & 7)) * 16) + (n & 7) * 2);
-          acc = fmaf(__half2float(wv), g[q], acc);
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) d_params[param_off(net, net.L) + n] += acc * (inv_gscale / s_c);
-    }
-    return;
-  }
+  if (l == net.L && w.fold_out) return;     // dW_out is finished by the blocks of layer L-1 (below)
   if (l == net.L) {     // dW_out: one partial [W] per item of layer 0; d_sigma entered unscaled
     const int n_items = w.item_begin[1] - w.item_begin[0];
     const float* p = partials + w.part_off[net.L];
@@ -1325,16 +1290,47 @@ __global__ void wgrad_reduce_kernel(Net net, const float* __restrict__ partials,
     return;
   }
   const int K = layer_K(net, l), Kr = layer_Kr(net, l);
-  const int64_t sz = (int64_t)K * net.W;
+  const int64_t sz = (int64_t)K * net.W;          // a multiple of 2048: every thread of a block runs the same trips
   const int n_items = w.item_begin[l + 1] - w.item_begin[l];
   const float* p = partials + w.part_off[l];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sz; i += (int64_t)gridDim.x * blockDim.x) {
+  // fold (layer L-1, K = W): the summed partial is G[n,k];  dW_{L-1}[n,k] = w_out[n] G[n,k] / (gscale c)  and
+  // dW_out[n] = sum_k W_{L-1}[n,k] G[n,k] / (gscale c) - a block covers 256 / K whole rows n per trip, reduced in a fixed
+  // order (warp shuffles, then the row's K / 32 warp sums): one writer per n, no atomics, nothing read twice
+  const bool fold_l = w.fold_out && l == net.L - 1;
+  const uint8_t* img = w.packed + packed_off(net, l);      // "bwd" image: [column block][K rows][128 B], swizzled
+  __shared__ float s_red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < sz; i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + threadIdx.x;
     const int n = (int)(i / K), k = (int)(i % K);         // partials are [out n][in k] at the kernel width
-    if (n >= net.Wr || k >= Kr) continue;                 // zero-padded part of a 64-wide network
+    const bool real = n < net.Wr && k < Kr;               // not the zero-padded part of a 64-wide network
     float s = 0.f;
-    for (int g = 0; g < n_items; ++g) s += p[(int64_t)g * sz + i];
-    const float sc = (w.fold_out && l == net.L - 1) ? inv_gscale * (w.wout[n] / s_c) : inv_gscale;   // fold: the partials are G
-    d_params[param_off(net, l) + (int64_t)n * Kr + k] += s * sc;
+    if (real) {
+#pragma unroll 8
+      for (int g = 0; g < n_items; ++g) s += p[(int64_t)g * sz + i];
+      const float sc = fold_l ? inv_gscale * (w.wout[n] / s_c) : inv_gscale;
+      d_params[param_off(net, l) + (int64_t)n * Kr + k] += s * sc;
+    }
+    if (fold_l) {
+      float v = 0.f;
+      if (real) {
+        const int cb = n >> 6, j = (n & 63) >> 3;
+        const __half wv = *reinterpret_cast<const __half*>(img + (int64_t)cb * K * 128 + (int64_t)k * 128 + ((j ^ (k & 7)) * 16) + (n & 7) * 2);
+        v = __half2float(wv) * s;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_red[warp] = v;
+      __syncthreads();
+      const int wpr = K >> 5;                               // warps per row n (K = 128 or 256; blockDim.x = 256)
+      if ((int)threadIdx.x < 256 / K) {
+        const int nr = (int)(i0 / K) + (int)threadIdx.x;
+        float t = 0.f;
+        for (int q = 0; q < wpr; ++q) t += s_red[threadIdx.x * wpr + q];
+        if (nr < net.Wr) d_params[param_off(net, net.L) + nr] += t * (inv_gscale / s_c);
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -1370,6 +1366,10 @@ inline WgradPlan plan_wgrad(const Net& net, bool gen_last, bool fold_out) {
     // streams at about half the rate of the others: weighted as if it still read dZ_L.  Sweep on a B200, C2, wgrad ms:
     // weight 0.25 nb 3.04, 0.75 nb 2.34, 1.0 nb 2.26, 1.25 nb 2.26, 1.5 nb 2.26)
     double w = (l == 0 ? 1.0 : (double)net.nb) + (double)net.nb + ((l == 0 && !fold_out) ? (double)net.nb : 0.0);
+    // Same rule for layer 0 once it no longer streams A_L (fold): its stages hold 8 + 32 KB instead of 64 KB, so a CTA keeps
+    // 120 KB in flight where a middle layer's keeps 192 KB, and needs a share in proportion to bytes per byte in flight:
+    // (1 + nb) / 120 = 2 nb / 192 for nb = 4.  LONER_NET_WG_PLAN_BYTES keeps the share proportional to bytes (A/B).
+    if (l == 0 && fold_out && !(net.flags & LONER_NET_WG_PLAN_BYTES)) w = 2.0 * (double)net.nb;
     (void)last; (void)gen_last;
     wgt[l] = w;
     total += w;

@@ -16,7 +16,7 @@ def _f32(t):
     return t.contiguous()
 
 
-NET_SINGLE_CTA, NET_STASH_DZL, NET_ONE_ISSUER, NET_DGRAD_ONE_ISSUER, NET_STASH_AL = 1, 2, 32, 64, 128   # LONER_NET_* (include/loner_b200.h)
+NET_SINGLE_CTA, NET_STASH_DZL, NET_ONE_ISSUER, NET_DGRAD_ONE_ISSUER, NET_STASH_AL, NET_WG_PLAN_BYTES = 1, 2, 32, 64, 128, 256   # LONER_NET_*
 HASH_SCALAR = 1                            # LONER_HASH_*
 DEFAULT_NET_FLAGS = 0                       # production: CTA pairs, dZ_L rebuilt inside wgrad, dW_out folded (no A_L stash)
 

@@ -5,7 +5,6 @@ tag=${1:-r2f}
 mkdir -p gpurun_out
 (timeout 300 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_pytest.log)
 grep -E "^FAILED|^ERROR|passed|failed|rc=" gpurun_out/${tag}_pytest.log | tail -12
-(timeout 120 python __graft_entry__.py --smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_smoke.log); tail -2 gpurun_out/${tag}_smoke.log
 (timeout 150 python tests/gpu_ab.py > gpurun_out/${tag}_ab.jsonl 2>&1); cat gpurun_out/${tag}_ab.jsonl
 (timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/${tag}_bench_c2.json 2> gpurun_out/${tag}_bench_c2.err)
 python - <<PY
@@ -16,8 +15,9 @@ try:
 except Exception as ex:
     print("bench line unreadable:", ex)
 PY
-(MB_N=8192 timeout 400 ncu --set full --clock-control none --profile-from-start off \
-   -k regex:'^(mlp_|wgrad_)' -o gpurun_out/${tag}_prof python tests/gpu_profile_target.py > gpurun_out/${tag}_ncu.log 2>&1)
+(timeout 120 python __graft_entry__.py --smoke > gpurun_out/${tag}_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/${tag}_smoke.log); tail -2 gpurun_out/${tag}_smoke.log
+(MB_N=8192 timeout ${NCU_T:-400} ncu --set full --clock-control none --profile-from-start off \
+   -k regex:"${NCU_K:-^(mlp_|wgrad_)}" -o gpurun_out/${tag}_prof python tests/gpu_profile_target.py > gpurun_out/${tag}_ncu.log 2>&1)
 ncu -i gpurun_out/${tag}_prof.ncu-rep --page raw --csv 2>/dev/null | python profiles/summarize_ncu.py > gpurun_out/${tag}_ncu_summary.csv
 [ -f gpurun_out/${tag}_prof.ncu-rep ] && [ $(stat -c %s gpurun_out/${tag}_prof.ncu-rep) -gt 30000000 ] && rm -f gpurun_out/${tag}_prof.ncu-rep
 cut -d, -f1-8 gpurun_out/${tag}_ncu_summary.csv | head -12

@@ -17,7 +17,7 @@ def test_algorithmic_flops_match_the_survey():
 
 def test_ncu_summary_is_readable_and_plausible():
     # C2-sized launches: stash / dZ / stash+dZ bytes; the upper bounds are round 1's design, round 2 moves less
-    for kern, lo, hi in (("mlp_fwd", 8e9, 11e9), ("mlp_dgrad", 5e9, 10e9), ("mlp_wgrad", 9e9, 16.5e9)):
+    for kern, lo, hi in (("mlp_fwd", 6.5e9, 11e9), ("mlp_dgrad", 5e9, 10e9), ("mlp_wgrad", 9e9, 16.5e9)):   # fwd: 7.5 GB since A_L left the stash
         t, src = bench.ncu_traffic_bytes(kern)
         assert t is not None and src.startswith("profiles/") and lo < t < hi, (kern, t)
 

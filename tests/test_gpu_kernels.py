@@ -99,7 +99,7 @@ def _rand_pos(P, seed):
 
 # kernel variants (loner_net_t.flags): CTA pairs + dZ_L rebuilt inside wgrad, and the round-1 single-CTA pipeline
 VARIANTS = [0, ops.NET_SINGLE_CTA | ops.NET_STASH_DZL, ops.NET_STASH_DZL, ops.NET_SINGLE_CTA, ops.NET_ONE_ISSUER,
-            ops.NET_DGRAD_ONE_ISSUER, ops.NET_STASH_AL, ops.NET_STASH_AL | ops.NET_SINGLE_CTA]
+            ops.NET_DGRAD_ONE_ISSUER, ops.NET_STASH_AL, ops.NET_STASH_AL | ops.NET_SINGLE_CTA, ops.NET_WG_PLAN_BYTES]
 
 
 @pytest.mark.parametrize("flags", [VARIANTS[0], VARIANTS[1], VARIANTS[4], VARIANTS[6]])
