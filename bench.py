@@ -153,7 +153,7 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-NCU_SUMMARY = ("profiles/r2f_ncu_summary.csv", "profiles/r2_ncu_summary.csv", "profiles/r1_ncu_summary.csv")
+NCU_SUMMARY = ("profiles/r2g_ncu_summary.csv", "profiles/r2f_ncu_summary.csv", "profiles/r2_ncu_summary.csv", "profiles/r1_ncu_summary.csv")
 
 
 def ncu_traffic_bytes(kernel_substr, stash=True):
