@@ -115,7 +115,8 @@ int loner_mlp_pack(const loner_net_t* net, const float* params, void* packed, vo
 
 /* forward.  Either pos [P,3] in [-1,1] (DecoupledNeRF.forward API) or, when pos == NULL,
  * rays [n,13] + z_vals [n,S] with P = n*S (points o + d*z are formed in registers, never stored).
- * sigma [P] fp32.  acts: NULL (inference) or the activation stash consumed by loner_mlp_bwd. */
+ * sigma [P] fp32.  acts: NULL (inference) or the activation stash consumed by loner_mlp_bwd (opaque: what it holds
+ * depends on net->flags - e.g. A_L only with LONER_NET_STASH_AL - so forward and backward take the same loner_net_t). */
 int loner_mlp_fwd(const loner_net_t* net, const void* packed, const float* pos, const float* rays,
                   const float* z_vals, int32_t S, int64_t P, float* sigma, void* acts, void* stream);
 

@@ -133,8 +133,8 @@ __global__ void pack_kernel(Net net, const float* __restrict__ params, uint8_t* 
 // ------------------------------------------------------------------------------------------
 // Shared pieces of the two pipelined kernels (forward, dgrad).
 //
-// One CTA per SM, 320 threads:  warp 0 = weight producer (bulk copies into a 3-slot ring),
-// warp 1 = MMA issuer, warps 2-9 = epilogue (two warps per TMEM lane quarter, each owning half of the
+// One CTA per SM, 320 threads (352 with a second issuing warp, warp 10):  warp 0 = weight producer (bulk copies into a
+// 3-slot ring), warp 1 = MMA issuer, warps 2-9 = epilogue (two warps per TMEM lane quarter, each owning half of the
 // columns).  Two tiles of 128 samples are in flight with one 256-column TMEM accumulator each; inside
 // a layer the MMAs of tile X (all K chunks) are followed by those of tile Y, and all eight epilogue
 // warps drain X, then Y, so X's epilogue has the whole of Y's tensor time to finish (and vice versa).
@@ -146,9 +146,11 @@ __global__ void pack_kernel(Net net, const float* __restrict__ params, uint8_t* 
 //    (tests/gpu_probe.py: 8 warps reach 99 / 140 B/clk with one / two 4 KB loads in flight);
 //  * no local memory at all (tables are address computations or live in shared memory): behind a
 //    saturated HBM a local load misses the 28 KB L1 and stalls its warp for microseconds;
-//  * the weight chunks are fetched once per TILE (sharing them between the tiles of a pair - issue order
-//    X[c0,c1] Y[c0,c1] X[c2,c3] Y[c2,c3] - halves the L2->SM traffic, but then a tile's epilogue overlaps only a
-//    quarter of the other tile's tensor work: measured slower in training, equal in inference, round 1);
+//  * with ONE issuing warp the weight chunks are fetched once per TILE (sharing them between the tiles of a pair from one
+//    issuer - issue order X[c0,c1] Y[c0,c1] X[c2,c3] Y[c2,c3] - halves the L2->SM traffic, but then a tile's epilogue
+//    overlaps only a quarter of the other tile's tensor work: measured slower in training, equal in inference, round 1);
+//    the training forward and dgrad of CTA pairs run with one issuing warp PER TILE (kIss = 2, below), which shares the
+//    chunks without that coupling;
 //  * as CTA PAIRS (cta_group::2, kCtas = 2: training forward and dgrad) each SM stages half of every weight
 //    chunk and one M = 256 MMA covers a tile of each CTA: -64 KB of operand reads and -64 KB of ring writes per
 //    tile and layer in each SM's shared-memory pipe, half the weight re-streaming through the L2 fabric;
