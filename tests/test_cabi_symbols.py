@@ -36,3 +36,25 @@ def test_no_compute_entry_points_need_a_gpu_to_query_sizes():
     bad = lib.NetT(10, 96, 1, 0)
     assert l.loner_mlp_param_count(ctypes.byref(bad)) == -1
     assert l.loner_error_string(2).decode().startswith("configuration not supported")
+
+
+def test_wgrad_plan_shares_every_sm_between_the_layers():
+    """loner_mlp_bwd_scratch_bytes = dZ stash + one fp32 partial per wgrad CTA (mlp.cu plan_wgrad; 148 SMs on a B200 and in
+    the no-GPU fallback): the CTA counts per layer follow from it.  4 x 256, E_pad = 64."""
+    l = lib.load()
+    P = 8192 * 512
+    dz = (P // 128) * 16384 * 4 * 4                       # L * nb column-block images of 16 KB per tile
+
+    def partial_floats(flags):
+        net = lib.NetT(10, 256, 4, flags)
+        return (l.loner_mlp_bwd_scratch_bytes(ctypes.byref(net), P) - dz) // 4
+
+    def floats(c0, c_rest):                               # layer 0: [W x E_pad] (+ a dW_out row), others [W x W]
+        return c0 * 64 * 256 + c_rest * 256 * 256 + c0 * 256
+
+    assert partial_floats(0) == floats(37, 3 * 37)        # fold: equal shares (bytes per byte in flight)
+    assert partial_floats(256) == floats(25, 3 * 41)      # LONER_NET_WG_PLAN_BYTES: 5 : 8 : 8 : 8
+    assert partial_floats(128) == floats(40, 3 * 36)      # LONER_NET_STASH_AL: layer 0 also streams A_L, 9 : 8 : 8 : 8
+    for flags in (0, 128, 256):                            # the stash layout itself does not depend on the variant
+        net = lib.NetT(10, 256, 4, flags)
+        assert l.loner_mlp_act_bytes(ctypes.byref(net), P) == (P // 128) * (16384 * 17 + 4 * 128 * 8 * 4)
